@@ -1,0 +1,169 @@
+/*
+ * refign_b200.h -- C ABI of librefign_b200.so (sm_100a kernels for the Refign
+ * per-training-step hot path).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer into memory owned by the caller
+ *     (the Python host allocates torch tensors and passes .data_ptr());
+ *   - tensors are dense, contiguous, row-major in the layout stated per call;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - calls are asynchronous with respect to the host and re-entrant per stream;
+ *   - return value: 0 on success, negative RF_E* on failure; the message of the
+ *     last failure on the calling thread is returned by rf_last_error();
+ *   - no torch types, no global state besides per-process cached attributes.
+ *
+ * The reference has no C ABI of its own: its only native boundary is the
+ * pybind11 module `correlation` (forward/backward) in
+ *   /root/reference/models/correlation_ops/correlation_sampler.cpp:62-132
+ * reached through
+ *   /root/reference/models/correlation_ops/correlation_function.py:14-94
+ * and tried-first as `spatial_correlation_sampler.spatial_correlation_sample`
+ *   /root/reference/models/modules.py:252-262.
+ * Each entry point below cites the reference interface it replaces.
+ */
+#ifndef REFIGN_B200_H_
+#define REFIGN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RF_OK 0
+#define RF_EINVAL (-1)   /* bad argument / unsupported shape            */
+#define RF_ECUDA (-2)    /* CUDA runtime / launch error                  */
+#define RF_ENODEV (-3)   /* no sm_100 device                             */
+
+/* ---- library ---------------------------------------------------------- */
+const char* rf_last_error(void);
+int rf_version(void);                 /* ABI version, currently 1         */
+int rf_device_check(void);            /* RF_OK iff current device is sm_100 */
+
+/* ---- local (windowed) correlation ------------------------------------- */
+/* Replaces correlation.forward (correlation_sampler.cpp:62-90 ->
+ * correlation_cuda_kernel.cu:241-278; CPU twin correlation.cpp:80-129).
+ *   in1,in2 : f32 [B,C,H,W]      out : f32 [B,pH,pW,oH,oW]
+ *   oH = (H + 2*padH - ((kH-1)*dilH + 1)) / sH + 1   (likewise oW)
+ * Terms whose shifted coordinate falls outside the image contribute 0.
+ * Every element of `out` is written (no pre-zeroing needed).
+ * fuse_relu_l2norm != 0 additionally applies
+ * LocalFeatureCorrelationLayer's  F.normalize(F.relu(.), dim=1) over the
+ * pH*pW displacement channels (models/modules.py:271-273); requires kH=kW=1,
+ * stride 1, pad 0, dilation_patch 1.  norm_out (f32 [B,oH,oW], may be NULL)
+ * then receives max(||relu(c)||_2, 1e-12) per pixel for the backward. */
+int rf_local_corr_fwd(const float* in1, const float* in2, float* out, float* norm_out,
+                      int B, int C, int H, int W,
+                      int kH, int kW, int pH, int pW, int padH, int padW,
+                      int dilH, int dilW, int dpH, int dpW, int sH, int sW,
+                      int fuse_relu_l2norm, void* stream);
+
+/* Replaces correlation.backward (correlation_sampler.cpp:92-127 ->
+ * correlation_cuda_kernel.cu:280-332; CPU twin correlation.cpp:131-183).
+ *   grad_out : f32 [B,pH,pW,oH,oW]   grad_in1, grad_in2 : f32 [B,C,H,W]
+ * Both gradients are fully written.  scratch: caller-provided f32 buffer of
+ * rf_local_corr_bwd_scratch_bytes() bytes (may be NULL if that is 0). */
+int64_t rf_local_corr_bwd_scratch_bytes(int B, int C, int H, int W, int kH, int kW,
+                                        int pH, int pW, int padH, int padW, int dilH,
+                                        int dilW, int dpH, int dpW, int sH, int sW);
+int rf_local_corr_bwd(const float* in1, const float* in2, const float* grad_out,
+                      float* grad_in1, float* grad_in2, void* scratch,
+                      int B, int C, int H, int W,
+                      int kH, int kW, int pH, int pW, int padH, int padW,
+                      int dilH, int dilW, int dpH, int dpW, int sH, int sW,
+                      void* stream);
+
+/* Backward of the fused ReLU + L2-norm epilogue: given y = normalize(relu(c))
+ * (the forward output, [B,K,HW]) and dL/dy, writes dL/dc into grad_c.
+ * Positions where the norm was clamped (all-zero vectors) get zero gradient
+ * scaled by 1/eps exactly as autograd of F.normalize does for the reference
+ * (models/modules.py:273). norm: f32 [B,HW] as saved by the forward. */
+int rf_relu_l2norm_bwd(const float* y, const float* norm, const float* grad_y,
+                       float* grad_c, int B, int K, int64_t HW, void* stream);
+
+/* ---- global correlation ----------------------------------------------- */
+/* Replaces GlobalFeatureCorrelationLayer.forward (models/modules.py:294-308:
+ * torch.bmm :362-374, mutual_matching :310-333, relu + normalize :307).
+ *   src : f32 [B,C,Ns]   trg : f32 [B,C,Nt]   out : f32 [B,Ns,Nt]
+ *   out[b,s,t] = <src[b,:,s], trg[b,:,t]>, source index row-major (h_s,w_s).
+ *   mode bit0: mutual matching (eps 1e-5); bit1: relu + L2-norm over s.
+ *   workspace: f32 [B*(Ns+2*Nt)] scratch for the row/column maxima and norms.
+ *   use_tensor_cores: 1 = tcgen05 TF32 path (needs C%32==0, Ns,Nt%128==0),
+ *                     0 = fp32 FFMA path, -1 = pick automatically. */
+int64_t rf_global_corr_workspace_bytes(int B, int64_t Ns, int64_t Nt);
+int rf_global_corr_fwd(const float* src, const float* trg, float* out, void* workspace,
+                       int B, int C, int64_t Ns, int64_t Nt, int mode,
+                       int use_tensor_cores, void* stream);
+
+/* ---- bilinear warp ---------------------------------------------------- */
+/* Replaces helpers.matching_utils.warp (matching_utils.py:11-49) for
+ * padding_mode='zeros': sample x at (col + flow_x, row + flow_y) with
+ * grid_sample(bilinear, zeros, align_corners=True) arithmetic in fp32, and the
+ * strict-inside validity mask of :45-47.  No host synchronisation: the
+ * reference's `torch.all(flo == 0)` early exit (:19-22) is replaced by the
+ * device-side flag `all_zero_flag` (int32, may be NULL): when non-NULL the
+ * kernel reads *all_zero_flag (1 = flow identically zero, as computed by
+ * rf_flow_is_zero) and then copies x and sets the mask to all-true.
+ *   x : f32 [B,C,H,W]  flow : f32 [B,2,H,W]  out : f32 [B,C,H,W]
+ *   mask : u8 [B,H,W] or NULL */
+int rf_flow_is_zero(const float* flow, int64_t n, int32_t* flag, void* stream);
+int rf_warp_bilinear_fwd(const float* x, const float* flow, float* out, uint8_t* mask,
+                         const int32_t* all_zero_flag, int B, int C, int H, int W,
+                         void* stream);
+/* Gradients of the above wrt x (scatter-add; grad_x must be zero-filled by the
+ * caller) and wrt flow (may be NULL). */
+int rf_warp_bilinear_bwd(const float* x, const float* flow, const float* grad_out,
+                         float* grad_x, float* grad_flow, const int32_t* all_zero_flag,
+                         int B, int C, int H, int W, void* stream);
+
+/* ---- confidence + label refinement ------------------------------------ */
+/* Replaces estimate_probability_of_confidence_interval_of_mixture_density
+ * (matching_utils.py:52-57), R = 1:  cert = 1 - exp(-1 / (2 exp(logvar))). */
+int rf_cert_fwd(const float* logvar, float* cert, int64_t n, void* stream);
+
+/* Replaces DomainAdaptationSegmentationModel.refine + eta
+ * (models/segmentation_model.py:438-491) and the torch.max of
+ * get_dacs_mix (:551).
+ *   logits_trg, logits_ref : f32 [B,K,H*W]  (K <= 32; Refign: 19)
+ *   certs  : f32 [B,H*W] confidence P_R, or NULL
+ *   logvar : f32 [B,H*W] log-variance (P_R computed in-kernel), or NULL;
+ *            certs == logvar == NULL  =>  P = 0.5  (:472-473)
+ *   warp_mask : u8 [B,H*W] or NULL
+ *   ent_fix : i64 [B] scratch (2^-40 fixed-point entropy sums), trust : f32 [B] out
+ *   probs_out : f32 [B,K,H*W];  label_out : i64 [B,H*W] or NULL;
+ *   maxprob_out : f32 [B,H*W] or NULL
+ *   static_mask : bit k set iff class k is in the static-large set S (:452)
+ *   flags bit0 = disable_M, bit1 = disable_P
+ * Integer outputs are bit-exact w.r.t. oracle/refign_oracle.c by construction
+ * (same IEEE operation sequence, order-independent fixed-point reduction). */
+int rf_refine_fwd(const float* logits_trg, const float* logits_ref, const float* certs,
+                  const float* logvar, const uint8_t* warp_mask, int64_t* ent_fix,
+                  float* trust, float* probs_out, int64_t* label_out, float* maxprob_out,
+                  int B, int K, int64_t HW, float gamma, uint64_t static_mask, int flags,
+                  void* stream);
+
+/* ---- optimiser-side multi-tensor ops on flat buffers ------------------- */
+/* Replaces update_momentum_encoder (segmentation_model.py:680-689):
+ *   ema = ema*m + live*(1-m)   over one flat f32 buffer.  momentum is a double
+ * because the reference forms (1. - m) in Python double precision before the
+ * tensor multiply rounds it to binary32; both factors are rounded here the same
+ * way so the update is bit-identical to the reference's. */
+int rf_ema_update(float* ema, const float* live, int64_t n, double momentum, void* stream);
+
+/* AdamW step (torch.optim.AdamW semantics: decoupled weight decay, bias
+ * correction) over flat f32 buffers split into `nseg` contiguous segments with
+ * their own lr / weight_decay -- the four param groups of
+ * segmentation_model.py:390-419.  seg_end[i] = exclusive end offset.
+ * seg_end / seg_lr / seg_wd are small HOST arrays (nseg <= 8), copied into the
+ * kernel arguments -- the one exception to the device-pointer convention.
+ * grad_scale multiplies the gradient first (1/world_size for a summed
+ * all-reduce). */
+int rf_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                  int64_t n, int nseg, const int64_t* seg_end, const float* seg_lr,
+                  const float* seg_wd, float beta1, float beta2, float eps, int step,
+                  float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REFIGN_B200_H_ */

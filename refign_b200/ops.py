@@ -1,0 +1,312 @@
+"""Host-side operators over the C-ABI (include/refign_b200.h).
+
+Each function mirrors the reference operator it replaces (same name, argument
+meaning and error behaviour) and launches the sm_100a kernel on torch's current
+stream.  Tensors are allocated by torch; only raw pointers cross the boundary.
+CUDA only -- no CPU implementation, no fallback.
+"""
+import ctypes
+
+import torch
+from torch.nn.modules.utils import _pair
+
+from . import _lib
+from ._lib import check, ptr, require_cuda
+
+STATIC_LARGE_CLASSES = (0, 1, 2, 3, 4, 8, 9, 10)  # reference segmentation_model.py:452
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32c(t):
+    return t.contiguous() if t.dtype == torch.float32 else t.float().contiguous()
+
+
+# --------------------------------------------------------------------------
+# local correlation (reference: models/correlation_ops/correlation_function.py)
+# --------------------------------------------------------------------------
+def _corr_out_size(H, W, k, pad, dil, s):
+    oH = (H + 2 * pad[0] - ((k[0] - 1) * dil[0] + 1)) // s[0] + 1
+    oW = (W + 2 * pad[1] - ((k[1] - 1) * dil[1] + 1)) // s[1] + 1
+    return oH, oW
+
+
+def _check_pair(input1, input2):
+    if input1.dim() != 4 or input2.dim() != 4:
+        raise RuntimeError("spatial_correlation_sample expects 4-D [B,C,H,W] inputs")
+    if input1.shape != input2.shape:
+        raise RuntimeError("input1 %s and input2 %s must have the same shape"
+                           % (tuple(input1.shape), tuple(input2.shape)))
+    require_cuda(input1, input2)
+    if input1.device != input2.device:
+        raise RuntimeError("inputs must live on the same device")
+
+
+class SpatialCorrelationSamplerFunction(torch.autograd.Function):
+    """Same contract as the reference's autograd function
+    (correlation_function.py:46-94): fp32 even under autocast, output
+    [B, patchH, patchW, oH, oW], differentiable w.r.t. both inputs."""
+
+    @staticmethod
+    def forward(ctx, input1, input2, kernel_size=1, patch_size=1, stride=1, padding=0,
+                dilation=1, dilation_patch=1):
+        _check_pair(input1, input2)
+        a, b = _f32c(input1), _f32c(input2)
+        k, p, s, pad, dil, dp = map(_pair, (kernel_size, patch_size, stride, padding, dilation,
+                                            dilation_patch))
+        B, C, H, W = a.shape
+        oH, oW = _corr_out_size(H, W, k, pad, dil, s)
+        if min(B, C, oH, oW) <= 0:
+            raise RuntimeError("spatial_correlation_sample: empty input/output (%s)" % (tuple(a.shape),))
+        out = torch.empty(B, p[0], p[1], oH, oW, device=a.device, dtype=torch.float32)
+        ctx.geom = (k, p, s, pad, dil, dp)
+        ctx.in_dtypes = (input1.dtype, input2.dtype)
+        ctx.save_for_backward(a, b)
+        with torch.cuda.device(a.device):
+            check(_lib.lib().rf_local_corr_fwd(ptr(a), ptr(b), ptr(out), None, B, C, H, W, k[0], k[1], p[0],
+                                               p[1], pad[0], pad[1], dil[0], dil[1], dp[0], dp[1], s[0],
+                                               s[1], 0, _stream()), "rf_local_corr_fwd")
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_output):
+        a, b = ctx.saved_tensors
+        k, p, s, pad, dil, dp = ctx.geom
+        B, C, H, W = a.shape
+        g = _f32c(grad_output)
+        ga = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        gb = torch.empty_like(b) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(a.device):
+            check(_lib.lib().rf_local_corr_bwd(ptr(a), ptr(b), ptr(g), ptr(ga), ptr(gb), None, B, C, H, W, k[0],
+                                               k[1], p[0], p[1], pad[0], pad[1], dil[0], dil[1], dp[0],
+                                               dp[1], s[0], s[1], _stream()), "rf_local_corr_bwd")
+        if ga is not None:
+            ga = ga.to(ctx.in_dtypes[0])
+        if gb is not None:
+            gb = gb.to(ctx.in_dtypes[1])
+        return ga, gb, None, None, None, None, None, None
+
+
+def spatial_correlation_sample(input1, input2, kernel_size=1, patch_size=1, stride=1, padding=0,
+                               dilation=1, dilation_patch=1):
+    """Drop-in for ``spatial_correlation_sampler.spatial_correlation_sample`` /
+    the reference's own wrapper (correlation_function.py:14-43)."""
+    return SpatialCorrelationSamplerFunction.apply(input1, input2, kernel_size, patch_size, stride,
+                                                   padding, dilation, dilation_patch)
+
+
+class _LocalCorrReluL2Norm(torch.autograd.Function):
+    """correlation (target centre, source searched) + view [B,P*P,H,W] + ReLU +
+    L2-norm fused in one kernel (reference models/modules.py:266-274)."""
+
+    @staticmethod
+    def forward(ctx, feature_source, feature_target, patch_size):
+        _check_pair(feature_target, feature_source)
+        t, s = _f32c(feature_target), _f32c(feature_source)
+        B, C, H, W = t.shape
+        P = int(patch_size)
+        out = torch.empty(B, P * P, H, W, device=t.device, dtype=torch.float32)
+        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        norm = torch.empty(B, H, W, device=t.device, dtype=torch.float32) if need_grad else None
+        with torch.cuda.device(t.device):
+            check(_lib.lib().rf_local_corr_fwd(ptr(t), ptr(s), ptr(out), ptr(norm), B, C, H, W, 1, 1, P, P, 0, 0,
+                                               1, 1, 1, 1, 1, 1, 1, _stream()), "rf_local_corr_fwd")
+        if need_grad:
+            ctx.save_for_backward(t, s, out, norm)
+            ctx.P = P
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        t, s, y, norm = ctx.saved_tensors
+        P = ctx.P
+        B, C, H, W = t.shape
+        gy = _f32c(grad_out)
+        gc = torch.empty_like(y)
+        L = _lib.lib()
+        with torch.cuda.device(t.device):
+            check(L.rf_relu_l2norm_bwd(ptr(y), ptr(norm), ptr(gy), ptr(gc), B, P * P, H * W, _stream()),
+                  "rf_relu_l2norm_bwd")
+            gt = torch.empty_like(t) if ctx.needs_input_grad[1] else None
+            gs = torch.empty_like(s) if ctx.needs_input_grad[0] else None
+            check(L.rf_local_corr_bwd(ptr(t), ptr(s), ptr(gc), ptr(gt), ptr(gs), None, B, C, H, W, 1, 1, P, P, 0,
+                                      0, 1, 1, 1, 1, 1, 1, _stream()), "rf_local_corr_bwd")
+        return gs, gt, None
+
+
+def local_correlation_relu_l2norm(feature_source, feature_target, patch_size=9):
+    return _LocalCorrReluL2Norm.apply(feature_source, feature_target, patch_size)
+
+
+# --------------------------------------------------------------------------
+# global correlation (reference: models/modules.py:294-392)
+# --------------------------------------------------------------------------
+def global_correlation(feature_source, feature_target, cyclic_consistency=True, normalise=True,
+                       use_tensor_cores=-1):
+    """GlobalFeatureCorrelationLayer.forward: [B,C,Hs,Ws],[B,C,Ht,Wt] -> [B,Hs*Ws,Ht,Wt]."""
+    require_cuda(feature_source, feature_target)
+    if feature_source.requires_grad or feature_target.requires_grad:
+        if torch.is_grad_enabled():
+            raise NotImplementedError("global_correlation: backward is not implemented (the alignment "
+                                      "network is frozen in Refign UDA training)")
+    s, t = _f32c(feature_source), _f32c(feature_target)
+    B, C, Hs, Ws = s.shape
+    Bt, Ct, Ht, Wt = t.shape
+    if B != Bt or C != Ct:
+        raise RuntimeError("global_correlation: batch/channel mismatch %s vs %s" % (tuple(s.shape), tuple(t.shape)))
+    Ns, Nt = Hs * Ws, Ht * Wt
+    out = torch.empty(B, Ns, Ht, Wt, device=s.device, dtype=torch.float32)
+    L = _lib.lib()
+    ws = torch.empty(max(1, L.rf_global_corr_workspace_bytes(B, Ns, Nt) // 4), device=s.device,
+                     dtype=torch.float32)
+    mode = int(bool(cyclic_consistency)) | (int(bool(normalise)) << 1)
+    with torch.cuda.device(s.device):
+        check(L.rf_global_corr_fwd(ptr(s), ptr(t), ptr(out), ptr(ws), B, C, Ns, Nt, mode, int(use_tensor_cores),
+                                   _stream()), "rf_global_corr_fwd")
+    return out
+
+
+# --------------------------------------------------------------------------
+# warp (reference: helpers/matching_utils.py:11-49)
+# --------------------------------------------------------------------------
+class _WarpFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, flo, want_mask):
+        require_cuda(x, flo)
+        xf, ff = _f32c(x), _f32c(flo)
+        B, C, H, W = xf.shape
+        if tuple(ff.shape) != (B, 2, H, W):
+            raise RuntimeError("warp: flow must be [B,2,H,W] matching x %s, got %s"
+                               % (tuple(xf.shape), tuple(ff.shape)))
+        out = torch.empty_like(xf)
+        mask = torch.empty(B, H, W, device=xf.device, dtype=torch.uint8) if want_mask else None
+        flag = torch.empty(1, device=xf.device, dtype=torch.int32)
+        L = _lib.lib()
+        with torch.cuda.device(xf.device):
+            check(L.rf_flow_is_zero(ptr(ff), ff.numel(), ptr(flag), _stream()), "rf_flow_is_zero")
+            check(L.rf_warp_bilinear_fwd(ptr(xf), ptr(ff), ptr(out), ptr(mask), ptr(flag), B, C, H, W, _stream()),
+                  "rf_warp_bilinear_fwd")
+        ctx.save_for_backward(xf, ff, flag)
+        if want_mask:
+            mask = mask.view(torch.bool) if hasattr(mask, "view") else mask.bool()
+            ctx.mark_non_differentiable(mask)
+            return out, mask
+        return out, None
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out, _grad_mask):
+        xf, ff, flag = ctx.saved_tensors
+        B, C, H, W = xf.shape
+        g = _f32c(grad_out)
+        gx = torch.zeros_like(xf) if ctx.needs_input_grad[0] else None
+        gf = torch.empty_like(ff) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(xf.device):
+            check(_lib.lib().rf_warp_bilinear_bwd(ptr(xf), ptr(ff), ptr(g), ptr(gx), ptr(gf), ptr(flag), B, C, H, W,
+                                                  _stream()), "rf_warp_bilinear_bwd")
+        return gx, gf, None
+
+
+def warp(x, flo, padding_mode="zeros", return_mask=False):
+    """Drop-in for helpers.matching_utils.warp.  Output is fp32 (the reference
+    forces full precision, matching_utils.py:41-43); no host synchronisation."""
+    if padding_mode != "zeros":
+        raise NotImplementedError("warp: only padding_mode='zeros' is implemented (the only mode Refign uses)")
+    out, mask = _WarpFunction.apply(x, flo, bool(return_mask))
+    return (out, mask) if return_mask else out
+
+
+# --------------------------------------------------------------------------
+# confidence + refinement (reference: matching_utils.py:52-57, segmentation_model.py:438-491)
+# --------------------------------------------------------------------------
+def estimate_probability_of_confidence_interval_of_mixture_density(uncert_output, R=1.0):
+    assert uncert_output.shape[1] == 1
+    if R != 1.0:
+        raise NotImplementedError("only R = 1 (the value Refign uses) is implemented")
+    require_cuda(uncert_output)
+    u = _f32c(uncert_output)
+    out = torch.empty_like(u)
+    with torch.cuda.device(u.device):
+        check(_lib.lib().rf_cert_fwd(ptr(u), ptr(out), u.numel(), _stream()), "rf_cert_fwd")
+    return out
+
+
+def static_mask_bits(classes=STATIC_LARGE_CLASSES):
+    m = 0
+    for c in classes:
+        m |= 1 << int(c)
+    return m
+
+
+@torch.no_grad()
+def refine_fused(logits_trg, logits_ref, warp_mask=None, certs=None, logvar=None, gamma=0.25,
+                 disable_M=False, disable_P=False, static_classes=STATIC_LARGE_CLASSES,
+                 want_label=True):
+    """refine() + pseudo-label in one pass.
+
+    Returns (probs_refined f32 [B,K,H,W], label i64 [B,H,W] | None,
+             maxprob f32 [B,H,W] | None, trust f32 [B]).
+    """
+    require_cuda(logits_trg, logits_ref, warp_mask, certs, logvar)
+    lt, lr = _f32c(logits_trg), _f32c(logits_ref)
+    if lt.shape != lr.shape or lt.dim() != 4:
+        raise RuntimeError("refine: logits must be two [B,K,H,W] tensors of equal shape")
+    B, K, H, W = lt.shape
+    HW = H * W
+    dev = lt.device
+    ent = torch.empty(B, device=dev, dtype=torch.int64)
+    trust = torch.empty(B, device=dev, dtype=torch.float32)
+    probs = torch.empty_like(lt)
+    label = torch.empty(B, H, W, device=dev, dtype=torch.int64) if want_label else None
+    maxp = torch.empty(B, H, W, device=dev, dtype=torch.float32) if want_label else None
+    m8 = None
+    if warp_mask is not None:
+        m8 = warp_mask.contiguous()
+        m8 = m8.view(torch.uint8) if m8.dtype == torch.bool else m8.to(torch.uint8)
+        assert m8.numel() == B * HW
+    ce = None if certs is None else _f32c(certs)
+    lv = None if logvar is None else _f32c(logvar)
+    for t in (ce, lv):
+        assert t is None or t.numel() == B * HW, "certs/logvar must be [B,1,H,W]"
+    flags = int(bool(disable_M)) | (int(bool(disable_P)) << 1)
+    with torch.cuda.device(dev):
+        check(_lib.lib().rf_refine_fwd(ptr(lt), ptr(lr), ptr(ce), ptr(lv), ptr(m8), ptr(ent), ptr(trust),
+                                       ptr(probs), ptr(label), ptr(maxp), B, K, HW, float(gamma),
+                                       static_mask_bits(static_classes), flags, _stream()), "rf_refine_fwd")
+    return probs, label, maxp, trust
+
+
+# --------------------------------------------------------------------------
+# flat-buffer optimiser ops (reference: segmentation_model.py:680-689, :390-419)
+# --------------------------------------------------------------------------
+@torch.no_grad()
+def ema_update_(ema_flat, live_flat, momentum):
+    require_cuda(ema_flat, live_flat)
+    assert ema_flat.dtype == live_flat.dtype == torch.float32 and ema_flat.numel() == live_flat.numel()
+    assert ema_flat.is_contiguous() and live_flat.is_contiguous()
+    with torch.cuda.device(ema_flat.device):
+        check(_lib.lib().rf_ema_update(ptr(ema_flat), ptr(live_flat), ema_flat.numel(), float(momentum), _stream()),
+              "rf_ema_update")
+    return ema_flat
+
+
+@torch.no_grad()
+def adamw_step_(param, grad, exp_avg, exp_avg_sq, seg_end, seg_lr, seg_wd, beta1, beta2, eps, step,
+                grad_scale=1.0):
+    require_cuda(param, grad, exp_avg, exp_avg_sq)
+    n = param.numel()
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == n
+    k = len(seg_end)
+    ends = (ctypes.c_int64 * k)(*[int(e) for e in seg_end])
+    lrs = (ctypes.c_float * k)(*[float(v) for v in seg_lr])
+    wds = (ctypes.c_float * k)(*[float(v) for v in seg_wd])
+    with torch.cuda.device(param.device):
+        check(_lib.lib().rf_adamw_step(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), n, k, ends, lrs, wds,
+                                       float(beta1), float(beta2), float(eps), int(step), float(grad_scale),
+                                       _stream()), "rf_adamw_step")
+    return param
