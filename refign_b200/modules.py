@@ -1,0 +1,233 @@
+"""Building blocks of the Refign hot path with the reference's class names, constructor
+arguments, forward signatures and ``state_dict`` keys (reference: models/modules.py), so
+the reference YAML ``class_path`` entries and checkpoints keep working.
+
+What is different underneath (B200-first):
+  * the correlation layers call the sm_100a kernels through the C-ABI (refign_b200.ops):
+    local correlation with the ReLU + L2-norm fused into the producing kernel, global
+    correlation with mutual matching + ReLU + L2-norm in one launch sequence;
+  * ``ConvBNReLU`` folds an eval-mode BatchNorm into the convolution (the alignment
+    network is frozen and in eval mode for the whole of Refign training,
+    reference segmentation_model.py:73-75,693-694), halving the launches of the flow and
+    uncertainty decoders;
+  * no host synchronisation anywhere.
+"""
+from functools import partial
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+
+class ConvBNReLU(nn.Module):
+    """conv [+ norm] [+ activation]; reference models/modules.py:16-56 (same attribute
+    names: ``conv``/``bn``/``activation`` or ``depthwise_conv``/``pointwise_conv``)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, dilation=1, groups=1, padding=None,
+                 norm_layer=nn.BatchNorm2d, activation_layer=nn.ReLU, bias='auto',
+                 depthwise_separable=False, inplace=True, affine=True):
+        super().__init__()
+        if padding is None:
+            padding = dilation * (kernel_size - 1) // 2
+        self.use_norm = norm_layer is not None
+        self.use_activation = activation_layer is not None
+        self.depthwise_separable = depthwise_separable
+        if bias == 'auto':
+            bias = not self.use_norm
+        if depthwise_separable:
+            assert kernel_size > 1 and groups == 1
+            self.depthwise_conv = ConvBNReLU(in_channels, in_channels, kernel_size, stride=stride, padding=padding,
+                                             dilation=dilation, groups=in_channels, norm_layer=norm_layer,
+                                             activation_layer=activation_layer)
+            self.pointwise_conv = ConvBNReLU(in_channels, out_channels, 1, norm_layer=norm_layer,
+                                             activation_layer=activation_layer)
+        else:
+            self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride, padding, dilation=dilation,
+                                  groups=groups, bias=bias)
+            if self.use_norm:
+                self.bn = norm_layer(out_channels, affine=affine)
+        if self.use_activation:
+            self.activation = activation_layer(inplace=inplace)
+        self._folded = None  # (key, weight, bias) cache of the BN-folded convolution
+
+    def _fold(self):
+        """Eval-mode BatchNorm folded into the conv weights (cached until a tensor changes)."""
+        bn, conv = self.bn, self.conv
+        tensors = (conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var)
+        key = tuple((t.data_ptr(), t._version) if t is not None else None for t in tensors)
+        if self._folded is None or self._folded[0] != key:
+            with torch.no_grad():
+                inv = torch.rsqrt(bn.running_var.float() + bn.eps)
+                scale = inv * bn.weight.float() if bn.weight is not None else inv
+                w = conv.weight.float() * scale.view(-1, 1, 1, 1)
+                b = -bn.running_mean.float() * scale
+                if bn.bias is not None:
+                    b = b + bn.bias.float()
+                if conv.bias is not None:
+                    b = b + conv.bias.float() * scale
+            self._folded = (key, w.contiguous(), b.contiguous())
+        return self._folded[1], self._folded[2]
+
+    def forward(self, x):
+        if self.depthwise_separable:
+            return self.pointwise_conv(self.depthwise_conv(x))
+        conv = self.conv
+        foldable = (self.use_norm and isinstance(self.bn, nn.BatchNorm2d) and not self.bn.training
+                    and self.bn.track_running_stats and not torch.is_grad_enabled())
+        if foldable:
+            w, b = self._fold()
+            x = F.conv2d(x, w.to(x.dtype), b.to(x.dtype), conv.stride, conv.padding, conv.dilation, conv.groups)
+        else:
+            x = conv(x)
+            if self.use_norm:
+                x = self.bn(x)
+        if self.use_activation:
+            x = self.activation(x)
+        return x
+
+
+class MLP(nn.Module):
+    """Linear embedding of an NCHW map, returned as tokens [B, HW, E] (models/modules.py:59-68)."""
+
+    def __init__(self, input_dim=2048, embed_dim=768):
+        super().__init__()
+        self.proj = nn.Linear(input_dim, embed_dim)
+
+    def forward(self, x):
+        return self.proj(x.flatten(2).transpose(1, 2))
+
+
+class DropPath(nn.Module):
+    """Per-sample stochastic depth (models/modules.py:564-596)."""
+
+    def __init__(self, drop_prob=None):
+        super().__init__()
+        self.drop_prob = drop_prob
+
+    def forward(self, x):
+        if not self.drop_prob or not self.training:
+            return x
+        keep = 1.0 - self.drop_prob
+        shape = (x.shape[0],) + (1,) * (x.dim() - 1)
+        mask = torch.empty(shape, dtype=x.dtype, device=x.device).bernoulli_(keep)
+        return x * (mask / keep)
+
+
+class LocalFeatureCorrelationLayer(nn.Module):
+    """9x9 local correlation + ReLU + L2-norm over the displacement channels in ONE sm_100a kernel
+    (reference models/modules.py:247-274: three extra elementwise passes over the volume)."""
+
+    def __init__(self, patch_size=9):
+        super().__init__()
+        self.patch_size = patch_size
+        self.local_correlation = ops.spatial_correlation_sample  # the drop-in sampler, kept for API parity
+
+    def forward(self, feature_source, feature_target):
+        return ops.local_correlation_relu_l2norm(feature_source, feature_target, self.patch_size)
+
+
+class GlobalFeatureCorrelationLayer(nn.Module):
+    """4-D global correlation + mutual matching + ReLU + L2-norm (reference models/modules.py:277-392)."""
+
+    def __init__(self, cyclic_consistency=True):
+        super().__init__()
+        self.cyclic_consistency = cyclic_consistency
+
+    def forward(self, feature_source, feature_target):
+        return ops.global_correlation(feature_source, feature_target, cyclic_consistency=self.cyclic_consistency,
+                                      normalise=True)
+
+
+def _leaky():
+    return partial(nn.LeakyReLU, negative_slope=0.1)
+
+
+class OpticalFlowEstimatorResidualConnection(nn.Module):
+    """Flow decoder with two residual skips (reference models/modules.py:395-443)."""
+
+    def __init__(self, in_channels, out_channels=2, batch_norm=True, output_x=False, extra_bias='auto'):
+        super().__init__()
+        self.output_x = output_x
+        norm = nn.BatchNorm2d if batch_norm else None
+        act = _leaky()
+        self.leaky_relu = act()
+        self.conv_0 = ConvBNReLU(in_channels, 128, 3, norm_layer=norm, activation_layer=None, bias=extra_bias)
+        self.conv0_skip = ConvBNReLU(128, 96, 1, norm_layer=norm, activation_layer=None)
+        self.conv_1 = ConvBNReLU(128, 128, 3, norm_layer=norm, activation_layer=act, bias=extra_bias)
+        self.conv_2 = ConvBNReLU(128, 96, 3, norm_layer=norm, activation_layer=None, bias=extra_bias)
+        self.conv2_skip = ConvBNReLU(96, 32, 1, norm_layer=norm, activation_layer=None)
+        self.conv_3 = ConvBNReLU(96, 64, 3, norm_layer=norm, activation_layer=act, bias=extra_bias)
+        self.conv_4 = ConvBNReLU(64, 32, 3, norm_layer=norm, activation_layer=None, bias=extra_bias)
+        self.predict_mapping = nn.Conv2d(32, out_channels, 3, padding=1, bias=True)
+
+    def forward(self, x):
+        x0 = self.conv_0(x)
+        x2 = self.conv_2(self.conv_1(F.leaky_relu(x0, 0.1)))
+        x2 = x2 + self.conv0_skip(x0)
+        x4 = self.conv_4(self.conv_3(F.leaky_relu(x2, 0.1)))
+        x4 = F.leaky_relu(x4 + self.conv2_skip(x2), 0.1)
+        mapping = self.predict_mapping(x4)
+        return (mapping, x4) if self.output_x else mapping
+
+
+class RefinementModule(nn.Module):
+    """Dilated context network (reference models/modules.py:446-477)."""
+
+    def __init__(self, in_channels, out_channels=2, batch_norm=True):
+        super().__init__()
+        norm = nn.BatchNorm2d if batch_norm else None
+        act = _leaky()
+        chans = [in_channels, 128, 128, 128, 96, 64, 32]
+        dil = [1, 2, 4, 8, 16, 1]
+        layers = [ConvBNReLU(chans[i], chans[i + 1], 3, dilation=dil[i], norm_layer=norm, activation_layer=act)
+                  for i in range(6)]
+        layers.append(nn.Conv2d(32, out_channels, 3, padding=1, bias=True))
+        self.dc_convs = nn.Sequential(*layers)
+
+    def forward(self, x):
+        return self.dc_convs(x)
+
+
+class UncertaintyModule(nn.Module):
+    """Per-pixel patch CNN over the correlation volume -> log-variance
+    (reference models/modules.py:480-561)."""
+
+    def __init__(self, in_channels, feed_in_previous=False, out_channels=1, search_size=9, batch_norm=True,
+                 depthwise_separable=False):
+        super().__init__()
+        norm = nn.BatchNorm2d if batch_norm else None
+        act = _leaky()
+        self.search_size = search_size
+        self.feed_in_previous = feed_in_previous
+        cbr = partial(ConvBNReLU, norm_layer=norm, activation_layer=act, depthwise_separable=depthwise_separable)
+        if search_size not in (9, 16):
+            raise ValueError("search_size must be 9 or 16")
+        out_channels = 1  # as in the reference (:506) the argument is ignored
+        self.conv_0 = cbr(in_channels, 32, 3, padding=0, depthwise_separable=False)
+        if search_size == 16:
+            self.maxpool = nn.MaxPool2d((2, 2))
+        self.conv_1 = cbr(32, 32, 3, padding=0)
+        self.conv_2 = cbr(32, 16, 3, padding=0)
+        self.predict_uncertainty = nn.Conv2d(16, 6, 3, 1, 0, bias=True)
+        extra = 3 if feed_in_previous else 0  # 2 flow channels + 1 log-variance channel
+        self.pred_conv_0 = cbr(6 + 32 + extra, 32, 3)
+        self.pred_conv_1 = cbr(32, 16, 3)
+        self.predict_uncertainty_final = nn.Conv2d(16, out_channels, 3, 1, 1, bias=True)
+
+    def forward(self, corr, feat, up_previous_uncertainty=None, up_previous_flow=None):
+        b, _, h, w = corr.shape
+        s = self.search_size
+        # channels-last view of the volume == [B*H*W, 1, s, s] patches; one transpose copy
+        x = corr.permute(0, 2, 3, 1).reshape(b * h * w, 1, s, s)
+        x = self.conv_0(x)
+        if s == 16:
+            x = self.maxpool(x)
+        x = self.predict_uncertainty(self.conv_2(self.conv_1(x)))
+        x = x.reshape(b, h, w, -1).permute(0, 3, 1, 2)
+        if self.feed_in_previous:
+            x = torch.cat((x, feat, up_previous_uncertainty, up_previous_flow), 1)
+        else:
+            x = torch.cat((x, feat), 1)
+        return self.predict_uncertainty_final(self.pred_conv_1(self.pred_conv_0(x)))

@@ -20,6 +20,53 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+class KernelTimer:
+    """Optional per-kernel device timing of the C-ABI launches (CUDA events on the launching
+    stream).  Used by bench.py for the live roofline figure and the launch count; off by default."""
+
+    def __init__(self):
+        self.records = []      # (name, start_event, end_event, work)
+        self.launches = 0
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1, work in self.records:
+            d = out.setdefault(name, dict(calls=0, ms=0.0, bytes=0, flops=0))
+            d["calls"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            if work:
+                d["bytes"] += work[0]
+                d["flops"] += work[1]
+        return out
+
+
+_TIMER = None
+
+
+def set_timer(timer):
+    """Install (or remove with None) a KernelTimer; returns the previous one."""
+    global _TIMER
+    prev, _TIMER = _TIMER, timer
+    return prev
+
+
+def _run(name, *args, work=None, tag=None):
+    """Launch one C-ABI entry point on the current stream and raise on a non-zero status."""
+    fn = getattr(_lib.lib(), name)
+    t = _TIMER
+    if t is None:
+        rc = fn(*args)
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        t.records.append((tag or name, e0, e1, work))
+        t.launches += 1
+    check(rc, name)
+
+
 def _f32c(t):
     return t.contiguous() if t.dtype == torch.float32 else t.float().contiguous()
 
@@ -65,9 +112,9 @@ class SpatialCorrelationSamplerFunction(torch.autograd.Function):
         ctx.in_dtypes = (input1.dtype, input2.dtype)
         ctx.save_for_backward(a, b)
         with torch.cuda.device(a.device):
-            check(_lib.lib().rf_local_corr_fwd(ptr(a), ptr(b), ptr(out), None, B, C, H, W, k[0], k[1], p[0],
+            _run("rf_local_corr_fwd", ptr(a), ptr(b), ptr(out), None, B, C, H, W, k[0], k[1], p[0],
                                                p[1], pad[0], pad[1], dil[0], dil[1], dp[0], dp[1], s[0],
-                                               s[1], 0, _stream()), "rf_local_corr_fwd")
+                                               s[1], 0, _stream())
         return out
 
     @staticmethod
@@ -80,9 +127,9 @@ class SpatialCorrelationSamplerFunction(torch.autograd.Function):
         ga = torch.empty_like(a) if ctx.needs_input_grad[0] else None
         gb = torch.empty_like(b) if ctx.needs_input_grad[1] else None
         with torch.cuda.device(a.device):
-            check(_lib.lib().rf_local_corr_bwd(ptr(a), ptr(b), ptr(g), ptr(ga), ptr(gb), None, B, C, H, W, k[0],
+            _run("rf_local_corr_bwd", ptr(a), ptr(b), ptr(g), ptr(ga), ptr(gb), None, B, C, H, W, k[0],
                                                k[1], p[0], p[1], pad[0], pad[1], dil[0], dil[1], dp[0],
-                                               dp[1], s[0], s[1], _stream()), "rf_local_corr_bwd")
+                                               dp[1], s[0], s[1], _stream())
         if ga is not None:
             ga = ga.to(ctx.in_dtypes[0])
         if gb is not None:
@@ -112,8 +159,9 @@ class _LocalCorrReluL2Norm(torch.autograd.Function):
         need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         norm = torch.empty(B, H, W, device=t.device, dtype=torch.float32) if need_grad else None
         with torch.cuda.device(t.device):
-            check(_lib.lib().rf_local_corr_fwd(ptr(t), ptr(s), ptr(out), ptr(norm), B, C, H, W, 1, 1, P, P, 0, 0,
-                                               1, 1, 1, 1, 1, 1, 1, _stream()), "rf_local_corr_fwd")
+            _run("rf_local_corr_fwd", ptr(t), ptr(s), ptr(out), ptr(norm), B, C, H, W, 1, 1, P, P, 0, 0,
+                 1, 1, 1, 1, 1, 1, 1, _stream(), tag="local_corr_fwd_relu_l2norm",
+                 work=(4 * B * H * W * (2 * C + P * P), 2 * B * H * W * P * P * C))
         if need_grad:
             ctx.save_for_backward(t, s, out, norm)
             ctx.P = P
@@ -129,12 +177,11 @@ class _LocalCorrReluL2Norm(torch.autograd.Function):
         gc = torch.empty_like(y)
         L = _lib.lib()
         with torch.cuda.device(t.device):
-            check(L.rf_relu_l2norm_bwd(ptr(y), ptr(norm), ptr(gy), ptr(gc), B, P * P, H * W, _stream()),
-                  "rf_relu_l2norm_bwd")
+            _run("rf_relu_l2norm_bwd", ptr(y), ptr(norm), ptr(gy), ptr(gc), B, P * P, H * W, _stream())
             gt = torch.empty_like(t) if ctx.needs_input_grad[1] else None
             gs = torch.empty_like(s) if ctx.needs_input_grad[0] else None
-            check(L.rf_local_corr_bwd(ptr(t), ptr(s), ptr(gc), ptr(gt), ptr(gs), None, B, C, H, W, 1, 1, P, P, 0,
-                                      0, 1, 1, 1, 1, 1, 1, _stream()), "rf_local_corr_bwd")
+            _run("rf_local_corr_bwd", ptr(t), ptr(s), ptr(gc), ptr(gt), ptr(gs), None, B, C, H, W, 1, 1, P, P, 0,
+                                      0, 1, 1, 1, 1, 1, 1, _stream())
         return gs, gt, None
 
 
@@ -165,8 +212,8 @@ def global_correlation(feature_source, feature_target, cyclic_consistency=True, 
                      dtype=torch.float32)
     mode = int(bool(cyclic_consistency)) | (int(bool(normalise)) << 1)
     with torch.cuda.device(s.device):
-        check(L.rf_global_corr_fwd(ptr(s), ptr(t), ptr(out), ptr(ws), B, C, Ns, Nt, mode, int(use_tensor_cores),
-                                   _stream()), "rf_global_corr_fwd")
+        _run("rf_global_corr_fwd", ptr(s), ptr(t), ptr(out), ptr(ws), B, C, Ns, Nt, mode, int(use_tensor_cores),
+             _stream(), work=(4 * B * (C * (Ns + Nt) + Ns * Nt), 2 * B * Ns * Nt * C))
     return out
 
 
@@ -187,9 +234,9 @@ class _WarpFunction(torch.autograd.Function):
         flag = torch.empty(1, device=xf.device, dtype=torch.int32)
         L = _lib.lib()
         with torch.cuda.device(xf.device):
-            check(L.rf_flow_is_zero(ptr(ff), ff.numel(), ptr(flag), _stream()), "rf_flow_is_zero")
-            check(L.rf_warp_bilinear_fwd(ptr(xf), ptr(ff), ptr(out), ptr(mask), ptr(flag), B, C, H, W, _stream()),
-                  "rf_warp_bilinear_fwd")
+            _run("rf_flow_is_zero", ptr(ff), ff.numel(), ptr(flag), _stream())
+            _run("rf_warp_bilinear_fwd", ptr(xf), ptr(ff), ptr(out), ptr(mask), ptr(flag), B, C, H, W, _stream(),
+                 work=(4 * B * H * W * (2 * C + 2) + B * H * W, 8 * B * C * H * W))
         ctx.save_for_backward(xf, ff, flag)
         if want_mask:
             mask = mask.view(torch.bool) if hasattr(mask, "view") else mask.bool()
@@ -206,8 +253,8 @@ class _WarpFunction(torch.autograd.Function):
         gx = torch.zeros_like(xf) if ctx.needs_input_grad[0] else None
         gf = torch.empty_like(ff) if ctx.needs_input_grad[1] else None
         with torch.cuda.device(xf.device):
-            check(_lib.lib().rf_warp_bilinear_bwd(ptr(xf), ptr(ff), ptr(g), ptr(gx), ptr(gf), ptr(flag), B, C, H, W,
-                                                  _stream()), "rf_warp_bilinear_bwd")
+            _run("rf_warp_bilinear_bwd", ptr(xf), ptr(ff), ptr(g), ptr(gx), ptr(gf), ptr(flag), B, C, H, W,
+                                                  _stream())
         return gx, gf, None
 
 
@@ -231,7 +278,7 @@ def estimate_probability_of_confidence_interval_of_mixture_density(uncert_output
     u = _f32c(uncert_output)
     out = torch.empty_like(u)
     with torch.cuda.device(u.device):
-        check(_lib.lib().rf_cert_fwd(ptr(u), ptr(out), u.numel(), _stream()), "rf_cert_fwd")
+        _run("rf_cert_fwd", ptr(u), ptr(out), u.numel(), _stream())
     return out
 
 
@@ -274,9 +321,10 @@ def refine_fused(logits_trg, logits_ref, warp_mask=None, certs=None, logvar=None
         assert t is None or t.numel() == B * HW, "certs/logvar must be [B,1,H,W]"
     flags = int(bool(disable_M)) | (int(bool(disable_P)) << 1)
     with torch.cuda.device(dev):
-        check(_lib.lib().rf_refine_fwd(ptr(lt), ptr(lr), ptr(ce), ptr(lv), ptr(m8), ptr(ent), ptr(trust),
+        _run("rf_refine_fwd", ptr(lt), ptr(lr), ptr(ce), ptr(lv), ptr(m8), ptr(ent), ptr(trust),
                                        ptr(probs), ptr(label), ptr(maxp), B, K, HW, float(gamma),
-                                       static_mask_bits(static_classes), flags, _stream()), "rf_refine_fwd")
+                                       static_mask_bits(static_classes), flags, _stream(),
+             work=(4 * B * HW * (3 * K + 1) + B * HW * 13, 0))
     return probs, label, maxp, trust
 
 
@@ -289,8 +337,8 @@ def ema_update_(ema_flat, live_flat, momentum):
     assert ema_flat.dtype == live_flat.dtype == torch.float32 and ema_flat.numel() == live_flat.numel()
     assert ema_flat.is_contiguous() and live_flat.is_contiguous()
     with torch.cuda.device(ema_flat.device):
-        check(_lib.lib().rf_ema_update(ptr(ema_flat), ptr(live_flat), ema_flat.numel(), float(momentum), _stream()),
-              "rf_ema_update")
+        _run("rf_ema_update", ptr(ema_flat), ptr(live_flat), ema_flat.numel(), float(momentum), _stream(),
+             work=(12 * ema_flat.numel(), 0))
     return ema_flat
 
 
@@ -306,7 +354,55 @@ def adamw_step_(param, grad, exp_avg, exp_avg_sq, seg_end, seg_lr, seg_wd, beta1
     lrs = (ctypes.c_float * k)(*[float(v) for v in seg_lr])
     wds = (ctypes.c_float * k)(*[float(v) for v in seg_wd])
     with torch.cuda.device(param.device):
-        check(_lib.lib().rf_adamw_step(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), n, k, ends, lrs, wds,
+        _run("rf_adamw_step", ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), n, k, ends, lrs, wds,
                                        float(beta1), float(beta2), float(eps), int(step), float(grad_scale),
-                                       _stream()), "rf_adamw_step")
+             _stream(), work=(28 * n, 0))
     return param
+
+
+# --------------------------------------------------------------------------
+# MiT operators (reference: models/backbones/mix_transformer.py)
+# --------------------------------------------------------------------------
+FUSED_ATTENTION = False      # set by _probe_kernels() when the library exports the kernel
+FUSED_DWCONV = False
+FUSED_PATCH_EMBED = False
+
+
+def _sr_attention_library(q, kv, heads, scale):
+    """softmax(q k^T * scale) v with library batched GEMMs (cuBLAS) -- the reference's formulation
+    (mix_transformer.py:156-160), materialising the [B,h,N,M] matrix.  Used for shapes/dtypes the
+    fused kernel does not cover, and as the comparison arm in tests and bench."""
+    B, N, C = q.shape
+    M = kv.shape[1]
+    d = C // heads
+    q4 = q.view(B, N, heads, d).transpose(1, 2)
+    k4 = kv[..., :C].reshape(B, M, heads, d).transpose(1, 2)
+    v4 = kv[..., C:].reshape(B, M, heads, d).transpose(1, 2)
+    attn = torch.softmax((q4 @ k4.transpose(-2, -1)) * scale, dim=-1)
+    return (attn @ v4).transpose(1, 2).reshape(B, N, C)
+
+
+def sr_attention(q, kv, heads, scale):
+    """Attention core of the MiT spatial-reduction attention.
+    q [B,N,h*d], kv [B,M,2*h*d] (k = first half of the channels, v = second half) -> [B,N,h*d]."""
+    if FUSED_ATTENTION and q.is_cuda and _sr_attention_supported(q, kv, heads):
+        return _SrAttentionFunction.apply(q, kv, heads, float(scale))
+    return _sr_attention_library(q, kv, heads, scale)
+
+
+def _sr_attention_supported(q, kv, heads):
+    return False
+
+
+class _SrAttentionFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, kv, heads, scale):
+        raise NotImplementedError
+
+
+def dwconv3x3_gelu(x, H, W, weight, bias):
+    raise NotImplementedError("fused dwconv+GELU kernel not built")
+
+
+def patch_embed_ln(x, conv_w, conv_b, ln_w, ln_b, eps):
+    raise NotImplementedError("fused patch-embed kernel not built")

@@ -1,0 +1,464 @@
+"""``DomainAdaptationSegmentationModel`` -- the Refign UDA train step -- with the reference's
+constructor, method names and ``state_dict`` layout (reference models/segmentation_model.py),
+running on the sm_100a kernels of this package.
+
+If pytorch_lightning is importable the class derives from ``pl.LightningModule`` (drop-in under
+``tools/run.py``); otherwise it derives from ``nn.Module`` and ``setup_runtime()`` supplies what
+Lightning/DDP/torch.optim would (refign_b200.runtime): flat parameter / gradient buffers, a fused
+AdamW step, a fused EMA update and ONE NCCL all-reduce per step.
+
+Differences to the reference that are visible to a caller (all documented in DESIGN.md):
+  * ``align`` fuses the confidence estimate into ``refine`` when called from ``training_step``;
+    called directly it returns the same three tensors as the reference;
+  * ``refine`` is one kernel sequence that also yields the pseudo-label / max-probability the
+    reference derives later in ``get_dacs_mix`` (:551);
+  * no host synchronisation inside the step; metrics are logged as device tensors.
+"""
+import copy
+import math
+import random
+from collections.abc import Sequence
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops, runtime
+from .dacs_transforms import get_class_masks, strong_transform
+from .matching_utils import estimate_probability_of_confidence_interval_of_mixture_density, warp
+from .modules import DropPath
+
+try:  # pragma: no cover - Lightning is not installed in the build image
+    import pytorch_lightning as pl
+    if not hasattr(pl.LightningModule, 'manual_backward'):  # a stub, not the real package
+        raise ImportError
+    _Base = pl.LightningModule
+    _HAVE_PL = True
+except Exception:  # ModuleNotFoundError or a broken install
+    _Base = nn.Module
+    _HAVE_PL = False
+
+
+class PixelWeightedCrossEntropyLoss(nn.Module):
+    """reference models/losses.py:10-22."""
+
+    def __init__(self, ignore_index=255):
+        super().__init__()
+        self.ignore_index = ignore_index
+
+    def forward(self, input, target, pixel_weight=None):
+        loss = F.cross_entropy(input.float(), target, ignore_index=self.ignore_index, reduction='none')
+        if pixel_weight is not None:
+            assert pixel_weight.dim() == loss.dim()
+            loss = loss * pixel_weight.to(loss.dtype)
+        return loss.mean()
+
+
+def _instantiate(args, init):
+    import importlib
+    module, _, name = init['class_path'].rpartition('.')
+    cls = getattr(importlib.import_module(module), name)
+    args = args if isinstance(args, tuple) else (args,)
+    return cls(*args, **init.get('init_args', {}))
+
+
+class DomainAdaptationSegmentationModel(_Base):
+    def __init__(self, optimizer_init, lr_scheduler_init, backbone, head, loss, alignment_backbone=None,
+                 alignment_head=None, metrics={}, backbone_lr_factor=1.0, use_refign=False, use_align=True,
+                 gamma=0.25, adapt_to_ref=False, disable_M=False, disable_P=False, ema_momentum=0.999,
+                 pseudo_label_threshold=0.968, psweight_ignore_top=0, psweight_ignore_bottom=0, enable_fdist=True,
+                 fdist_lambda=0.005, fdist_classes=[6, 7, 11, 12, 13, 14, 15, 16, 17, 18],
+                 fdist_scale_min_ratio=0.75, color_jitter_s=0.2, color_jitter_p=0.2, blur=True, use_hrda=False,
+                 hrda_output_stride=4, hrda_scale_attention=None, hr_loss_weight=0.1, use_slide_inference=False,
+                 inference_batched_slide=True, inference_crop_size=[1080, 1080], inference_stride=[420, 420],
+                 pretrained=None, precision='fp32'):
+        super().__init__()
+        if use_hrda:
+            raise NotImplementedError("HRDA multi-resolution wrappers (BASELINE config 4) are not built yet")
+        # ---- model -------------------------------------------------------------------------------
+        self.backbone = backbone
+        self.head = head
+        self.hrda_scale_attention = None
+        self.alignment_backbone = alignment_backbone
+        self.alignment_head = alignment_head
+        for m in filter(None, [self.alignment_backbone, self.alignment_head]):
+            for p in m.parameters():
+                p.requires_grad = False
+        self.m_backbone = copy.deepcopy(self.backbone)
+        self.m_head = copy.deepcopy(self.head)
+        self.m_hrda_scale_attention = None
+        for p in self.ema_parameters():
+            p.requires_grad = False
+        self.enable_fdist = enable_fdist
+        if enable_fdist:
+            self.imnet_backbone = copy.deepcopy(self.backbone)
+            for p in self.imnet_backbone.parameters():
+                p.requires_grad = False
+        self.loss = loss
+        self.metrics_cfg = metrics
+        self.optimizer_init = optimizer_init
+        self.lr_scheduler_init = lr_scheduler_init
+        self.backbone_lr_factor = backbone_lr_factor
+        # ---- refign ------------------------------------------------------------------------------
+        self.use_refign = use_refign
+        self.use_align = use_align
+        self.gamma = gamma
+        self.adapt_to_ref = adapt_to_ref
+        self.disable_M = disable_M
+        self.disable_P = disable_P
+        # ---- other -------------------------------------------------------------------------------
+        self.ema_momentum = ema_momentum
+        self.pseudo_label_threshold = pseudo_label_threshold
+        self.psweight_ignore_top = psweight_ignore_top
+        self.psweight_ignore_bottom = psweight_ignore_bottom
+        self.fdist_lambda = fdist_lambda
+        self.fdist_classes = fdist_classes
+        self.fdist_scale_min_ratio = fdist_scale_min_ratio
+        self.color_jitter_s = color_jitter_s
+        self.color_jitter_p = color_jitter_p
+        self.blur = blur
+        self.use_hrda = use_hrda
+        self.hr_loss_weight = hr_loss_weight
+        self.use_slide_inference = use_slide_inference
+        self.inference_batched_slide = inference_batched_slide
+        self.inference_crop_size = inference_crop_size
+        self.inference_stride = inference_stride
+        self.automatic_optimization = False
+        self.precision = precision            # 'fp32' | 'bf16' (autocast of the library GEMMs/convs)
+        self._rt = None                       # runtime installed by setup_runtime()
+        self._step = 0
+        self._logged = {}
+        self._fused_pseudo = None             # (probs tensor, label, maxprob) handed from refine to get_dacs_mix
+        self.load_weights(pretrained)
+
+    # ---- what Lightning would provide ---------------------------------------------------------------
+    def setup_runtime(self, process_group=None, world_size=1, betas=(0.9, 0.999), eps=1e-8, sync_batchnorm=None):
+        """Flat parameter/gradient/EMA buffers + fused optimiser + LR schedule (replaces
+        ``configure_optimizers`` + Lightning's DDP wrap).  Call after ``.to(device)``."""
+        if sync_batchnorm is None:
+            sync_batchnorm = world_size > 1
+        if sync_batchnorm and world_size > 1:
+            self.head = nn.SyncBatchNorm.convert_sync_batchnorm(self.head, process_group)
+            self.m_head = nn.SyncBatchNorm.convert_sync_batchnorm(self.m_head, process_group)
+        groups = runtime.group_parameters(self.named_parameters())
+        lr = self.optimizer_init['init_args']['lr']
+        wd = self.optimizer_init['init_args'].get('weight_decay', 0.01)
+        order = ['head_weight', 'head_bias', 'backbone_weight', 'backbone_bias']
+        live, names = [], []
+        seg_end, seg_lr, seg_wd = [], [], []
+        for g in order:
+            for n, p in groups[g]:
+                live.append(p)
+                names.append(n)
+            seg_end.append(sum(runtime._round_up(p.numel()) for p in live))
+            seg_lr.append(lr * (self.backbone_lr_factor if g.startswith('backbone') else 1.0))
+            seg_wd.append(wd if g.endswith('weight') else 0.0)
+        ema_by_name = dict(self.named_parameters())
+        ema = []
+        for n in names:  # same permutation for the teacher: backbone.x <-> m_backbone.x, head.x <-> m_head.x
+            ema.append(ema_by_name['m_' + n])
+        flat_live = runtime.FlatParams(live, with_grad=True)
+        flat_ema = runtime.FlatParams(ema, with_grad=False)
+        init = self.optimizer_init.get('init_args', {})
+        opt = runtime.FlatAdamW(flat_live, seg_end, seg_lr, seg_wd, betas=tuple(init.get('betas', betas)),
+                                eps=init.get('eps', eps), process_group=process_group, world_size=world_size)
+        sch_args = dict(self.lr_scheduler_init.get('init_args', {})) if self.lr_scheduler_init else {}
+        sch = runtime.PolyLRSchedule(opt, max_steps=sch_args.get('max_steps', 40000),
+                                     warmup_iters=sch_args.get('warmup_iters', 1500),
+                                     warmup_ratio=sch_args.get('warmup_ratio', 1e-6),
+                                     power=sch_args.get('power', 0.9), min_lr=sch_args.get('min_lr', 0.0))
+        self._rt = dict(opt=opt, sch=sch, live=flat_live, ema=flat_ema, names=names, world_size=world_size,
+                        group=process_group)
+        return self._rt
+
+    if not _HAVE_PL:
+        def optimizers(self):
+            return self._rt['opt']
+
+        def lr_schedulers(self):
+            return self._rt['sch']
+
+        def manual_backward(self, loss, **kwargs):
+            loss.backward(**kwargs)
+
+        def log(self, name, value, **kwargs):
+            self._logged[name] = value.detach() if torch.is_tensor(value) else value
+
+        @property
+        def global_step(self):
+            return self._step
+
+        @property
+        def device(self):
+            return next(self.parameters()).device
+
+    def _autocast(self):
+        on = self.precision == 'bf16' and next(self.parameters()).is_cuda
+        return torch.autocast('cuda', dtype=torch.bfloat16, enabled=on)
+
+    # ---- the hot loop ------------------------------------------------------------------------------
+    def training_step(self, batch, batch_idx):
+        """One Refign UDA step (reference segmentation_model.py:146-253): EMA update, source CE
+        (+ ImageNet feature distance), teacher + align + refine -> pseudo-label, DACS mix, mixed CE,
+        optimiser step.  Three backward passes accumulate into the flat gradient buffer; the single
+        gradient all-reduce happens inside ``opt.step()``."""
+        opt = self.optimizers()
+        sch = self.lr_schedulers()
+        opt.zero_grad()
+        self.update_momentum_encoder()
+
+        # ---- source ----------------------------------------------------------------------------
+        images_src, gt_src = batch['image_src'], batch['semantic_src']
+        with self._autocast():
+            feats_src = self.backbone(images_src)
+            logits_src = self.head(feats_src)
+            logits_src = F.interpolate(logits_src.float(), images_src.shape[-2:], mode='bilinear',
+                                       align_corners=False)
+            loss_src = self.loss(logits_src, gt_src)
+        self.log("train_loss_src", loss_src)
+        self.manual_backward(loss_src, retain_graph=self.enable_fdist)
+        del loss_src, logits_src
+
+        if self.enable_fdist:
+            with self._autocast():
+                loss_fd = self.calc_feat_dist(images_src, gt_src, feats_src)
+            self.log("train_loss_featdist_src", loss_fd)
+            self.manual_backward(loss_fd)
+            del loss_fd
+        del feats_src
+
+        # ---- target (no grad) ------------------------------------------------------------------
+        with torch.no_grad(), self._autocast():
+            if self.adapt_to_ref and random.random() < 0.5:
+                adapt_to_ref, images_trg = True, batch['image_ref']
+            else:
+                adapt_to_ref, images_trg = False, batch['image_trg']
+            if self.use_refign and not adapt_to_ref:
+                images_ref = batch['image_ref']
+                b = images_trg.shape[0]
+                m_input = torch.cat((images_trg, images_ref))
+                m_logits = self.m_head(self.m_backbone(m_input))
+                m_logits = F.interpolate(m_logits.float(), size=m_input.shape[-2:], mode='bilinear',
+                                         align_corners=False)
+                m_logits_trg, m_logits_ref = m_logits[:b], m_logits[b:]
+                if self.use_align:
+                    warped_ref, warp_mask, logvar = self.align(m_logits_ref, images_ref, images_trg,
+                                                               return_logvar=True)
+                    m_probs_trg = self.refine(m_logits_trg, warped_ref, warp_mask, None, logvar=logvar)
+                else:
+                    m_probs_trg = self.refine(m_logits_trg, m_logits_ref, None, None)
+            else:
+                m_logits_trg = self.m_head(self.m_backbone(images_trg))
+                m_logits_trg = F.interpolate(m_logits_trg.float(), size=images_trg.shape[-2:], mode='bilinear',
+                                             align_corners=False)
+                m_probs_trg = F.softmax(m_logits_trg, dim=1)
+            mixed_img, mixed_lbl, mixed_weight = self.get_dacs_mix(images_trg, m_probs_trg, images_src, gt_src)
+
+        # ---- mixed -----------------------------------------------------------------------------
+        with self._autocast():
+            mixed_pred = self.head(self.backbone(mixed_img))
+            mixed_pred = F.interpolate(mixed_pred.float(), mixed_img.shape[-2:], mode='bilinear',
+                                       align_corners=False)
+            mixed_loss = self.loss(mixed_pred, mixed_lbl, pixel_weight=mixed_weight)
+        self.log("train_loss_uda_trg", mixed_loss)
+        self.manual_backward(mixed_loss)
+        del mixed_loss, mixed_pred
+
+        opt.step()
+        sch.step()
+        if not _HAVE_PL:
+            self._step += 1
+
+    # ---- inference ---------------------------------------------------------------------------------
+    def forward(self, x, out_size=None):
+        if self.use_slide_inference:
+            raise NotImplementedError("slide inference is eval-only and out of the hot-path scope")
+        logits = self.whole_inference(x)
+        if out_size is not None:
+            logits = F.interpolate(logits, size=out_size, mode='bilinear', align_corners=False)
+        return logits
+
+    def whole_inference(self, x):
+        with self._autocast():
+            logits = self.head(self.backbone(x))
+        return F.interpolate(logits.float(), x.shape[-2:], mode='bilinear', align_corners=False)
+
+    # ---- optimisation plumbing (reference :384-419) ------------------------------------------------
+    def configure_optimizers(self):
+        optimizer = _instantiate(self.optimizer_parameters(), self.optimizer_init)
+        lr_scheduler = _instantiate(optimizer, self.lr_scheduler_init)
+        return [optimizer], [lr_scheduler]
+
+    def optimizer_parameters(self):
+        groups = runtime.group_parameters(self.named_parameters())
+        lr = self.optimizer_init['init_args']['lr']
+        wd = self.optimizer_init['init_args']['weight_decay']
+        mk = lambda name, lr_, wd_: {'name': name, 'params': [p for _, p in groups[name]], 'lr': lr_,
+                                     'weight_decay': wd_}
+        return [mk('head_weight', lr, wd), mk('head_bias', lr, 0),
+                mk('backbone_weight', self.backbone_lr_factor * lr, wd),
+                mk('backbone_bias', self.backbone_lr_factor * lr, 0)]
+
+    def load_weights(self, pretrain_path):
+        if pretrain_path is None:
+            return
+        from .mix_transformer import resolve_checkpoint
+        ckpt = torch.load(resolve_checkpoint(pretrain_path), map_location='cpu')
+        self.load_state_dict(ckpt['state_dict'] if 'state_dict' in ckpt else ckpt, strict=True)
+
+    # ---- Refign: refine / eta / align --------------------------------------------------------------
+    @torch.no_grad()
+    def refine(self, logits_trg, logits_ref, warp_mask, certs, logvar=None):
+        """Adaptive label refinement (reference :438-482) in one fused pass; also caches the
+        pseudo-label / max-probability of the refined distribution for ``get_dacs_mix``."""
+        assert logits_trg.shape[1] == 19, 'we assume cityscapes classes'
+        probs, label, maxprob, _ = ops.refine_fused(
+            logits_trg, logits_ref, warp_mask, certs=certs, logvar=logvar, gamma=self.gamma,
+            disable_M=self.disable_M, disable_P=self.disable_P)
+        self._fused_pseudo = (probs, label, maxprob)
+        return probs
+
+    @staticmethod
+    @torch.no_grad()
+    def eta(logits):
+        """Normalised entropy (reference :484-491); kept for API parity -- ``refine`` computes it
+        inside the fused kernel."""
+        p_log_p = F.softmax(logits, dim=1) * F.log_softmax(logits, dim=1)
+        return -p_log_p.sum(dim=1) / math.log(logits.shape[1])
+
+    @torch.no_grad()
+    def align(self, logits_ref, images_ref, images_trg, return_logvar=False):
+        """Warp the reference logits into the target frame (reference :493-523).  Returns
+        (warped logits, validity mask, confidence P_R) -- or the upsampled log-variance instead of
+        P_R when ``return_logvar`` (the confidence is then evaluated inside the refine kernel)."""
+        assert self.alignment_head is not None
+        b, _, h, w = images_trg.shape
+        flow, uncert = _alignment_flow(self.alignment_backbone, self.alignment_head, images_trg, images_ref)
+        warped, mask = warp(logits_ref, flow, return_mask=True)
+        if return_logvar:
+            return warped, mask, uncert
+        return warped, mask, estimate_probability_of_confidence_interval_of_mixture_density(uncert, R=1.0)
+
+    # ---- DACS mix (reference :525-582) -------------------------------------------------------------
+    @torch.no_grad()
+    def get_dacs_mix(self, images_trg, probs_trg, images_src, gt_src):
+        nt = images_trg.shape[0]
+        if images_src.shape[0] > nt:
+            images_src, gt_src = images_src[:nt], gt_src[:nt]
+        strong = {'mix': None, 'color_jitter': random.uniform(0, 1), 'color_jitter_s': self.color_jitter_s,
+                  'color_jitter_p': self.color_jitter_p, 'blur': random.uniform(0, 1) if self.blur else 0}
+        fp = self._fused_pseudo
+        if fp is not None and fp[0] is probs_trg and fp[1] is not None:
+            pseudo_label, pseudo_prob = fp[1], fp[2]
+        else:
+            pseudo_prob, pseudo_label = torch.max(probs_trg, dim=1)
+        self._fused_pseudo = None
+        frac = (pseudo_prob >= self.pseudo_label_threshold).sum() / pseudo_label.numel()
+        pseudo_weight = frac.to(pseudo_prob.dtype).expand_as(pseudo_prob).clone()
+        if self.psweight_ignore_top > 0:
+            pseudo_weight[:, :self.psweight_ignore_top, :] = 0
+        if self.psweight_ignore_bottom > 0:
+            pseudo_weight[:, -self.psweight_ignore_bottom:, :] = 0
+        gt_weight = torch.ones_like(pseudo_weight)
+        mix_masks = get_class_masks(gt_src.unsqueeze(1))
+        mixed_img, mixed_lbl = [None] * nt, [None] * nt
+        for i in range(nt):
+            strong['mix'] = mix_masks[i]
+            mixed_img[i], mixed_lbl[i] = strong_transform(
+                strong, data=torch.stack((images_src[i], images_trg[i])),
+                target=torch.stack((gt_src[i], pseudo_label[i])))
+            _, pseudo_weight[i] = strong_transform(strong, target=torch.stack((gt_weight[i], pseudo_weight[i])))
+        return torch.cat(mixed_img), torch.cat(mixed_lbl).squeeze(1), pseudo_weight
+
+    # ---- ImageNet feature distance (reference :584-668) --------------------------------------------
+    def calc_feat_dist(self, img, gt, feat=None):
+        assert self.enable_fdist
+        with torch.no_grad():
+            feat_imnet = self.imnet_backbone(img)
+            feat_imnet = [f.detach() for f in feat_imnet] if isinstance(feat_imnet, Sequence) else [feat_imnet.detach()]
+        if not isinstance(feat, Sequence):
+            feat = [feat]
+        lay = -1
+        mask = None
+        if self.fdist_classes is not None:
+            fdclasses = torch.tensor(self.fdist_classes, device=gt.device)
+            scale = gt.shape[-1] // feat[lay].shape[-1]
+            gt_small = self.downscale_label_ratio(gt.unsqueeze(1), scale, self.fdist_scale_min_ratio,
+                                                  self.head.num_classes, 255).long().detach()
+            mask = torch.any(gt_small[..., None] == fdclasses, -1)
+        return self.fdist_lambda * self.masked_feat_dist(feat[lay], feat_imnet[lay], mask)
+
+    @staticmethod
+    def masked_feat_dist(f1, f2, mask=None):
+        """Mean L2 feature distance over the masked pixels (reference :621-635) without the
+        boolean-index gather (a host sync): sum(d * m) / sum(m); an empty mask gives NaN as before."""
+        d = torch.norm((f1 - f2).float(), dim=1, p=2)
+        if mask is None:
+            return d.mean()
+        m = mask.squeeze(1).to(d.dtype)
+        return (d * m).sum() / m.sum()
+
+    @staticmethod
+    def downscale_label_ratio(gt, scale_factor, min_ratio, n_classes, ignore_index=255):
+        """Majority label per ``scale_factor`` block, ignore when the majority covers less than
+        ``min_ratio`` (reference :637-668)."""
+        assert scale_factor > 1
+        bs, c, H, W = gt.shape
+        assert c == 1
+        out = torch.where(gt == ignore_index, torch.full_like(gt, n_classes), gt)
+        onehot = F.one_hot(out.squeeze(1), num_classes=n_classes + 1).permute(0, 3, 1, 2).float()
+        ratio, lab = torch.max(F.avg_pool2d(onehot, kernel_size=scale_factor), dim=1, keepdim=True)
+        lab = torch.where((lab == n_classes) | (ratio < min_ratio), torch.full_like(lab, ignore_index), lab)
+        return lab
+
+    # ---- EMA teacher -------------------------------------------------------------------------------
+    def ema_parameters(self):
+        for m in filter(None, [self.m_backbone, self.m_head, self.m_hrda_scale_attention]):
+            yield from m.parameters()
+
+    def live_parameters(self):
+        for m in filter(None, [self.backbone, self.head, self.hrda_scale_attention]):
+            yield from m.parameters()
+
+    @torch.no_grad()
+    def update_momentum_encoder(self):
+        """theta_m <- m * theta_m + (1 - m) * theta, m = min(1 - 1/(step+1), ema_momentum)
+        (reference :680-689) as ONE kernel over the flat buffers."""
+        m = runtime.ema_momentum(self.global_step, self.ema_momentum)
+        if self._rt is not None:
+            ops.ema_update_(self._rt['ema'].data, self._rt['live'].data, m)
+        else:  # no runtime installed (e.g. under Lightning without setup_runtime): per-tensor kernel launches
+            for p, pm in zip(self.live_parameters(), self.ema_parameters()):
+                ops.ema_update_(pm.data.view(-1), p.data.contiguous().view(-1), m)
+
+    def train(self, mode=True):
+        """Alignment network and ImageNet copy always in eval mode; the teacher keeps train-mode
+        BatchNorm and -- the reference's quirk (:695-699) -- its dropout and
+        drop-path stay ACTIVE because only the top-level teacher modules are type-checked."""
+        super().train(mode=mode)
+        for m in filter(None, [self.alignment_backbone, self.alignment_head]):
+            m.eval()
+        for m in filter(None, [self.m_backbone, self.m_head, self.m_hrda_scale_attention]):
+            if isinstance(m, (nn.modules.dropout._DropoutNd, DropPath)):
+                m.training = False
+        if self.enable_fdist:
+            self.imnet_backbone.eval()
+        return self
+
+
+def _alignment_flow(alignment_backbone, alignment_head, images_i, images_j):
+    """Shared by ``align`` (reference segmentation_model.py:493-517) and ``AlignmentModel.forward``
+    (alignment_model.py:55-75): VGG pyramids of both images at full and 256x256 resolution, UAWarpC
+    head, bilinear upsample of the finest flow / log-variance to the image size (values already in
+    image pixels).  Returns (flow i->j [B,2,h,w], log-variance [B,1,h,w]) in fp32."""
+    b, _, h, w = images_i.shape
+    i256 = F.interpolate(images_i, size=(256, 256), mode='area')
+    j256 = F.interpolate(images_j, size=(256, 256), mode='area')
+    full = alignment_backbone(torch.cat([images_j, images_i]), extract_only_indices=[-3, -2])
+    low = alignment_backbone(torch.cat([j256, i256]), extract_only_indices=[-2, -1])
+    pyr_j, pyr_i = zip(*[(l[:b], l[b:]) for l in full])
+    pyr_j256, pyr_i256 = zip(*[(l[:b], l[b:]) for l in low])
+    flow, uncert = alignment_head(pyr_i, pyr_j, pyr_i256, pyr_j256, (h, w))[-1]
+    flow = F.interpolate(flow.float(), size=(h, w), mode='bilinear', align_corners=False)
+    uncert = F.interpolate(uncert.float(), size=(h, w), mode='bilinear', align_corners=False)
+    return flow, uncert

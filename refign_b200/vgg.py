@@ -1,0 +1,73 @@
+"""VGG feature pyramid of the (frozen) alignment network; reference interface and ``state_dict``
+keys (``features.<idx>.weight``; reference models/backbones/vgg.py:32-149).
+
+The convolutions are plain library convs (cuDNN through torch) run channels-last; the pyramid is
+returned as ordinary NCHW-shaped tensors (channels-last strides on CUDA)."""
+import torch
+import torch.nn as nn
+
+_CFGS = {
+    'A': [64, 'M', 128, 'M', 256, 256, 'M', 512, 512, 'M', 512, 512, 'M'],
+    'B': [64, 64, 'M', 128, 128, 'M', 256, 256, 'M', 512, 512, 'M', 512, 512, 'M'],
+    'D': [64, 64, 'M', 128, 128, 'M', 256, 256, 256, 'M', 512, 512, 512, 'M', 512, 512, 512, 'M'],
+    'E': [64, 64, 'M', 128, 128, 'M', 256, 256, 256, 256, 'M', 512, 512, 512, 512, 'M', 512, 512, 512, 512, 'M'],
+}
+
+
+class VGG(nn.Module):
+    arch_settings = {name + bn: {'cfg': cfg, 'batch_norm': bool(bn)}
+                     for name, cfg in (('vgg11', 'A'), ('vgg13', 'B'), ('vgg16', 'D'), ('vgg19', 'E'))
+                     for bn in ('', '_bn')}
+
+    def __init__(self, model_type, out_indices=[0, 1, 2, 3, 4, 5], pretrained=None):
+        super().__init__()
+        self.model_type = model_type
+        s = self.arch_settings[model_type]
+        self.features, cuts = self._make_layers(_CFGS[s['cfg']], s['batch_norm'])
+        self.layer_indices = [cuts[i] for i in out_indices]
+        self.init_weights(pretrained)
+
+    @staticmethod
+    def _make_layers(cfg, batch_norm=False):
+        """Sequential of conv/(bn)/relu/pool plus the reference's cut points (vgg.py:122-149): the index
+        right after the first ReLU, then right after every MaxPool (vgg16: [2, 5, 10, 17, 24, 31])."""
+        layers, cuts, c_in = [], [], 3
+        for v in cfg:
+            if v == 'M':
+                layers.append(nn.MaxPool2d(kernel_size=2, stride=2))
+                cuts.append(len(layers))
+            else:
+                layers.append(nn.Conv2d(c_in, v, kernel_size=3, padding=1))
+                if batch_norm:
+                    layers.append(nn.BatchNorm2d(v))
+                layers.append(nn.ReLU(inplace=True))
+                c_in = v
+                if not cuts:
+                    cuts.append(len(layers))
+        return nn.Sequential(*layers), cuts
+
+    def init_weights(self, pretrained=None):
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='relu')
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.ones_(m.weight)
+                nn.init.zeros_(m.bias)
+        if pretrained is not None:
+            from .mix_transformer import resolve_checkpoint
+            ckpt = torch.load(resolve_checkpoint(pretrained, self.model_type), map_location='cpu')
+            sd = ckpt['state_dict'] if 'state_dict' in ckpt else ckpt
+            self.load_state_dict({k: v for k, v in sd.items() if not k.startswith('classifier.')}, strict=True)
+
+    def forward(self, x, extract_only_indices=None):
+        cuts = [self.layer_indices[i] for i in extract_only_indices] if extract_only_indices else self.layer_indices
+        if x.is_cuda:
+            x = x.contiguous(memory_format=torch.channels_last)
+        outs, prev = [], 0
+        for c in cuts:
+            x = self.features[prev:c](x)
+            outs.append(x)
+            prev = c
+        return outs

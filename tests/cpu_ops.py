@@ -1,0 +1,59 @@
+"""TEST-ONLY: run the host-side modules of refign_b200 on CPU by routing the operator layer
+(refign_b200.ops) to the CPU oracle.  This exercises the host logic (module wiring, state_dict
+compatibility, scale bookkeeping, runtime) without a GPU; the kernels themselves are tested by the
+``-m gpu`` tests.  Never used by the product."""
+import contextlib
+
+import torch
+
+import oracle
+from refign_b200 import ops
+
+
+def _refine(lt, lr, warp_mask=None, certs=None, logvar=None, gamma=0.25, disable_M=False, disable_P=False,
+            static_classes=ops.STATIC_LARGE_CLASSES, want_label=True):
+    return oracle.refine(lt, lr, warp_mask, certs=certs, logvar=logvar, gamma=gamma, disable_M=disable_M,
+                         disable_P=disable_P)
+
+
+def _ema(ema, live, m):
+    ema.mul_(float(torch.tensor(m, dtype=torch.float32))).add_(live * float(torch.tensor(1.0 - m, dtype=torch.float32)))
+    return ema
+
+
+def _adamw(param, grad, exp_avg, exp_avg_sq, seg_end, seg_lr, seg_wd, beta1, beta2, eps, step, grad_scale=1.0):
+    start = 0
+    for end, lr, wd in zip(seg_end, seg_lr, seg_wd):
+        p, g = param[start:end], grad[start:end] * grad_scale
+        m, v = exp_avg[start:end], exp_avg_sq[start:end]
+        p.mul_(1 - lr * wd)
+        m.mul_(beta1).add_(g, alpha=1 - beta1)
+        v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+        bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+        p.addcdiv_(m, (v.sqrt() / (bc2 ** 0.5)).add_(eps), value=-lr / bc1)
+        start = end
+    return param
+
+
+_PATCH = {
+    "local_correlation_relu_l2norm": lambda s, t, P=9: oracle.local_corr_layer(s, t, P),
+    "global_correlation": lambda s, t, cyclic_consistency=True, normalise=True, use_tensor_cores=-1:
+        oracle.global_corr(s, t),
+    "warp": lambda x, flo, padding_mode="zeros", return_mask=False: oracle.warp(x, flo, return_mask=return_mask),
+    "estimate_probability_of_confidence_interval_of_mixture_density": lambda u, R=1.0: oracle.cert(u),
+    "refine_fused": _refine,
+    "ema_update_": _ema,
+    "adamw_step_": _adamw,
+}
+
+
+@contextlib.contextmanager
+def cpu_ops():
+    saved = {k: getattr(ops, k) for k in _PATCH}
+    try:
+        for k, v in _PATCH.items():
+            setattr(ops, k, v)
+        yield
+    finally:
+        for k, v in saved.items():
+            setattr(ops, k, v)
