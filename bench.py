@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""Benchmark of the Refign per-training-step hot path (BASELINE.json metric:
+"Refign train-step image-pairs/sec @1024x1024").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one full DAFormer-MiT-B5 + Refign UDA train step (EMA update, source fwd/bwd, ImageNet
+feature distance, EMA-teacher fwd on target+reference, UAWarpC align, warp, refine, DACS mix, mixed
+fwd/bwd, gradient all-reduce, AdamW) on synthetic 1024x1024 data, 2 (target, reference) pairs + 2
+source images per GPU (the reference's batch of 4, configs/cityscapes_acdc/refign_daformer.yaml:5).
+Weak scaling: per-GPU work is fixed, value = N * 2 pairs / step time (max over ranks).
+
+Prints ONE JSON line (rank 0).  ``--impl reference`` times the CPU oracle port of the same step on
+the host cores (bounded sample, see cpu_baseline.sample) -- /root/reference cannot travel to the
+GPU box and its own code path needs pytorch-lightning/kornia, which are not installable offline.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "refign_daformer_mitb5_train_step"
+METRIC = "refign_train_step_image_pairs_per_s"
+PAIRS_PER_GPU = 2
+OPT = {'class_path': 'torch.optim.AdamW', 'init_args': {'lr': 6e-5 * 10, 'weight_decay': 0.01}}
+SCH = {'class_path': 'helpers.lr_scheduler.LinearWarmupPolynomialLR',
+       'init_args': {'warmup_iters': 1500, 'warmup_ratio': 1e-6, 'power': 1.0, 'max_steps': 40000}}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=1024, help="crop size (BASELINE metric: 1024)")
+    ap.add_argument("--model", default="mit_b5")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-size", type=int, default=256, help="crop size of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def build_model(model_type, precision, device):
+    import torch
+    import refign_b200 as P
+    dims = P.MixVisionTransformer.arch_settings[model_type]['embed_dims']
+    torch.manual_seed(0)  # identical weights on every rank
+    model = P.DomainAdaptationSegmentationModel(
+        optimizer_init=OPT, lr_scheduler_init=SCH,
+        backbone=P.MixVisionTransformer(model_type),
+        head=P.DAFormerHead(dims, [0, 1, 2, 3], 19, 'multiple_select'),
+        loss=P.PixelWeightedCrossEntropyLoss(),
+        alignment_backbone=P.VGG('vgg16', out_indices=[2, 3, 4]),
+        alignment_head=P.UAWarpCHead(in_index=[0, 1], input_transform='multiple_select', estimate_uncertainty=True),
+        backbone_lr_factor=0.1, enable_fdist=True, use_refign=True, adapt_to_ref=False, gamma=0.25,
+        precision=precision)
+    return model.to(device).train()
+
+
+def synth_batch(size, n, seed, device, pin=False):
+    """Synthetic batch of SURVEY 8d: images ~ N(0,1), labels uniform in [0,19) with 5 % ignore; the
+    reference image is the target shifted by a few pixels plus noise so the alignment is non-trivial."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    img_s = torch.randn(n, 3, size, size, generator=g)
+    img_t = torch.randn(n, 3, size, size, generator=g)
+    img_r = img_t.roll((5, -7), (2, 3)) + 0.05 * torch.randn(n, 3, size, size, generator=g)
+    # blocky labels (64x64 blocks) so that the feature-distance mask is populated like on real data
+    lab = torch.randint(0, 19, (n, size // 64, size // 64), generator=g)
+    lab = lab.repeat_interleave(64, 1).repeat_interleave(64, 2)
+    ign = torch.rand(n, size, size, generator=g) < 0.05
+    lab = torch.where(ign, torch.full_like(lab, 255), lab)
+    b = {'image_src': img_s, 'semantic_src': lab, 'image_trg': img_t, 'image_ref': img_r}
+    if pin:
+        return {k: v.pin_memory() for k, v in b.items()}
+    return {k: v.to(device) for k, v in b.items()}
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
+        if sm:
+            out["sm_mhz"] = sm[len(sm) // 2]
+            out["sm_max_mhz"] = int(rows[0][1]) if rows[0][1].isdigit() else None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        out["reasons"] = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in rows)]
+        out["samples"] = len(sm)
+        return out
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+def cpu_reference_step(size, model_type, steps, warmup):
+    """The CPU oracle port of the train step on the host cores: returns (pairs/s scaled to the 1024^2
+    workload by pixel count, seconds per CPU step, cores, sample description)."""
+    import torch
+    import refign_b200 as P  # module constructors only (weights for the oracle); no product compute here
+    from oracle.train_step import CpuTrainStep
+    import oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    oracle.set_num_threads(cores)
+    model = build_model(model_type, "fp32", "cpu")
+    step = CpuTrainStep(model.state_dict(), model_type=model_type)
+    del model
+    batch = synth_batch(size, 1, 1234, "cpu")
+    ts = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        step.step(batch)
+        ts.append(time.perf_counter() - t0)
+    sec = sum(ts[warmup:]) / max(1, steps)
+    return sec, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = min(args.steps, 3), min(args.warmup, 1)
+    sec, cores = cpu_reference_step(args.cpu_size, args.model, steps, warmup)
+    scale = (args.cpu_size / float(args.size)) ** 2
+    value = 1.0 / sec * scale
+    sample = ("oracle port (oracle/train_step.py, torch-CPU + C oracle ops) of the full train step, %s, 1 pair + "
+              "1 source image at %dx%d, fp32, %d timed step(s); pairs/s scaled to %dx%d by pixel count (x%.4f)"
+              % (args.model, args.cpu_size, args.cpu_size, steps, args.size, args.size, scale))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s_%dx%d_b%d" % (WORKLOAD, args.size, args.size, PAIRS_PER_GPU),
+                       "model": args.model},
+            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    import torch
+    import torch.distributed as dist
+    from refign_b200 import _lib, ops
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    assert _lib.lib().rf_device_check() == 0, _lib.lib().rf_last_error().decode()
+    torch.backends.cudnn.benchmark = True
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+
+    model = build_model(args.model, args.precision, dev)
+    model.setup_runtime(process_group=group, world_size=world)
+    batch = synth_batch(args.size, PAIRS_PER_GPU, 100 + rank, dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, step_fn):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            step_fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for i in range(args.warmup):
+        model.training_step(batch, i)
+    # ---- timed region: inputs resident in HBM -------------------------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    timer = ops.KernelTimer()
+    ops.set_timer(timer)
+    ms = timed(args.steps, lambda i: model.training_step(batch, args.warmup + i))
+    ops.set_timer(None)
+    clocks = sampler.stop() if sampler else None
+    kern = timer.summary()
+    launches = timer.launches
+    loss = float(model._logged["train_loss_src"])
+    ms_step = ms / args.steps
+    value = world * PAIRS_PER_GPU / (ms_step * 1e-3)
+
+    # ---- end to end: pinned host inputs -> device each step, loss read back each step -------------
+    e2e = None
+    if not args.no_e2e:
+        host = synth_batch(args.size, PAIRS_PER_GPU, 100 + rank, dev, pin=True)
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+
+        def e2e_step(i):
+            b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+            model.training_step(b, i)
+            return float(model._logged["train_loss_uda_trg"])  # 4-byte D2H read of the step's result
+
+        e2e_step(0)
+        ms_e = timed(args.steps, e2e_step) / args.steps
+        e2e = {"value": world * PAIRS_PER_GPU / (ms_e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": 4, "ms_per_step": ms_e}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    hbm, tf, which = peaks()
+    # dominant own kernel by device time inside the timed region
+    roof = None
+    if kern:
+        name, d = max(kern.items(), key=lambda kv: kv[1]["ms"])
+        per_ms = d["ms"] / d["calls"]
+        tensor_bound = name.startswith("sr_attention") or name.startswith("global_corr_umma")
+        if tensor_bound:
+            ach = d["flops"] / d["calls"] / (per_ms * 1e-3) / 1e12
+            roof = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": tf, "unit": "TFLOP/s",
+                    "frac": ach / tf, "traffic": None}
+        else:
+            ach = d["bytes"] / d["calls"] / (per_ms * 1e-3) / 1e9
+            roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
+                    "frac": ach / hbm, "traffic": None}
+        roof.update({"peak_source": which, "avg_launch_us": per_ms * 1e3, "calls_per_step": d["calls"] / args.steps,
+                     "share_of_step": d["ms"] / ms})
+    own = {k: {"calls_per_step": v["calls"] / args.steps, "ms_per_step": v["ms"] / args.steps,
+               "GBps": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 and v["bytes"] else None,
+               "TFLOPs": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 and v["flops"] else None}
+           for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        sec, cores = cpu_reference_step(args.cpu_size, args.model, 1, 1)
+        scale = (args.cpu_size / float(args.size)) ** 2
+        cpu = {"value": scale / sec, "unit": "pairs/s", "cores": cores, "kind": "port",
+               "sample": "oracle port of the full train step, %s, 1 pair + 1 source at %dx%d fp32, 1 timed step after "
+                         "1 warm-up (%.1f s); scaled to %dx%d by pixel count" % (args.model, args.cpu_size,
+                                                                               args.cpu_size, sec, args.size, args.size)}
+    line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.precision if args.precision != "fp32" else "f32", "data": "synthetic",
+            "config": {"workload": "%s_%dx%d_b%d" % (WORKLOAD, args.size, args.size, PAIRS_PER_GPU),
+                       "model": args.model, "pairs_per_gpu": PAIRS_PER_GPU, "source_images_per_gpu": PAIRS_PER_GPU,
+                       "global_batch_pairs": world * PAIRS_PER_GPU, "parallelism": "dp%d" % world,
+                       "l2": "working set per step (>= 340 MB of parameters + activations) exceeds the 126 MB L2",
+                       "precision_note": "bf16 autocast for library GEMMs/convs; correlation, warp, refine fp32"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+            "own_kernels": own, "loss_src": loss}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

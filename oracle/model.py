@@ -42,7 +42,8 @@ class SD:
         self.sd, self.prefix = sd, prefix
 
     def __call__(self, name):
-        return self.sd[self.prefix + name].detach().float()
+        t = self.sd[self.prefix + name]      # not detached: oracle.train_step differentiates through these
+        return t if t.dtype == torch.float32 else t.float()
 
     def has(self, name):
         return (self.prefix + name) in self.sd
