@@ -142,6 +142,71 @@ int rf_refine_fwd(const float* logits_trg, const float* logits_ref, const float*
                   int B, int K, int64_t HW, float gamma, uint64_t static_mask, int flags,
                   void* stream);
 
+/* ---- depthwise 3x3 convolution, channels-last --------------------------- */
+/* Replaces the two depthwise convolutions of the train step, both stride 1,
+ * padding = dilation, on NHWC (== token [B,H*W,C]) tensors:
+ *   - Mix-FFN DWConv + nn.GELU (models/backbones/mix_transformer.py:96-103,
+ *     556-568): dilation 1, bias, gelu = 1 (exact erf form);
+ *   - the depthwise stage of DAFormer's separable ASPP branches
+ *     (models/heads/daformer.py:26-35, models/modules.py:29-36): dilation
+ *     6/12/18, bias NULL, gelu = 0.
+ *   x, y : dtype 0 = f32, 1 = bf16, [B,H,W,C], C % 8 == 0, 16-byte aligned
+ *   weight : f32 [C,1,3,3] (native parameter layout), bias : f32 [C] or NULL
+ * Accumulation is fp32. */
+int rf_dwconv3x3_nhwc_fwd(const void* x, const float* weight, const float* bias, void* y,
+                          int B, int H, int W, int C, int dilation, int gelu, int dtype,
+                          void* stream);
+/* grad_x = conv with the flipped kernel of grad_y (plain conv, no activation). */
+int rf_dwconv3x3_nhwc_bwd_input(const void* grad_y, const float* weight, void* grad_x,
+                                int B, int H, int W, int C, int dilation, int dtype,
+                                void* stream);
+/* GELU backward pre-pass: grad_pre = grad_out * gelu'(conv(x) + bias); the
+ * pre-activation is recomputed instead of being saved by the forward. */
+int rf_dwconv3x3_gelu_bwd_pre(const void* x, const float* weight, const float* bias,
+                              const void* grad_out, void* grad_pre, int B, int H, int W,
+                              int C, int dilation, int dtype, void* stream);
+/* grad_weight f32 [C,1,3,3] and grad_bias f32 [C] (or NULL); both are zeroed
+ * by the call and then accumulated with fp32 atomics. */
+int rf_dwconv3x3_nhwc_bwd_weight(const void* x, const void* grad_pre, float* grad_weight,
+                                 float* grad_bias, int B, int H, int W, int C, int dilation,
+                                 int dtype, void* stream);
+
+/* ---- MiT spatial-reduction attention core (tcgen05 / TMEM / TMA) --------- */
+/* Replaces the attention core of Attention.forward
+ * (models/backbones/mix_transformer.py:150-160):
+ *   out[b,n,h,:] = softmax_m(scale * <q[b,n,h,:], k[b,m,h,:]>) v[b,m,h,:], head_dim 64
+ *   q   : bf16 [B,N,heads*64]        (output of the q projection, read in place)
+ *   kv  : bf16 [B,M,2*heads*64]      (output of the kv projection: k = [0,C), v = [C,2C))
+ *   out : bf16 [B,N,heads*64];  lse : f32 [B,heads,N] log-sum-exp of the scaled scores, or NULL
+ * The [B,heads,N,M] attention matrix is never written to memory. */
+int rf_sr_attention_fwd(const void* q, const void* kv, void* out, float* lse, int B, int N,
+                        int M, int heads, float scale, void* stream);
+
+/* ---- residual add + LayerNorm ------------------------------------------- */
+/* Replaces the LayerNorms of the MiT encoder and the residual adds in front of
+ * them (models/backbones/mix_transformer.py:203-207 Block.forward, :135/:148 SR
+ * norm, :234/:240 patch-embed norm, :378-426 stage norms; drop-path scaling
+ * models/modules.py:587-596):
+ *   xn = x + scale[row / rows_per_sample] * branch     (branch may be NULL: xn = x)
+ *   y  = (xn - mean) * rstd * gamma + beta,  mean/rstd over the C channels, fp32
+ * x: [rows,C] dtype x_dtype (0 = f32, 1 = bf16; f32 when branch != NULL);
+ * branch: [rows,C] dtype branch_dtype or NULL; scale: f32 [rows/rows_per_sample] or NULL (= 1);
+ * xn_out: f32 [rows,C] or NULL; y: [rows,C] dtype y_dtype; mean, rstd: f32 [rows] or NULL.
+ * C % 32 == 0, C <= 512. */
+int rf_add_layernorm_fwd(const void* x, const void* branch, const float* scale,
+                         const float* gamma, const float* beta, float* xn_out, void* y,
+                         float* mean, float* rstd, int64_t rows, int C,
+                         int64_t rows_per_sample, float eps, int x_dtype, int branch_dtype,
+                         int y_dtype, void* stream);
+/* Backward: dxn = dxn_in (or 0 when NULL) + LN'(dy);  dbranch = scale * dxn (or NULL);
+ * dgamma, dbeta: f32 [C], zeroed by the call then accumulated with fp32 atomics.
+ * xn: the forward's xn (dtype xn_dtype), dy dtype dy_dtype, dbranch dtype branch_dtype. */
+int rf_add_layernorm_bwd(const void* xn, const void* dy, const float* dxn_in,
+                         const float* mean, const float* rstd, const float* gamma,
+                         const float* scale, float* dxn, void* dbranch, float* dgamma,
+                         float* dbeta, int64_t rows, int C, int64_t rows_per_sample,
+                         int xn_dtype, int dy_dtype, int branch_dtype, void* stream);
+
 /* ---- optimiser-side multi-tensor ops on flat buffers ------------------- */
 /* Replaces update_momentum_encoder (segmentation_model.py:680-689):
  *   ema = ema*m + live*(1-m)   over one flat f32 buffer.  momentum is a double

@@ -30,6 +30,13 @@ _SIGNATURES = {
     "rf_warp_bilinear_bwd": (c_int, [c_p] * 6 + [c_int] * 4 + [c_p]),
     "rf_cert_fwd": (c_int, [c_p, c_p, c_i64, c_p]),
     "rf_refine_fwd": (c_int, [c_p] * 10 + [c_int, c_int, c_i64, c_f32, c_u64, c_int, c_p]),
+    "rf_dwconv3x3_nhwc_fwd": (c_int, [c_p, c_p, c_p, c_p] + [c_int] * 7 + [c_p]),
+    "rf_dwconv3x3_nhwc_bwd_input": (c_int, [c_p, c_p, c_p] + [c_int] * 6 + [c_p]),
+    "rf_dwconv3x3_gelu_bwd_pre": (c_int, [c_p] * 5 + [c_int] * 6 + [c_p]),
+    "rf_dwconv3x3_nhwc_bwd_weight": (c_int, [c_p] * 4 + [c_int] * 6 + [c_p]),
+    "rf_add_layernorm_fwd": (c_int, [c_p] * 9 + [c_i64, c_int, c_i64, c_f32, c_int, c_int, c_int, c_p]),
+    "rf_add_layernorm_bwd": (c_int, [c_p] * 11 + [c_i64, c_int, c_i64, c_int, c_int, c_int, c_p]),
+    "rf_sr_attention_fwd": (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_f32, c_p]),
     "rf_ema_update": (c_int, [c_p, c_p, c_i64, ctypes.c_double, c_p]),
     "rf_adamw_step": (c_int, [c_p, c_p, c_p, c_p, c_i64, c_int, ctypes.POINTER(c_i64),
                               ctypes.POINTER(c_f32), ctypes.POINTER(c_f32), c_f32, c_f32, c_f32,

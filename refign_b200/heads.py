@@ -102,7 +102,10 @@ class DAFormerHead(BaseHead):
             c = self.embed_layers[str(i)](x[i])                 # [n, hi*wi, E] tokens
             c = c.view(n, hi, wi, -1).permute(0, 3, 1, 2)       # NCHW view, channels-last memory
             if (hi, wi) != tuple(os_size):
-                c = F.interpolate(c, size=os_size, mode='bilinear', align_corners=False)
+                # autocast would promote the upsampling to fp32 (a 4-byte [n,256,H/4,W/4] tensor per stage and an
+                # fp32 ASPP input); the kernel accumulates in fp32 either way, keep the activations bf16
+                with torch.autocast('cuda', enabled=False):
+                    c = F.interpolate(c, size=os_size, mode='bilinear', align_corners=False)
             embedded.append(c)
         y = torch.cat(embedded, dim=1)
         if cl:

@@ -95,7 +95,7 @@ class Attention(nn.Module):
         q = self.q(x)                                        # [B, N, h*d]   (read strided per head)
         if self.sr_ratio > 1:
             x_ = _tokens(self.sr(_nhwc_view(x, H, W)))
-            x_ = self.norm(x_)
+            x_ = ops.layer_norm(x_, self.norm)
         else:
             x_ = x
         kv = self.kv(x_)                                     # [B, M, 2*h*d]: k = [..., :C], v = [..., C:]
@@ -117,10 +117,28 @@ class Block(nn.Module):
         self.norm2 = norm_layer(dim)
         self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
 
-    def forward(self, x, H, W):
-        x = x + self.drop_path(self.attn(self.norm1(x), H, W))
-        x = x + self.drop_path(self.mlp(self.norm2(x), H, W))
-        return x
+    def _path_scale(self, x):
+        """Per-sample drop-path factor mask / keep_prob as a [B] tensor, or None (reference
+        models/modules.py:587-596)."""
+        dp = self.drop_path
+        if not isinstance(dp, DropPath) or not dp.drop_prob or not dp.training:
+            return None
+        keep = 1.0 - dp.drop_prob
+        return torch.empty(x.shape[0], dtype=torch.float32, device=x.device).bernoulli_(keep) / keep
+
+    def forward(self, x, H, W, carry=None):
+        """x: residual stream [B,N,C]; ``carry`` = (branch, scale) of the previous block's still
+        un-added MLP branch.  The residual adds are fused into the LayerNorm that follows them
+        (refign_b200.ops.add_layer_norm), so this returns (x, carry) with the last add pending:
+            x = x + dp(attn(norm1(x))); x = x + dp(mlp(norm2(x)))          (reference :203-207)"""
+        if carry is None:
+            h = ops.layer_norm(x, self.norm1)
+        else:
+            x, h = ops.add_layer_norm(x, carry[0], carry[1], self.norm1)
+        a = self.attn(h, H, W)
+        x, h = ops.add_layer_norm(x, a, self._path_scale(x), self.norm2)
+        m = self.mlp(h, H, W)
+        return x, (m, self._path_scale(x))
 
 
 class OverlapPatchEmbed(nn.Module):
@@ -143,7 +161,9 @@ class OverlapPatchEmbed(nn.Module):
                                       self.norm.eps)
         y = self.proj(x.contiguous(memory_format=torch.channels_last) if x.is_cuda and x.shape[1] > 3 else x)
         _, _, H, W = y.shape
-        return self.norm(_tokens(y)), H, W
+        # the residual stream starts here and stays fp32 (as under the reference's AMP, where LayerNorm
+        # autocasts to fp32)
+        return ops.layer_norm(_tokens(y), self.norm, out_dtype=torch.float32), H, W
 
 
 class MixVisionTransformer(nn.Module):
@@ -234,9 +254,16 @@ class MixVisionTransformer(nn.Module):
         B = x.shape[0]
         for s in range(4):
             x, H, W = getattr(self, 'patch_embed%d' % (s + 1))(x)
+            carry = None
             for blk in getattr(self, 'block%d' % (s + 1)):
-                x = blk(x, H, W)
-            x = getattr(self, 'norm%d' % (s + 1))(x)
+                x, carry = blk(x, H, W, carry)
+            norm = getattr(self, 'norm%d' % (s + 1))
+            # stage outputs keep the residual stream's dtype (fp32, like LayerNorm under the reference's AMP):
+            # they feed the feature-distance loss as well as the decode head
+            if carry is None:
+                x = ops.layer_norm(x, norm, out_dtype=x.dtype)
+            else:
+                _, x = ops.add_layer_norm(x, carry[0], carry[1], norm, out_dtype=x.dtype)
             # stage output: logical NCHW, physically channels-last (zero-copy view of the tokens);
             # consumers that need plain NCHW call .contiguous()
             x = x.view(B, H, W, -1).permute(0, 3, 1, 2)

@@ -52,6 +52,12 @@ class ConvBNReLU(nn.Module):
             self.activation = activation_layer(inplace=inplace)
         self._folded = None  # (key, weight, bias) cache of the BN-folded convolution
 
+    def _is_depthwise3x3(self):
+        c = self.conv
+        return (c.groups == c.in_channels == c.out_channels and c.kernel_size == (3, 3) and c.stride == (1, 1)
+                and c.dilation[0] == c.dilation[1] and c.padding == c.dilation and c.in_channels % 8 == 0
+                and c.padding_mode == 'zeros')
+
     def _fold(self):
         """Eval-mode BatchNorm folded into the conv weights (cached until a tensor changes)."""
         bn, conv = self.bn, self.conv
@@ -80,7 +86,11 @@ class ConvBNReLU(nn.Module):
             w, b = self._fold()
             x = F.conv2d(x, w.to(x.dtype), b.to(x.dtype), conv.stride, conv.padding, conv.dilation, conv.groups)
         else:
-            x = conv(x)
+            if self._is_depthwise3x3():
+                # channels-last depthwise kernel (cuDNN's grouped-direct path is ~100x off the HBM roofline here)
+                x = ops.dwconv3x3_nhwc(x, conv.weight, conv.bias, conv.dilation[0])
+            else:
+                x = conv(x)
             if self.use_norm:
                 x = self.bn(x)
         if self.use_activation:

@@ -363,8 +363,8 @@ def adamw_step_(param, grad, exp_avg, exp_avg_sq, seg_end, seg_lr, seg_wd, beta1
 # --------------------------------------------------------------------------
 # MiT operators (reference: models/backbones/mix_transformer.py)
 # --------------------------------------------------------------------------
-FUSED_ATTENTION = False      # set by _probe_kernels() when the library exports the kernel
-FUSED_DWCONV = False
+FUSED_ATTENTION = True
+FUSED_DWCONV = True
 FUSED_PATCH_EMBED = False
 
 
@@ -391,17 +391,249 @@ def sr_attention(q, kv, heads, scale):
 
 
 def _sr_attention_supported(q, kv, heads):
-    return False
+    """The tcgen05 kernel covers bf16 operands with head_dim 64 (every MiT variant); fp32 parity
+    runs use the library formulation."""
+    return (q.dtype == torch.bfloat16 and kv.dtype == torch.bfloat16 and q.shape[-1] == heads * 64
+            and kv.shape[-1] == 2 * heads * 64)
+
+
+def sr_attention_fwd(q, kv, heads, scale, want_lse=False):
+    """Launch the fused forward kernel; returns (out bf16 [B,N,C], lse f32 [B,h,N] | None)."""
+    require_cuda(q, kv)
+    q, kv = q.contiguous(), kv.contiguous()
+    B, N, C = q.shape
+    M = kv.shape[1]
+    out = torch.empty_like(q)
+    lse = torch.empty(B, heads, N, device=q.device, dtype=torch.float32) if want_lse else None
+    with torch.cuda.device(q.device):
+        _run("rf_sr_attention_fwd", ptr(q), ptr(kv), ptr(out), ptr(lse), B, N, M, heads, float(scale), _stream(),
+             work=(2 * (2 * q.numel() + kv.numel()), 4 * B * heads * N * M * 64), tag="sr_attention_fwd")
+    return out, lse
 
 
 class _SrAttentionFunction(torch.autograd.Function):
+    """Fused forward (no [B,h,N,M] matrix in HBM, nothing but q / kv saved).  The backward re-forms
+    the probabilities per call with library GEMMs from the saved q / kv (flash-style recompute);
+    a fused tcgen05 backward is the next step."""
+
     @staticmethod
     def forward(ctx, q, kv, heads, scale):
-        raise NotImplementedError
+        out, _ = sr_attention_fwd(q, kv, heads, scale)
+        ctx.save_for_backward(q, kv)
+        ctx.cfg = (heads, scale)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, go):
+        q, kv = ctx.saved_tensors
+        heads, scale = ctx.cfg
+        B, N, C = q.shape
+        M = kv.shape[1]
+        d = C // heads
+        q4 = q.view(B, N, heads, d).transpose(1, 2)
+        k4 = kv[..., :C].reshape(B, M, heads, d).transpose(1, 2)
+        v4 = kv[..., C:].reshape(B, M, heads, d).transpose(1, 2)
+        g4 = go.reshape(B, N, heads, d).transpose(1, 2).to(q.dtype)
+        p = torch.softmax((q4 @ k4.transpose(-2, -1)).float() * scale, dim=-1)
+        pb = p.to(q.dtype)
+        dv = pb.transpose(-2, -1) @ g4
+        dp = (g4 @ v4.transpose(-2, -1)).float()
+        ds = (p * (dp - (dp * p).sum(-1, keepdim=True)) * scale).to(q.dtype)
+        dq = (ds @ k4).transpose(1, 2).reshape(B, N, C)
+        dk = (ds.transpose(-2, -1) @ q4).transpose(1, 2).reshape(B, M, C)
+        dkv = torch.cat([dk, dv.transpose(1, 2).reshape(B, M, C)], dim=-1)
+        return dq, dkv, None, None
+
+
+def _dt_code(t):
+    if t.dtype == torch.bfloat16:
+        return 1
+    if t.dtype == torch.float32:
+        return 0
+    raise RuntimeError("refign_b200: unsupported dtype %s (float32 / bfloat16 only)" % t.dtype)
+
+
+class _DwConv3x3(torch.autograd.Function):
+    """Depthwise 3x3 conv (stride 1, padding = dilation) on a contiguous [B,H,W,C] tensor, optional
+    bias and fused exact-erf GELU; fp32 parameters in their native [C,1,3,3] layout."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, dilation, gelu):
+        require_cuda(x, weight, bias)
+        B, H, W, C = x.shape
+        assert x.is_contiguous() and weight.numel() == 9 * C
+        w = _f32c(weight)
+        b = None if bias is None else _f32c(bias)
+        y = torch.empty_like(x)
+        dt = _dt_code(x)
+        nbytes = 2 * x.numel() * x.element_size()
+        with torch.cuda.device(x.device):
+            _run("rf_dwconv3x3_nhwc_fwd", ptr(x), ptr(w), ptr(b), ptr(y), B, H, W, C, int(dilation), int(bool(gelu)),
+                 dt, _stream(), work=(nbytes, 18 * x.numel()), tag="dwconv3x3_fwd")
+        ctx.save_for_backward(x, w, b)
+        ctx.cfg = (int(dilation), bool(gelu), dt, bias is not None, weight.shape)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        x, w, b = ctx.saved_tensors
+        dil, gelu, dt, has_bias, wshape = ctx.cfg
+        B, H, W, C = x.shape
+        gy = gy.contiguous()
+        if gy.dtype != x.dtype:
+            gy = gy.to(x.dtype)
+        nbytes = x.numel() * x.element_size()
+        with torch.cuda.device(x.device):
+            if gelu:
+                g = torch.empty_like(x)
+                _run("rf_dwconv3x3_gelu_bwd_pre", ptr(x), ptr(w), ptr(b), ptr(gy), ptr(g), B, H, W, C, dil, dt,
+                     _stream(), work=(3 * nbytes, 18 * x.numel()), tag="dwconv3x3_gelu_bwd_pre")
+            else:
+                g = gy
+            gx = gw = gb = None
+            if ctx.needs_input_grad[0]:
+                gx = torch.empty_like(x)
+                _run("rf_dwconv3x3_nhwc_bwd_input", ptr(g), ptr(w), ptr(gx), B, H, W, C, dil, dt, _stream(),
+                     work=(2 * nbytes, 18 * x.numel()), tag="dwconv3x3_bwd_input")
+            if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
+                gw = torch.empty(wshape, device=x.device, dtype=torch.float32)
+                gb = torch.empty(C, device=x.device, dtype=torch.float32) if has_bias else None
+                _run("rf_dwconv3x3_nhwc_bwd_weight", ptr(x), ptr(g), ptr(gw), ptr(gb), B, H, W, C, dil, dt, _stream(),
+                     work=(2 * nbytes, 18 * x.numel()), tag="dwconv3x3_bwd_weight")
+        return gx, gw, gb, None, None
 
 
 def dwconv3x3_gelu(x, H, W, weight, bias):
-    raise NotImplementedError("fused dwconv+GELU kernel not built")
+    """Mix-FFN ``act(dwconv(x))`` on tokens [B, H*W, C] (reference mix_transformer.py:96-103,556-568)."""
+    B, N, C = x.shape
+    y = _DwConv3x3.apply(x.contiguous().view(B, H, W, C), weight, bias, 1, True)
+    return y.view(B, N, C)
+
+
+def dwconv3x3_nhwc(x, weight, bias=None, dilation=1):
+    """Depthwise 3x3 conv (padding = dilation) of a logical-NCHW tensor held channels-last; returns the
+    same kind of tensor (reference modules.py:29-36 depthwise branch of the separable ASPP convs)."""
+    xh = x.permute(0, 2, 3, 1)
+    if not xh.is_contiguous():
+        xh = xh.contiguous()
+    y = _DwConv3x3.apply(xh, weight, bias, int(dilation), False)
+    return y.permute(0, 3, 1, 2)
+
+
+def _ln_out_dtype(x):
+    """LayerNorm output dtype: bf16 under bf16 autocast (it feeds a tensor-core GEMM that would cast it
+    anyway), else the input dtype."""
+    if torch.is_autocast_enabled() and torch.get_autocast_gpu_dtype() == torch.bfloat16:
+        return torch.bfloat16
+    return x.dtype
+
+
+class _LayerNorm(torch.autograd.Function):
+    """y = LayerNorm(x) over the last dim of [..., C]; statistics and parameters fp32."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, out_dtype):
+        require_cuda(x, gamma, beta)
+        C = x.shape[-1]
+        xc = x.contiguous()
+        rows = xc.numel() // C
+        y = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+        g, b = _f32c(gamma), _f32c(beta)
+        need = any(ctx.needs_input_grad[:3])
+        mean = torch.empty(rows, device=x.device, dtype=torch.float32) if need else None
+        rstd = torch.empty(rows, device=x.device, dtype=torch.float32) if need else None
+        with torch.cuda.device(x.device):
+            _run("rf_add_layernorm_fwd", ptr(xc), None, None, ptr(g), ptr(b), None, ptr(y), ptr(mean), ptr(rstd),
+                 rows, C, rows, float(eps), _dt_code(xc), 0, _dt_code(y), _stream(),
+                 work=(xc.numel() * xc.element_size() + y.numel() * y.element_size(), 8 * xc.numel()),
+                 tag="layernorm_fwd")
+        if need:
+            ctx.save_for_backward(xc, g, mean, rstd)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        xc, g, mean, rstd = ctx.saved_tensors
+        C = xc.shape[-1]
+        rows = xc.numel() // C
+        dy = dy.contiguous()
+        dx = torch.empty(xc.shape, device=xc.device, dtype=torch.float32)
+        dg = torch.empty(C, device=xc.device, dtype=torch.float32)
+        db = torch.empty(C, device=xc.device, dtype=torch.float32)
+        with torch.cuda.device(xc.device):
+            _run("rf_add_layernorm_bwd", ptr(xc), ptr(dy), None, ptr(mean), ptr(rstd), ptr(g), None, ptr(dx), None,
+                 ptr(dg), ptr(db), rows, C, rows, _dt_code(xc), _dt_code(dy), 0, _stream(),
+                 work=(xc.numel() * (xc.element_size() + dy.element_size() + 4), 12 * xc.numel()),
+                 tag="layernorm_bwd")
+        return (dx if xc.dtype == torch.float32 else dx.to(xc.dtype)), dg, db, None, None
+
+
+class _AddLayerNorm(torch.autograd.Function):
+    """(xn, y) = (x + scale[b] * branch, LayerNorm(xn)) for the pre-LN residual blocks; xn fp32."""
+
+    @staticmethod
+    def forward(ctx, x, branch, scale, gamma, beta, eps, out_dtype):
+        require_cuda(x, branch, scale, gamma, beta)
+        assert x.dim() == 3 and branch.shape == x.shape
+        B, N, C = x.shape
+        xc, bc = _f32c(x), branch.contiguous()
+        sc = None if scale is None else _f32c(scale)
+        rows = B * N
+        xn = torch.empty_like(xc)
+        y = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+        g, b = _f32c(gamma), _f32c(beta)
+        need = any(ctx.needs_input_grad[:5])
+        mean = torch.empty(rows, device=x.device, dtype=torch.float32) if need else None
+        rstd = torch.empty(rows, device=x.device, dtype=torch.float32) if need else None
+        with torch.cuda.device(x.device):
+            _run("rf_add_layernorm_fwd", ptr(xc), ptr(bc), ptr(sc), ptr(g), ptr(b), ptr(xn), ptr(y), ptr(mean),
+                 ptr(rstd), rows, C, N, float(eps), 0, _dt_code(bc), _dt_code(y), _stream(),
+                 work=(xc.numel() * (8 + bc.element_size() + y.element_size()), 10 * xc.numel()),
+                 tag="add_layernorm_fwd")
+        if need:
+            ctx.save_for_backward(xn, g, mean, rstd, sc)
+            ctx.meta = (branch.dtype, x.dtype, N)
+        ctx.set_materialize_grads(False)
+        return xn, y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dxn, dy):
+        xn, g, mean, rstd, sc = ctx.saved_tensors
+        bdtype, xdtype, N = ctx.meta
+        C = xn.shape[-1]
+        rows = xn.numel() // C
+        if dy is None:  # the normalised output was not used: pure residual pass-through
+            dx = dxn
+            dbr = dxn if sc is None else dxn * sc.view(-1, 1, 1)
+            return dx.to(xdtype), dbr.to(bdtype), None, None, None, None, None
+        dy = dy.contiguous()
+        dxi = None if dxn is None else _f32c(dxn)
+        dx = torch.empty_like(xn)
+        dbr = torch.empty(xn.shape, device=xn.device, dtype=bdtype)
+        dg = torch.empty(C, device=xn.device, dtype=torch.float32)
+        db = torch.empty(C, device=xn.device, dtype=torch.float32)
+        with torch.cuda.device(xn.device):
+            _run("rf_add_layernorm_bwd", ptr(xn), ptr(dy), ptr(dxi), ptr(mean), ptr(rstd), ptr(g), ptr(sc), ptr(dx),
+                 ptr(dbr), ptr(dg), ptr(db), rows, C, N, 0, _dt_code(dy), _dt_code(dbr), _stream(),
+                 work=(xn.numel() * (4 + dy.element_size() + (4 if dxi is not None else 0) + 4 + dbr.element_size()),
+                       14 * xn.numel()), tag="add_layernorm_bwd")
+        return (dx if xdtype == torch.float32 else dx.to(xdtype)), dbr, None, dg, db, None, None
+
+
+def layer_norm(x, norm, out_dtype=None):
+    """``norm(x)`` for an ``nn.LayerNorm`` over the last dimension (reference mix_transformer.py:135,234,
+    304): one kernel, fp32 statistics, output dtype ``out_dtype`` (default: bf16 under bf16 autocast)."""
+    return _LayerNorm.apply(x, norm.weight, norm.bias, norm.eps, out_dtype or _ln_out_dtype(x))
+
+
+def add_layer_norm(x, branch, scale, norm, out_dtype=None):
+    """Residual add fused with the following LayerNorm: returns ``(x + scale[b] * branch, norm(...))``
+    (reference mix_transformer.py:203-207; ``scale`` = per-sample drop-path factor or None)."""
+    return _AddLayerNorm.apply(x, branch, scale, norm.weight, norm.bias, norm.eps, out_dtype or _ln_out_dtype(x))
 
 
 def patch_embed_ln(x, conv_w, conv_b, ln_w, ln_b, eps):

@@ -5,6 +5,7 @@ compatibility, scale bookkeeping, runtime) without a GPU; the kernels themselves
 import contextlib
 
 import torch
+import torch.nn.functional as F
 
 import oracle
 from refign_b200 import ops
@@ -35,7 +36,30 @@ def _adamw(param, grad, exp_avg, exp_avg_sq, seg_end, seg_lr, seg_wd, beta1, bet
     return param
 
 
+def _dwconv_gelu(x, H, W, weight, bias):
+    B, N, C = x.shape
+    y = F.conv2d(x.transpose(1, 2).reshape(B, C, H, W), weight, bias, padding=1, groups=C)
+    return F.gelu(y).flatten(2).transpose(1, 2)
+
+
+def _dwconv_nhwc(x, weight, bias=None, dilation=1):
+    return F.conv2d(x, weight, bias, padding=dilation, dilation=dilation, groups=x.shape[1])
+
+
+def _layer_norm(x, norm, out_dtype=None):
+    return F.layer_norm(x, (x.shape[-1],), norm.weight, norm.bias, norm.eps)
+
+
+def _add_layer_norm(x, branch, scale, norm, out_dtype=None):
+    xn = x + (branch if scale is None else branch * scale.view(-1, 1, 1))
+    return xn, F.layer_norm(xn, (xn.shape[-1],), norm.weight, norm.bias, norm.eps)
+
+
 _PATCH = {
+    "layer_norm": _layer_norm,
+    "add_layer_norm": _add_layer_norm,
+    "dwconv3x3_gelu": _dwconv_gelu,
+    "dwconv3x3_nhwc": _dwconv_nhwc,
     "local_correlation_relu_l2norm": lambda s, t, P=9: oracle.local_corr_layer(s, t, P),
     "global_correlation": lambda s, t, cyclic_consistency=True, normalise=True, use_tensor_cores=-1:
         oracle.global_corr(s, t),

@@ -1,0 +1,189 @@
+"""GPU parity tests of the MiT / DAFormer operator kernels (depthwise conv, SR-attention, patch
+embedding, LayerNorm) called through the C-ABI, against a plain PyTorch fp32 reference of the same
+op (these are floating-point kernels; the tolerance is written in each test).
+
+fp32 I/O: 1e-3 relative (north_star).  bf16 I/O: the result is compared with the fp32 reference
+evaluated on the SAME bf16-rounded inputs; the tolerance is two bf16 ulps of the output scale
+(2 * 2^-8), i.e. the rounding of the stored result, not of the arithmetic (which is fp32)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from refign_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _close(got, want, rtol, atol, what=""):
+    got, want = got.detach().float().cpu(), want.detach().float().cpu()
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    err = (got - want).abs()
+    tol = atol + rtol * want.abs()
+    assert bool((err <= tol).all()), "%s: max abs err %.3e at |want| max %.3e" % (what, err.max().item(),
+                                                                                  want.abs().max().item())
+
+
+DW_SPECS = [  # B, H, W, C, dilation, gelu, bias
+    (2, 16, 16, 64, 1, True, True),      # Mix-FFN shape family
+    (1, 9, 13, 32, 1, True, True),       # ragged W (W % 4 != 0)
+    (2, 24, 20, 128, 6, False, False),   # ASPP depthwise branches
+    (1, 40, 40, 64, 12, False, False),
+    (1, 40, 24, 16, 18, False, False),   # dilation close to the map size: most taps out of range
+    (1, 5, 7, 8, 2, False, True),
+]
+
+
+@pytest.mark.parametrize("spec", DW_SPECS)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_dwconv3x3_fwd_bwd(spec, dtype):
+    B, H, W, C, dil, gelu, has_bias = spec
+    torch.manual_seed(sum(spec[:5]))
+    x = torch.randn(B, H, W, C, device=DEV).to(dtype)
+    w = (torch.randn(C, 1, 3, 3, device=DEV) * 0.4).requires_grad_(True)
+    b = (torch.randn(C, device=DEV) * 0.2).requires_grad_(True) if has_bias else None
+    gy = torch.randn(B, H, W, C, device=DEV).to(dtype)
+    xr = x.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    ref = F.conv2d(xr, w, b, padding=dil, dilation=dil, groups=C)
+    if gelu:
+        ref = F.gelu(ref)
+    ref.backward(gy.float().permute(0, 3, 1, 2))
+    gw_ref, gb_ref, gx_ref = w.grad.clone(), (b.grad.clone() if has_bias else None), xr.grad.permute(0, 2, 3, 1)
+    w.grad = None
+    if has_bias:
+        b.grad = None
+    xm = x.clone().requires_grad_(True)
+    if gelu:
+        out = ops.dwconv3x3_gelu(xm.view(B, H * W, C), H, W, w, b).view(B, H, W, C)
+    else:
+        out = ops.dwconv3x3_nhwc(xm.permute(0, 3, 1, 2), w, b, dil).permute(0, 2, 3, 1)
+    assert out.dtype == dtype
+    out.backward(gy)
+    if dtype == torch.float32:
+        rt, at = 1e-3, 1e-5
+    else:
+        rt, at = 2 * 2 ** -8, 2 * 2 ** -8
+    _close(out, ref.permute(0, 2, 3, 1), rt, at, "forward")
+    _close(xm.grad, gx_ref, rt, at * 4, "grad_input")
+    # weight / bias gradients are fp32 sums over B*H*W terms; with bf16 I/O the GELU pre-pass stores a
+    # bf16-rounded gradient, so the sums carry ~2^-9 relative noise per term
+    scale = float(gw_ref.abs().max())
+    _close(w.grad, gw_ref, rt, (1e-4 if dtype == torch.float32 else 2e-2) * max(scale, 1.0), "grad_weight")
+    if has_bias:
+        _close(b.grad, gb_ref, rt, (1e-4 if dtype == torch.float32 else 2e-2) * max(float(gb_ref.abs().max()), 1.0),
+               "grad_bias")
+
+
+def test_dwconv_rejects_bad_channels():
+    x = torch.randn(1, 4, 4, 12, device=DEV)
+    w = torch.randn(12, 1, 3, 3, device=DEV)
+    with pytest.raises(RuntimeError):
+        ops.dwconv3x3_nhwc(x.permute(0, 3, 1, 2), w, None, 1)
+
+
+LN_SPECS = [  # B, N, C, with_branch, with_scale
+    (2, 50, 64, False, False),
+    (2, 33, 128, True, True),
+    (3, 17, 320, True, False),
+    (2, 40, 512, True, True),
+    (2, 9, 32, True, True),       # generic (C % 64 != 0) path: mit_b0 widths
+    (1, 7, 160, False, False),
+    (2, 5, 256, True, False),
+]
+
+
+@pytest.mark.parametrize("spec", LN_SPECS)
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_add_layernorm_fwd_bwd(spec, mode):
+    B, N, C, with_branch, with_scale = spec
+    torch.manual_seed(B * 1000 + N * 10 + C)
+    ln = torch.nn.LayerNorm(C, eps=1e-6).to(DEV)
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5)
+        ln.bias.uniform_(-0.5, 0.5)
+    bdt = torch.bfloat16 if mode == "bf16" else torch.float32
+    ydt = bdt
+    x = (torch.randn(B, N, C, device=DEV) * 2 + 0.3).requires_grad_(True)
+    br = torch.randn(B, N, C, device=DEV).to(bdt).requires_grad_(True) if with_branch else None
+    sc = (torch.rand(B, device=DEV) > 0.3).float() / 0.7 if with_scale else None
+    gy = torch.randn(B, N, C, device=DEV).to(ydt)
+    gxn = torch.randn(B, N, C, device=DEV)
+    # reference in fp32 on the same (rounded) inputs
+    xr = x.detach().clone().requires_grad_(True)
+    brr = br.detach().float().clone().requires_grad_(True) if with_branch else None
+    xn_r = xr if not with_branch else xr + (brr if sc is None else brr * sc.view(-1, 1, 1))
+    y_r = F.layer_norm(xn_r, (C,), ln.weight, ln.bias, ln.eps)
+    loss_r = (y_r * gy.float()).sum() + ((xn_r * gxn).sum() if with_branch else 0)
+    loss_r.backward()
+    ref_g = (ln.weight.grad.clone(), ln.bias.grad.clone())
+    ln.weight.grad = ln.bias.grad = None
+    if with_branch:
+        xn, y = ops.add_layer_norm(x, br, sc, ln, out_dtype=ydt)
+        ((y * gy).sum() + (xn * gxn).sum()).backward()
+        _close(xn, xn_r, 1e-6, 1e-6, "xn")
+    else:
+        y = ops.layer_norm(x, ln, out_dtype=ydt)
+        (y * gy).sum().backward()
+    assert y.dtype == ydt
+    rt, at = (1e-3, 1e-4) if mode == "fp32" else (2 * 2 ** -8, 2 * 2 ** -8)
+    _close(y, y_r, rt, at, "y")
+    _close(x.grad, xr.grad, 1e-3, 1e-3 if mode == "fp32" else 2e-2, "dx")
+    if with_branch:
+        _close(br.grad, brr.grad, rt, 1e-3 if mode == "fp32" else 3e-2, "dbranch")
+    _close(ln.weight.grad, ref_g[0], 1e-3, 1e-3 * max(1.0, float(ref_g[0].abs().max())), "dgamma")
+    _close(ln.bias.grad, ref_g[1], 1e-3, 1e-3 * max(1.0, float(ref_g[1].abs().max())), "dbeta")
+
+
+AT_SPECS = [  # B, heads, N, M
+    (1, 1, 128, 128),       # one tile, one chunk
+    (2, 2, 256, 256),       # 512x512 input shapes: M = 256
+    (1, 5, 200, 256),       # ragged query tile
+    (2, 1, 384, 1024),      # 1024x1024 input shapes: M = 1024 (8 chunks)
+    (1, 8, 1024, 1024),     # stage-4 shape at 1024x1024
+    (1, 2, 130, 72),        # ragged key chunk (masking) + ragged query tile
+    (1, 1, 64, 320),        # N < tile, M not a multiple of the chunk
+]
+
+
+def _attention_ref(q, kv, heads, scale):
+    B, N, C = q.shape
+    M = kv.shape[1]
+    d = C // heads
+    q4 = q.float().view(B, N, heads, d).transpose(1, 2)
+    k4 = kv[..., :C].float().reshape(B, M, heads, d).transpose(1, 2)
+    v4 = kv[..., C:].float().reshape(B, M, heads, d).transpose(1, 2)
+    s = (q4 @ k4.transpose(-2, -1)) * scale
+    p = torch.softmax(s, dim=-1)
+    return (p @ v4).transpose(1, 2).reshape(B, N, C), torch.logsumexp(s, dim=-1)
+
+
+@pytest.mark.parametrize("spec", AT_SPECS)
+def test_sr_attention_fwd(spec):
+    """bf16 operands, fp32 accumulation; P is rounded to bf16 before the PV product (as every
+    flash-attention kernel does) and the output is stored in bf16 -> tolerance 2^-7 relative to the
+    output scale; the fp32 log-sum-exp is held to 1e-3."""
+    B, heads, N, M = spec
+    torch.manual_seed(B + heads * 10 + N + M)
+    C = heads * 64
+    q = (torch.randn(B, N, C, device=DEV) * 1.5).bfloat16()
+    kv = (torch.randn(B, M, 2 * C, device=DEV) * 1.5).bfloat16()
+    scale = 0.125
+    out, lse = ops.sr_attention_fwd(q, kv, heads, scale, want_lse=True)
+    ref, lse_ref = _attention_ref(q, kv, heads, scale)
+    assert out.dtype == torch.bfloat16 and out.shape == q.shape
+    _close(lse, lse_ref, 1e-3, 1e-3, "lse")
+    _close(out, ref, 2 ** -7, 2 ** -7 * float(ref.abs().max()), "out")
+
+
+def test_sr_attention_autograd_matches_library():
+    torch.manual_seed(5)
+    B, heads, N, M, C = 2, 2, 256, 256, 128
+    q = (torch.randn(B, N, C, device=DEV)).bfloat16().requires_grad_(True)
+    kv = (torch.randn(B, M, 2 * C, device=DEV)).bfloat16().requires_grad_(True)
+    go = torch.randn(B, N, C, device=DEV).bfloat16()
+    ops.sr_attention(q, kv, heads, 0.125).backward(go)
+    gq, gkv = q.grad.clone(), kv.grad.clone()
+    q.grad = kv.grad = None
+    ops._sr_attention_library(q, kv, heads, 0.125).backward(go)
+    _close(gq, q.grad, 2 ** -6, 2 ** -6 * float(q.grad.abs().max()), "dq")
+    _close(gkv, kv.grad, 2 ** -6, 2 ** -6 * float(kv.grad.abs().max()), "dkv")

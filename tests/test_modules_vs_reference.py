@@ -14,6 +14,13 @@ import torch
 import refshim
 from cpu_ops import cpu_ops
 
+
+@pytest.fixture(autouse=True)
+def _cpu_operator_layer():
+    """Every test of this module runs the host-side modules on CPU: route refign_b200.ops to the oracle."""
+    with cpu_ops():
+        yield
+
 pytestmark = pytest.mark.needs_reference
 
 

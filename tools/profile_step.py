@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "step_profile.json"))
     ap.add_argument("--top", type=int, default=60)
+    ap.add_argument("--ops", action="store_true", help="also list the top aten ops by device time with shapes + source line")
     args = ap.parse_args()
     import torch
     from torch.profiler import ProfilerActivity, profile
@@ -38,7 +39,8 @@ def main():
     t_host = time.perf_counter() - t0
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t0
-    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=args.ops,
+                 with_stack=args.ops) as prof:
         model.training_step(batch, 4)
         torch.cuda.synchronize()
     rows = []
@@ -60,6 +62,16 @@ def main():
     print(json.dumps({k: v for k, v in out.items() if k != "top"}))
     for r in out["top"][:40]:
         print("%8.3f ms %5.1f%% x%-5d %s" % (r["ms"], 100 * r["share"], r["calls"], r["kernel"][:110]))
+
+
+    if args.ops:
+        ev = [e for e in prof.key_averages(group_by_input_shape=True, group_by_stack_n=6)
+              if getattr(e, "self_device_time_total", 0) > 0 and e.device_type.name != "CUDA"]
+        ev.sort(key=lambda e: -e.self_device_time_total)
+        for e in ev[:45]:
+            stack = [l for l in (e.stack or []) if "refign_b200" in l or "bench.py" in l]
+            print("%8.3f ms x%-5d %-28s %s | %s" % (e.self_device_time_total / 1e3, e.count, e.key[:28],
+                                                  str(e.input_shapes)[:90], (stack[0].split("/")[-1] if stack else "")[:70]))
 
 
 if __name__ == "__main__":
