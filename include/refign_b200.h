@@ -39,6 +39,10 @@ extern "C" {
 const char* rf_last_error(void);
 int rf_version(void);                 /* ABI version, currently 1         */
 int rf_device_check(void);            /* RF_OK iff current device is sm_100 */
+/* Bind `device` to the calling host thread for this library (it links the CUDA
+ * runtime statically, so its per-thread current device is its own).  Call once
+ * per host thread that uses the library -- the Python binding does it. */
+int rf_set_device(int device);
 
 /* ---- local (windowed) correlation ------------------------------------- */
 /* Replaces correlation.forward (correlation_sampler.cpp:62-90 ->
@@ -181,6 +185,17 @@ int rf_dwconv3x3_nhwc_bwd_weight(const void* x, const void* grad_pre, float* gra
  * The [B,heads,N,M] attention matrix is never written to memory. */
 int rf_sr_attention_fwd(const void* q, const void* kv, void* out, float* lse, int B, int N,
                         int M, int heads, float scale, void* stream);
+
+/* Backward of the above (autograd of mix_transformer.py:150-160) with the probabilities recomputed
+ * from q, k and the forward's lse:
+ *   out, grad_out, grad_q : bf16 [B,N,heads*64];  lse : f32 [B,heads,N] (from the forward)
+ *   grad_kv_f32 : f32 [B,M,2*heads*64]  (dK | dV; zeroed by the call, query splits are combined with
+ *                 fp32 atomics; the caller rounds it to the kv dtype)
+ *   workspace   : rf_sr_attention_bwd_workspace_bytes() bytes of scratch */
+int64_t rf_sr_attention_bwd_workspace_bytes(int B, int N, int M, int heads);
+int rf_sr_attention_bwd(const void* q, const void* kv, const void* out, const void* grad_out,
+                        const float* lse, void* grad_q, float* grad_kv_f32, void* workspace,
+                        int B, int N, int M, int heads, float scale, void* stream);
 
 /* ---- residual add + LayerNorm ------------------------------------------- */
 /* Replaces the LayerNorms of the MiT encoder and the residual adds in front of

@@ -19,6 +19,7 @@ _SIGNATURES = {
     "rf_last_error": (ctypes.c_char_p, []),
     "rf_version": (c_int, []),
     "rf_device_check": (c_int, []),
+    "rf_set_device": (c_int, [c_int]),
     "rf_local_corr_fwd": (c_int, [c_p, c_p, c_p, c_p] + [c_int] * 16 + [c_int, c_p]),
     "rf_local_corr_bwd_scratch_bytes": (c_i64, [c_int] * 16),
     "rf_local_corr_bwd": (c_int, [c_p] * 6 + [c_int] * 16 + [c_p]),
@@ -37,6 +38,8 @@ _SIGNATURES = {
     "rf_add_layernorm_fwd": (c_int, [c_p] * 9 + [c_i64, c_int, c_i64, c_f32, c_int, c_int, c_int, c_p]),
     "rf_add_layernorm_bwd": (c_int, [c_p] * 11 + [c_i64, c_int, c_i64, c_int, c_int, c_int, c_p]),
     "rf_sr_attention_fwd": (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_f32, c_p]),
+    "rf_sr_attention_bwd_workspace_bytes": (c_i64, [c_int, c_int, c_int, c_int]),
+    "rf_sr_attention_bwd": (c_int, [c_p] * 8 + [c_int, c_int, c_int, c_int, c_f32, c_p]),
     "rf_ema_update": (c_int, [c_p, c_p, c_i64, ctypes.c_double, c_p]),
     "rf_adamw_step": (c_int, [c_p, c_p, c_p, c_p, c_i64, c_int, ctypes.POINTER(c_i64),
                               ctypes.POINTER(c_f32), ctypes.POINTER(c_f32), c_f32, c_f32, c_f32,

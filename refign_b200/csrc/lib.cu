@@ -28,3 +28,17 @@ extern "C" int rf_device_check(void) {
   }
   return RF_OK;
 }
+
+// Binds `device` (and its primary context) to the calling host thread for this library's CUDA runtime
+// instance.  The library links cudart statically, so its per-thread current device is separate from
+// the caller's runtime (e.g. torch's): a fresh thread -- autograd's backward worker -- would otherwise
+// default to device 0 and have no context current for driver-API calls (cuTensorMapEncodeTiled).
+extern "C" int rf_set_device(int device) {
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaFree(nullptr);
+  if (e != cudaSuccess) {
+    rf::set_error("rf_set_device(%d): %s", device, cudaGetErrorString(e));
+    return RF_ECUDA;
+  }
+  return RF_OK;
+}

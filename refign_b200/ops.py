@@ -6,6 +6,7 @@ stream.  Tensors are allocated by torch; only raw pointers cross the boundary.
 CUDA only -- no CPU implementation, no fallback.
 """
 import ctypes
+import threading
 
 import torch
 from torch.nn.modules.utils import _pair
@@ -51,9 +52,17 @@ def set_timer(timer):
     return prev
 
 
+_TLS = threading.local()
+
+
 def _run(name, *args, work=None, tag=None):
     """Launch one C-ABI entry point on the current stream and raise on a non-zero status."""
-    fn = getattr(_lib.lib(), name)
+    L = _lib.lib()
+    dev = torch.cuda.current_device()
+    if getattr(_TLS, "dev", None) != dev:   # once per host thread (autograd's backward worker included)
+        check(L.rf_set_device(dev), "rf_set_device")
+        _TLS.dev = dev
+    fn = getattr(L, name)
     t = _TIMER
     if t is None:
         rc = fn(*args)
@@ -412,38 +421,40 @@ def sr_attention_fwd(q, kv, heads, scale, want_lse=False):
 
 
 class _SrAttentionFunction(torch.autograd.Function):
-    """Fused forward (no [B,h,N,M] matrix in HBM, nothing but q / kv saved).  The backward re-forms
-    the probabilities per call with library GEMMs from the saved q / kv (flash-style recompute);
-    a fused tcgen05 backward is the next step."""
+    """Fused tcgen05 forward and backward: the [B,h,N,M] matrix never exists in HBM; saved for the
+    backward are q, kv, the output (which the following projection keeps alive anyway) and the fp32
+    log-sum-exp [B,h,N]."""
 
     @staticmethod
     def forward(ctx, q, kv, heads, scale):
-        out, _ = sr_attention_fwd(q, kv, heads, scale)
-        ctx.save_for_backward(q, kv)
-        ctx.cfg = (heads, scale)
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        q, kv = q.contiguous(), kv.contiguous()
+        out, lse = sr_attention_fwd(q, kv, heads, scale, want_lse=need)
+        if need:
+            ctx.save_for_backward(q, kv, out, lse)
+            ctx.cfg = (heads, scale)
         return out
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, go):
-        q, kv = ctx.saved_tensors
+        q, kv, out, lse = ctx.saved_tensors
         heads, scale = ctx.cfg
         B, N, C = q.shape
         M = kv.shape[1]
-        d = C // heads
-        q4 = q.view(B, N, heads, d).transpose(1, 2)
-        k4 = kv[..., :C].reshape(B, M, heads, d).transpose(1, 2)
-        v4 = kv[..., C:].reshape(B, M, heads, d).transpose(1, 2)
-        g4 = go.reshape(B, N, heads, d).transpose(1, 2).to(q.dtype)
-        p = torch.softmax((q4 @ k4.transpose(-2, -1)).float() * scale, dim=-1)
-        pb = p.to(q.dtype)
-        dv = pb.transpose(-2, -1) @ g4
-        dp = (g4 @ v4.transpose(-2, -1)).float()
-        ds = (p * (dp - (dp * p).sum(-1, keepdim=True)) * scale).to(q.dtype)
-        dq = (ds @ k4).transpose(1, 2).reshape(B, N, C)
-        dk = (ds.transpose(-2, -1) @ q4).transpose(1, 2).reshape(B, M, C)
-        dkv = torch.cat([dk, dv.transpose(1, 2).reshape(B, M, C)], dim=-1)
-        return dq, dkv, None, None
+        go = go.contiguous()
+        if go.dtype != q.dtype:
+            go = go.to(q.dtype)
+        dq = torch.empty_like(q)
+        dkv = torch.empty(B, M, 2 * C, device=q.device, dtype=torch.float32)
+        L = _lib.lib()
+        ws = torch.empty(L.rf_sr_attention_bwd_workspace_bytes(B, N, M, heads) // 4, device=q.device,
+                         dtype=torch.float32)
+        with torch.cuda.device(q.device):
+            _run("rf_sr_attention_bwd", ptr(q), ptr(kv), ptr(out), ptr(go), ptr(lse), ptr(dq), ptr(dkv), ptr(ws), B, N,
+                 M, heads, float(scale), _stream(),
+                 work=(2 * (4 * q.numel() + 2 * kv.numel()), 14 * B * heads * N * M * 64), tag="sr_attention_bwd")
+        return dq, dkv.to(kv.dtype), None, None
 
 
 def _dt_code(t):

@@ -175,15 +175,25 @@ def test_sr_attention_fwd(spec):
     _close(out, ref, 2 ** -7, 2 ** -7 * float(ref.abs().max()), "out")
 
 
-def test_sr_attention_autograd_matches_library():
-    torch.manual_seed(5)
-    B, heads, N, M, C = 2, 2, 256, 256, 128
-    q = (torch.randn(B, N, C, device=DEV)).bfloat16().requires_grad_(True)
-    kv = (torch.randn(B, M, 2 * C, device=DEV)).bfloat16().requires_grad_(True)
+@pytest.mark.parametrize("spec", AT_SPECS)
+def test_sr_attention_bwd(spec):
+    """Fused backward (P recomputed from q, k and the fp32 LSE) against autograd of the fp32 reference on
+    the same bf16 inputs.  dS is rounded to bf16 before its two products and the gradients are stored in
+    bf16: tolerance 2^-6 relative to the gradient scale."""
+    B, heads, N, M = spec
+    torch.manual_seed(B + heads * 10 + N + M + 1)
+    C = heads * 64
+    q = torch.randn(B, N, C, device=DEV).bfloat16().requires_grad_(True)
+    kv = torch.randn(B, M, 2 * C, device=DEV).bfloat16().requires_grad_(True)
     go = torch.randn(B, N, C, device=DEV).bfloat16()
-    ops.sr_attention(q, kv, heads, 0.125).backward(go)
+    out = ops.sr_attention(q, kv, heads, 0.125)
+    out.backward(go)
     gq, gkv = q.grad.clone(), kv.grad.clone()
     q.grad = kv.grad = None
-    ops._sr_attention_library(q, kv, heads, 0.125).backward(go)
-    _close(gq, q.grad, 2 ** -6, 2 ** -6 * float(q.grad.abs().max()), "dq")
-    _close(gkv, kv.grad, 2 ** -6, 2 ** -6 * float(kv.grad.abs().max()), "dkv")
+    qr = q.detach().float().requires_grad_(True)
+    kvr = kv.detach().float().requires_grad_(True)
+    ref, _ = _attention_ref(qr, kvr, heads, 0.125)
+    ref.backward(go.float())
+    _close(gq, qr.grad, 2 ** -6, 2 ** -6 * float(qr.grad.abs().max()), "dq")
+    _close(gkv[..., :C], kvr.grad[..., :C], 2 ** -6, 2 ** -6 * float(kvr.grad[..., :C].abs().max()), "dk")
+    _close(gkv[..., C:], kvr.grad[..., C:], 2 ** -6, 2 ** -6 * float(kvr.grad[..., C:].abs().max()), "dv")

@@ -28,7 +28,13 @@ for size in (512, 1024):
         kv = torch.randn(B, M, 2 * C, device="cuda").bfloat16()
         ms = timeit(lambda: ops.sr_attention_fwd(q, kv, heads, 0.125))
         ms_lib = timeit(lambda: ops._sr_attention_library(q, kv, heads, 0.125))
+        qg = q.clone().requires_grad_(True); kvg = kv.clone().requires_grad_(True)
+        o = ops.sr_attention(qg, kvg, heads, 0.125); go = torch.randn_like(o)
+        ms_bwd = timeit(lambda: torch.autograd.grad(o, (qg, kvg), go, retain_graph=True))
+        ol = ops._sr_attention_library(qg, kvg, heads, 0.125)
+        ms_bwd_lib = timeit(lambda: torch.autograd.grad(ol, (qg, kvg), go, retain_graph=True))
         fl = 4.0 * B * heads * N * M * 64
         print(json.dumps({"kernel": "sr_attention_fwd", "size": size, "stage": stage + 1, "B": B, "N": N, "M": M, "heads": heads,
                           "us": round(ms * 1e3, 1), "TFLOPs": round(fl / ms / 1e9, 1), "frac_of_bf16_peak": round(fl / ms / 1e9 / peak, 4),
-                          "library_us": round(ms_lib * 1e3, 1)}))
+                          "library_us": round(ms_lib * 1e3, 1),
+                          "bwd_us": round(ms_bwd * 1e3, 1), "bwd_TFLOPs": round(3.5 * fl / ms_bwd / 1e9, 1), "bwd_library_us": round(ms_bwd_lib * 1e3, 1)}))
