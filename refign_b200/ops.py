@@ -52,6 +52,8 @@ def set_timer(timer):
     return prev
 
 
+# kernels launched per C-ABI call (memsets not counted), for bench.py's gpu_launches figure
+KERNELS_PER_CALL = {"rf_refine_fwd": 3, "rf_sr_attention_bwd": 2, "rf_global_corr_fwd": 3}
 _TLS = threading.local()
 
 
@@ -72,7 +74,7 @@ def _run(name, *args, work=None, tag=None):
         rc = fn(*args)
         e1.record()
         t.records.append((tag or name, e0, e1, work))
-        t.launches += 1
+        t.launches += KERNELS_PER_CALL.get(name, 1)
     check(rc, name)
 
 
