@@ -243,6 +243,16 @@ int rf_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_av
                   const float* seg_wd, float beta1, float beta2, float eps, int step,
                   float grad_scale, void* stream);
 
+/* CUDA-graph friendly variants: the step-dependent scalars are read from a DEVICE block
+ *   hyper[0..7] = per-segment learning rate, hyper[8] = 1 - beta1^t, hyper[9] = sqrt(1 - beta2^t),
+ *   hyper[10] = EMA momentum m, hyper[11] = 1 - m   (all f32, written by the host before the replay)
+ * so that a captured train step can be replayed while the schedule advances. */
+int rf_ema_update_dev(float* ema, const float* live, int64_t n, const float* hyper, void* stream);
+int rf_adamw_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                      int64_t n, int nseg, const int64_t* seg_end, const float* seg_wd,
+                      float beta1, float beta2, float eps, float grad_scale, const float* hyper,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

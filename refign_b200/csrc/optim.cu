@@ -12,7 +12,12 @@
 namespace rf {
 
 __global__ void __launch_bounds__(256)
-ema_kernel(float* __restrict__ ema, const float* __restrict__ live, long n, float m, float om) {
+ema_kernel(float* __restrict__ ema, const float* __restrict__ live, long n, float m, float om,
+           const float* __restrict__ hyper) {
+  if (hyper != nullptr) {  // step-dependent scalars from device memory (CUDA-graph replay)
+    m = __ldg(hyper + 10);
+    om = __ldg(hyper + 11);
+  }
   const long n4 = n >> 2;
   float4* e4 = reinterpret_cast<float4*>(ema);
   const float4* l4 = reinterpret_cast<const float4*>(live);
@@ -43,7 +48,14 @@ struct AdamSegs {
 //   p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-             long n, AdamSegs segs, float b1, float b2, float eps, float bc1, float sqrt_bc2, float gscale) {
+             long n, AdamSegs segs, float b1, float b2, float eps, float bc1, float sqrt_bc2, float gscale,
+             const float* __restrict__ hyper) {
+  if (hyper != nullptr) {  // per-segment lr and the bias corrections from device memory (CUDA-graph replay)
+#pragma unroll
+    for (int k = 0; k < ADAM_MAX_SEG; ++k) segs.lr[k] = __ldg(hyper + k);
+    bc1 = __ldg(hyper + 8);
+    sqrt_bc2 = __ldg(hyper + 9);
+  }
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     int s = 0;
 #pragma unroll
@@ -65,19 +77,29 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
 
 using namespace rf;
 
-extern "C" int rf_ema_update(float* ema, const float* live, int64_t n, double momentum, void* stream) {
+static int ema_launch(float* ema, const float* live, int64_t n, double momentum, const float* hyper, void* stream) {
   RF_REQUIRE(ema && live && n > 0, "rf_ema_update: bad argument");
   RF_REQUIRE((((uintptr_t)ema | (uintptr_t)live) & 15) == 0, "rf_ema_update: buffers must be 16-byte aligned");
   long blocks = ceil_div(n / 4 + 1, 256);
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  ema_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(ema, live, n, (float)momentum, (float)(1.0 - momentum));
+  ema_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(ema, live, n, (float)momentum, (float)(1.0 - momentum),
+                                                            hyper);
   RF_CHECK_LAUNCH("ema_kernel");
   return RF_OK;
 }
 
-extern "C" int rf_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, int nseg,
-                             const int64_t* seg_end, const float* seg_lr, const float* seg_wd, float beta1,
-                             float beta2, float eps, int step, float grad_scale, void* stream) {
+extern "C" int rf_ema_update(float* ema, const float* live, int64_t n, double momentum, void* stream) {
+  return ema_launch(ema, live, n, momentum, nullptr, stream);
+}
+
+extern "C" int rf_ema_update_dev(float* ema, const float* live, int64_t n, const float* hyper, void* stream) {
+  RF_REQUIRE(hyper != nullptr, "rf_ema_update_dev: null hyper-parameter block");
+  return ema_launch(ema, live, n, 0.0, hyper, stream);
+}
+
+static int adamw_launch(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, int nseg,
+                        const int64_t* seg_end, const float* seg_lr, const float* seg_wd, float beta1, float beta2,
+                        float eps, int step, float grad_scale, const float* hyper, void* stream) {
   RF_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0, "rf_adamw_step: bad argument");
   RF_REQUIRE(nseg >= 1 && nseg <= ADAM_MAX_SEG && seg_end && seg_lr && seg_wd, "rf_adamw_step: 1..%d segments", ADAM_MAX_SEG);
   RF_REQUIRE(step >= 1, "rf_adamw_step: step counts from 1");
@@ -93,7 +115,23 @@ extern "C" int rf_adamw_step(float* param, const float* grad, float* exp_avg, fl
   long blocks = ceil_div(n, 256);
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
   adamw_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, segs, beta1, beta2, eps,
-                                                              (float)bc1, (float)sqrt(bc2), grad_scale);
+                                                              (float)bc1, (float)sqrt(bc2), grad_scale, hyper);
   RF_CHECK_LAUNCH("adamw_kernel");
   return RF_OK;
+}
+
+extern "C" int rf_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, int nseg,
+                             const int64_t* seg_end, const float* seg_lr, const float* seg_wd, float beta1,
+                             float beta2, float eps, int step, float grad_scale, void* stream) {
+  return adamw_launch(param, grad, exp_avg, exp_avg_sq, n, nseg, seg_end, seg_lr, seg_wd, beta1, beta2, eps, step,
+                      grad_scale, nullptr, stream);
+}
+
+extern "C" int rf_adamw_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                 int nseg, const int64_t* seg_end, const float* seg_wd, float beta1, float beta2,
+                                 float eps, float grad_scale, const float* hyper, void* stream) {
+  RF_REQUIRE(hyper != nullptr, "rf_adamw_step_dev: null hyper-parameter block");
+  const float zero[ADAM_MAX_SEG] = {0, 0, 0, 0, 0, 0, 0, 0};
+  return adamw_launch(param, grad, exp_avg, exp_avg_sq, n, nseg, seg_end, zero, seg_wd, beta1, beta2, eps, 1,
+                      grad_scale, hyper, stream);
 }

@@ -128,8 +128,11 @@ def _up(x, size):
 
 
 def _scale_flow(flow, sx, sy):
-    """flow * (sx, sy) per channel without the reference's in-place clone dance."""
-    return flow * flow.new_tensor([sx, sy]).view(1, 2, 1, 1)
+    """flow * (sx, sy) per channel without the reference's in-place clone dance (and without a
+    host->device tensor creation, which a CUDA-graph capture of the step would not allow)."""
+    if sx == sy:
+        return flow * sx
+    return torch.cat((flow[:, 0:1] * sx, flow[:, 1:2] * sy), dim=1)
 
 
 class UAWarpCHead(BaseHead):

@@ -371,6 +371,32 @@ def adamw_step_(param, grad, exp_avg, exp_avg_sq, seg_end, seg_lr, seg_wd, beta1
     return param
 
 
+@torch.no_grad()
+def ema_update_dev_(ema_flat, live_flat, hyper):
+    """EMA update with the momentum read from the device block ``hyper`` (CUDA-graph replay)."""
+    require_cuda(ema_flat, live_flat, hyper)
+    assert ema_flat.dtype == live_flat.dtype == torch.float32 and ema_flat.numel() == live_flat.numel()
+    with torch.cuda.device(ema_flat.device):
+        _run("rf_ema_update_dev", ptr(ema_flat), ptr(live_flat), ema_flat.numel(), ptr(hyper), _stream(),
+             work=(12 * ema_flat.numel(), 0), tag="rf_ema_update")
+    return ema_flat
+
+
+@torch.no_grad()
+def adamw_step_dev_(param, grad, exp_avg, exp_avg_sq, seg_end, seg_wd, beta1, beta2, eps, hyper, grad_scale=1.0):
+    """AdamW step with lr / bias corrections read from the device block ``hyper`` (CUDA-graph replay)."""
+    require_cuda(param, grad, exp_avg, exp_avg_sq, hyper)
+    n = param.numel()
+    k = len(seg_end)
+    ends = (ctypes.c_int64 * k)(*[int(e) for e in seg_end])
+    wds = (ctypes.c_float * k)(*[float(v) for v in seg_wd])
+    with torch.cuda.device(param.device):
+        _run("rf_adamw_step_dev", ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), n, k, ends, wds,
+             float(beta1), float(beta2), float(eps), float(grad_scale), ptr(hyper), _stream(), work=(28 * n, 0),
+             tag="rf_adamw_step")
+    return param
+
+
 # --------------------------------------------------------------------------
 # MiT operators (reference: models/backbones/mix_transformer.py)
 # --------------------------------------------------------------------------

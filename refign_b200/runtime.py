@@ -78,6 +78,7 @@ class FlatAdamW:
         self.exp_avg_sq = torch.zeros_like(flat.data)
         self.step_count = 0
         self.group, self.world_size = process_group, world_size
+        self.hyper = None          # device block of step-dependent scalars (enable_device_hyper)
 
     def zero_grad(self, set_to_none=False):
         self.flat.rebind_grads()
@@ -88,12 +89,40 @@ class FlatAdamW:
         if self.world_size > 1:
             dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM, group=self.group)
 
-    def step(self):
+    def enable_device_hyper(self):
+        """Keep the step-dependent scalars (per-segment lr, Adam bias corrections, EMA momentum) in a
+        12-float device block so that a captured step can be replayed while the schedule advances."""
+        if self.hyper is None:
+            self.hyper = torch.zeros(12, dtype=torch.float32, device=self.flat.data.device)
+            self._hyper_host = torch.zeros(12, dtype=torch.float32).pin_memory()
+
+    def upload_hyper(self, ema_m):
+        """Host -> device copy of the scalars of the step about to run (async, pinned)."""
+        h = self._hyper_host
+        t = self.step_count + 1
+        for i, lr in enumerate(self.seg_lr):
+            h[i] = lr
+        h[8] = 1.0 - self.betas[0] ** t
+        h[9] = (1.0 - self.betas[1] ** t) ** 0.5
+        h[10] = ema_m
+        h[11] = 1.0 - ema_m
+        self.hyper.copy_(h, non_blocking=True)
+
+    def launch_step(self):
+        """Device work of one optimiser step (all-reduce + AdamW kernel), no host bookkeeping."""
         self.all_reduce_grads()
+        if self.hyper is not None:
+            ops.adamw_step_dev_(self.flat.data, self.flat.grad, self.exp_avg, self.exp_avg_sq, self.seg_end,
+                                self.seg_wd, self.betas[0], self.betas[1], self.eps, self.hyper,
+                                grad_scale=1.0 / self.world_size)
+        else:
+            ops.adamw_step_(self.flat.data, self.flat.grad, self.exp_avg, self.exp_avg_sq, self.seg_end, self.seg_lr,
+                            self.seg_wd, self.betas[0], self.betas[1], self.eps, self.step_count + 1,
+                            grad_scale=1.0 / self.world_size)
+
+    def step(self):
+        self.launch_step()
         self.step_count += 1
-        ops.adamw_step_(self.flat.data, self.flat.grad, self.exp_avg, self.exp_avg_sq, self.seg_end, self.seg_lr,
-                        self.seg_wd, self.betas[0], self.betas[1], self.eps, self.step_count,
-                        grad_scale=1.0 / self.world_size)
 
 
 class PolyLRSchedule:

@@ -129,6 +129,7 @@ class DomainAdaptationSegmentationModel(_Base):
         self._step = 0
         self._logged = {}
         self._fused_pseudo = None             # (probs tensor, label, maxprob) handed from refine to get_dacs_mix
+        self._graphs = None                   # CUDA-graph state installed by enable_cuda_graphs()
         self.load_weights(pretrained)
 
     # ---- what Lightning would provide ---------------------------------------------------------------
@@ -201,9 +202,24 @@ class DomainAdaptationSegmentationModel(_Base):
         """One Refign UDA step (reference segmentation_model.py:146-253): EMA update, source CE
         (+ ImageNet feature distance), teacher + align + refine -> pseudo-label, DACS mix, mixed CE,
         optimiser step.  Three backward passes accumulate into the flat gradient buffer; the single
-        gradient all-reduce happens inside ``opt.step()``."""
+        gradient all-reduce happens inside ``opt.step()``.  With ``enable_cuda_graphs()`` the two
+        device-heavy parts are replayed as CUDA graphs (see ``_training_step_graphed``)."""
+        if self._graphs is not None:
+            return self._training_step_graphed(batch, batch_idx)
         opt = self.optimizers()
         sch = self.lr_schedulers()
+        target = self._step_part_a(batch, opt)
+        mixed = self.get_dacs_mix(target['images_trg'], target['probs'], batch['image_src'], batch['semantic_src'],
+                                  fused=target['fused'])
+        self._step_part_b(mixed, opt)
+        opt.step()
+        sch.step()
+        if not _HAVE_PL:
+            self._step += 1
+
+    def _step_part_a(self, batch, opt):
+        """zero_grad, EMA update, source forward/backward (+ feature distance), teacher forward on
+        target + reference, align, warp, refine.  Returns what the DACS mix needs."""
         opt.zero_grad()
         self.update_momentum_encoder()
 
@@ -228,6 +244,7 @@ class DomainAdaptationSegmentationModel(_Base):
         del feats_src
 
         # ---- target (no grad) ------------------------------------------------------------------
+        self._fused_pseudo = None
         with torch.no_grad(), self._autocast():
             if self.adapt_to_ref and random.random() < 0.5:
                 adapt_to_ref, images_trg = True, batch['image_ref']
@@ -252,9 +269,12 @@ class DomainAdaptationSegmentationModel(_Base):
                 m_logits_trg = F.interpolate(m_logits_trg.float(), size=images_trg.shape[-2:], mode='bilinear',
                                              align_corners=False)
                 m_probs_trg = F.softmax(m_logits_trg, dim=1)
-            mixed_img, mixed_lbl, mixed_weight = self.get_dacs_mix(images_trg, m_probs_trg, images_src, gt_src)
+        fused, self._fused_pseudo = self._fused_pseudo, None
+        return {'images_trg': images_trg, 'probs': m_probs_trg, 'fused': fused}
 
-        # ---- mixed -----------------------------------------------------------------------------
+    def _step_part_b(self, mixed, opt):
+        """Student forward/backward on the class-mixed images (the third backward pass)."""
+        mixed_img, mixed_lbl, mixed_weight = mixed
         with self._autocast():
             mixed_pred = self.head(self.backbone(mixed_img))
             mixed_pred = F.interpolate(mixed_pred.float(), mixed_img.shape[-2:], mode='bilinear',
@@ -264,8 +284,61 @@ class DomainAdaptationSegmentationModel(_Base):
         self.manual_backward(mixed_loss)
         del mixed_loss, mixed_pred
 
-        opt.step()
+    # ---- CUDA-graph replay of the step -------------------------------------------------------------
+    def enable_cuda_graphs(self, warmup=3):
+        """Replay the step as two CUDA graphs (B200: the eager step issues ~20 k launches and is bound
+        by the host).  Graph A = zero_grad .. refine, graph B = mixed forward/backward + all-reduce +
+        AdamW; the DACS mix between them (host-side random augmentation parameters) stays eager.
+        Requires the flat-buffer runtime, static shapes and ``adapt_to_ref=False``."""
+        assert self._rt is not None, "call setup_runtime() first"
+        assert not self.adapt_to_ref, "the adapt_to_ref coin changes the control flow per step"
+        self._rt['opt'].enable_device_hyper()
+        self._graphs = {'n': 0, 'warmup': int(warmup), 'a': None, 'b': None, 'batch': None, 'mixed': None,
+                        'out_a': None}
+
+    def _training_step_graphed(self, batch, batch_idx):
+        G = self._graphs
+        opt, sch = self.optimizers(), self.lr_schedulers()
+        if G['batch'] is None:
+            G['batch'] = {k: torch.empty_like(v, device=self.device) for k, v in batch.items()}
+        for k, v in batch.items():
+            G['batch'][k].copy_(v, non_blocking=True)
+        sb = G['batch']
+        # step-dependent scalars (lr, Adam bias corrections, EMA momentum) -> device block read by the kernels
+        opt.upload_hyper(runtime.ema_momentum(self.global_step, self.ema_momentum))
+
+        def dacs(out):
+            mixed = self.get_dacs_mix(out['images_trg'], out['probs'], sb['image_src'], sb['semantic_src'],
+                                      fused=out['fused'])
+            if G['mixed'] is None:
+                G['mixed'] = tuple(t.clone() for t in mixed)
+            else:
+                for dst, src in zip(G['mixed'], mixed):
+                    dst.copy_(src)
+            return G['mixed']
+
+        if G['n'] < G['warmup']:
+            self._step_part_b(dacs(self._step_part_a(sb, opt)), opt)
+            opt.launch_step()
+        elif G['a'] is None:
+            torch.cuda.synchronize()
+            G['a'] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(G['a']):
+                G['out_a'] = self._step_part_a(sb, opt)
+            G['a'].replay()
+            mixed = dacs(G['out_a'])
+            G['b'] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(G['b'], pool=G['a'].pool()):
+                self._step_part_b(mixed, opt)
+                opt.launch_step()
+            G['b'].replay()
+        else:
+            G['a'].replay()
+            dacs(G['out_a'])
+            G['b'].replay()
+        opt.step_count += 1
         sch.step()
+        G['n'] += 1
         if not _HAVE_PL:
             self._step += 1
 
@@ -341,13 +414,13 @@ class DomainAdaptationSegmentationModel(_Base):
 
     # ---- DACS mix (reference :525-582) -------------------------------------------------------------
     @torch.no_grad()
-    def get_dacs_mix(self, images_trg, probs_trg, images_src, gt_src):
+    def get_dacs_mix(self, images_trg, probs_trg, images_src, gt_src, fused=None):
         nt = images_trg.shape[0]
         if images_src.shape[0] > nt:
             images_src, gt_src = images_src[:nt], gt_src[:nt]
         strong = {'mix': None, 'color_jitter': random.uniform(0, 1), 'color_jitter_s': self.color_jitter_s,
                   'color_jitter_p': self.color_jitter_p, 'blur': random.uniform(0, 1) if self.blur else 0}
-        fp = self._fused_pseudo
+        fp = fused if fused is not None else self._fused_pseudo
         if fp is not None and fp[0] is probs_trg and fp[1] is not None:
             pseudo_label, pseudo_prob = fp[1], fp[2]
         else:
@@ -381,7 +454,9 @@ class DomainAdaptationSegmentationModel(_Base):
         lay = -1
         mask = None
         if self.fdist_classes is not None:
-            fdclasses = torch.tensor(self.fdist_classes, device=gt.device)
+            fdclasses = getattr(self, '_fdclasses', None)
+            if fdclasses is None or fdclasses.device != gt.device:   # cached: no H2D copy inside the step
+                fdclasses = self._fdclasses = torch.tensor(self.fdist_classes, device=gt.device)
             scale = gt.shape[-1] // feat[lay].shape[-1]
             gt_small = self.downscale_label_ratio(gt.unsqueeze(1), scale, self.fdist_scale_min_ratio,
                                                   self.head.num_classes, 255).long().detach()
@@ -425,7 +500,9 @@ class DomainAdaptationSegmentationModel(_Base):
         """theta_m <- m * theta_m + (1 - m) * theta, m = min(1 - 1/(step+1), ema_momentum)
         (reference :680-689) as ONE kernel over the flat buffers."""
         m = runtime.ema_momentum(self.global_step, self.ema_momentum)
-        if self._rt is not None:
+        if self._rt is not None and self._rt['opt'].hyper is not None:
+            ops.ema_update_dev_(self._rt['ema'].data, self._rt['live'].data, self._rt['opt'].hyper)
+        elif self._rt is not None:
             ops.ema_update_(self._rt['ema'].data, self._rt['live'].data, m)
         else:  # no runtime installed (e.g. under Lightning without setup_runtime): per-tensor kernel launches
             for p, pm in zip(self.live_parameters(), self.ema_parameters()):

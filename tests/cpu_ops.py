@@ -55,7 +55,28 @@ def _add_layer_norm(x, branch, scale, norm, out_dtype=None):
     return xn, F.layer_norm(xn, (xn.shape[-1],), norm.weight, norm.bias, norm.eps)
 
 
+def _ema_dev(ema, live, hyper):
+    return ema.mul_(float(hyper[10])).add_(live * float(hyper[11]))
+
+
+def _adamw_dev(param, grad, exp_avg, exp_avg_sq, seg_end, seg_wd, beta1, beta2, eps, hyper, grad_scale=1.0):
+    start = 0
+    bc1, sq2 = float(hyper[8]), float(hyper[9])
+    for i, (end, wd) in enumerate(zip(seg_end, seg_wd)):
+        lr = float(hyper[i])
+        p, g = param[start:end], grad[start:end] * grad_scale
+        m, v = exp_avg[start:end], exp_avg_sq[start:end]
+        p.mul_(1 - lr * wd)
+        m.mul_(beta1).add_(g, alpha=1 - beta1)
+        v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+        p.addcdiv_(m, (v.sqrt() / sq2).add_(eps), value=-lr / bc1)
+        start = end
+    return param
+
+
 _PATCH = {
+    "ema_update_dev_": _ema_dev,
+    "adamw_step_dev_": _adamw_dev,
     "layer_norm": _layer_norm,
     "add_layer_norm": _add_layer_norm,
     "dwconv3x3_gelu": _dwconv_gelu,

@@ -197,3 +197,49 @@ def test_sr_attention_bwd(spec):
     _close(gq, qr.grad, 2 ** -6, 2 ** -6 * float(qr.grad.abs().max()), "dq")
     _close(gkv[..., :C], kvr.grad[..., :C], 2 ** -6, 2 ** -6 * float(kvr.grad[..., :C].abs().max()), "dk")
     _close(gkv[..., C:], kvr.grad[..., C:], 2 ** -6, 2 ** -6 * float(kvr.grad[..., C:].abs().max()), "dv")
+
+
+def test_graphed_train_step_matches_eager():
+    """The CUDA-graph replay of the train step (enable_cuda_graphs) must follow the same trajectory as
+    the eager step: 6 steps, mit_b0, 128x128, randomness off (drop-path / dropout 0, no jitter / blur).
+    Tolerance 2e-3 on the parameters: the fp32 atomics of the weight-gradient kernels make both runs
+    order-dependent at the 1e-6 level and Adam amplifies that during its first steps."""
+    import bench
+    import refign_b200 as P
+
+    def build():
+        torch.manual_seed(0)
+        dims = P.MixVisionTransformer.arch_settings['mit_b0']['embed_dims']
+        m = P.DomainAdaptationSegmentationModel(
+            optimizer_init={'class_path': 'torch.optim.AdamW', 'init_args': {'lr': 6e-4, 'weight_decay': 0.01, 'eps': 1e-2}},
+            lr_scheduler_init=bench.SCH, backbone=P.MixVisionTransformer('mit_b0', drop_path_rate=0.0),
+            head=P.DAFormerHead(dims, [0, 1, 2, 3], 19, 'multiple_select', dropout_ratio=0.0),
+            loss=P.PixelWeightedCrossEntropyLoss(), alignment_backbone=P.VGG('vgg16', out_indices=[2, 3, 4]),
+            alignment_head=P.UAWarpCHead(in_index=[0, 1], input_transform='multiple_select', estimate_uncertainty=True),
+            backbone_lr_factor=0.1, enable_fdist=True, use_refign=True, adapt_to_ref=False, color_jitter_p=1.1,
+            blur=False, precision='bf16').to(DEV).train()
+        with torch.no_grad():   # a distinct ImageNet copy so that the feature distance has a gradient
+            g = torch.Generator(device=DEV).manual_seed(1)
+            for p_ in m.imnet_backbone.parameters():
+                p_.add_(0.02 * torch.randn(p_.shape, device=DEV, generator=g))
+        m.setup_runtime()
+        return m
+
+    batch = bench.synth_batch(128, 2, 5, torch.device(DEV))
+    runs = []
+    for graphed in (False, True):
+        m = build()
+        if graphed:
+            m.enable_cuda_graphs(warmup=2)
+        torch.manual_seed(123)
+        for i in range(6):
+            m.training_step(batch, i)
+        torch.cuda.synchronize()
+        runs.append((m._rt['live'].data.clone(), m._rt['ema'].data.clone(),
+                     {k: float(v) for k, v in m._logged.items()}))
+        del m
+    (p0, e0, l0), (p1, e1, l1) = runs
+    for k in l0:
+        assert abs(l0[k] - l1[k]) <= 2e-2 * max(1.0, abs(l0[k])), (k, l0[k], l1[k])
+    _close(p1, p0, 2e-3, 2e-3, "parameters")
+    _close(e1, e0, 2e-3, 2e-3, "ema parameters")
