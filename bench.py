@@ -262,9 +262,17 @@ def main():
         e2e = {"value": world * PAIRS_PER_GPU / (ms_e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": 4, "ms_per_step": ms_e}
 
-    if rank != 0:
+    def finish():
+        """Leave without tearing NCCL down: destroying a communicator whose collectives were captured into
+        live CUDA graphs can block forever, and the measurement is complete at this point."""
+        sys.stdout.flush()
+        sys.stderr.flush()
         if world > 1:
-            dist.destroy_process_group()
+            barrier()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
     hbm, tf, which = peaks()
     # dominant own kernel by device time inside the timed region
@@ -308,8 +316,7 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
             "own_kernels": own, "loss_src": loss}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == "__main__":
