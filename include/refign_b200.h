@@ -243,6 +243,15 @@ int rf_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_av
                   const float* seg_wd, float beta1, float beta2, float eps, int step,
                   float grad_scale, void* stream);
 
+/* ---- helpers around the library GEMMs of the Linear layers ----------------- */
+/* Bias gradient of a Linear layer (autograd of nn.Linear in mix_transformer.py / modules.py:59-68):
+ * out[c] = sum_r g[r,c];  g: [rows,cols] dtype 0 = f32 / 1 = bf16, cols % 8 == 0; out f32 [cols]
+ * (zeroed by the call). */
+int rf_colsum(const void* g, float* out, int64_t rows, int cols, int dtype, void* stream);
+/* fp32 -> bf16 copy of a flat parameter buffer (the bf16 shadow weights read by the tensor-core
+ * GEMMs; replaces the per-tensor autocast casts of the reference's AMP path). */
+int rf_cast_bf16(const float* src, void* dst, int64_t n, void* stream);
+
 /* CUDA-graph friendly variants: the step-dependent scalars are read from a DEVICE block
  *   hyper[0..7] = per-segment learning rate, hyper[8] = 1 - beta1^t, hyper[9] = sqrt(1 - beta2^t),
  *   hyper[10] = EMA momentum m, hyper[11] = 1 - m   (all f32, written by the host before the replay)

@@ -41,6 +41,8 @@ _SIGNATURES = {
     "rf_sr_attention_bwd_workspace_bytes": (c_i64, [c_int, c_int, c_int, c_int]),
     "rf_sr_attention_bwd": (c_int, [c_p] * 8 + [c_int, c_int, c_int, c_int, c_f32, c_p]),
     "rf_ema_update": (c_int, [c_p, c_p, c_i64, ctypes.c_double, c_p]),
+    "rf_colsum": (c_int, [c_p, c_p, c_i64, c_int, c_int, c_p]),
+    "rf_cast_bf16": (c_int, [c_p, c_p, c_i64, c_p]),
     "rf_ema_update_dev": (c_int, [c_p, c_p, c_i64, c_p, c_p]),
     "rf_adamw_step_dev": (c_int, [c_p, c_p, c_p, c_p, c_i64, c_int, ctypes.POINTER(c_i64), ctypes.POINTER(c_f32),
                                   c_f32, c_f32, c_f32, c_f32, c_p, c_p]),

@@ -286,6 +286,99 @@ dwconv3x3_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ g, float* 
   }
 }
 
+// Dilation-1 weight gradient: a thread owns 8 channels of PPT consecutive pixels of ROWS rows and slides
+// the 3 x (PPT+2) input window like the forward, so each input vector is loaded once per thread
+// ((3*(PPT+2) + PPT) / PPT = 4.75 loads per pixel instead of 10).  CTA = 32 channel groups x 8 pixel
+// strips; partial sums are combined with shared-memory atomics, one red.global per (channel, tap) per CTA.
+template <typename T, int PPT, int ROWS>
+__global__ void __launch_bounds__(WG_CG * WG_PL)
+dwconv3x3_d1_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ g, float* __restrict__ dw,
+                          float* __restrict__ db, int B, int H, int W, int C) {
+  __shared__ float red[80][WG_CG];
+  const int CG = C / DW_VEC;
+  const int lane_cg = threadIdx.x % WG_CG, pl = threadIdx.x / WG_CG;
+  const int cg = blockIdx.x * WG_CG + lane_cg;
+  const bool live = cg < CG;
+  const int c0 = cg * DW_VEC;
+  const int WX = (W + PPT - 1) / PPT;          // pixel strips per row
+  const int SG = (WX + WG_PL - 1) / WG_PL;     // strip groups per row (WG_PL strips per CTA)
+  const int RG = (H + ROWS - 1) / ROWS;
+  int t = blockIdx.y;
+  const int sg = t % SG;
+  t /= SG;
+  const int rg = t % RG;
+  const int b = t / RG;
+  const int xs = (sg * WG_PL + pl) * PPT;
+  for (int i = threadIdx.x; i < 80 * WG_CG; i += WG_CG * WG_PL) (&red[0][0])[i] = 0.f;
+  __syncthreads();
+  if (live && xs < W) {
+    float acc[8][9];
+    float accb[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      accb[k] = 0.f;
+#pragma unroll
+      for (int tt = 0; tt < 9; ++tt) acc[k][tt] = 0.f;
+    }
+    const T* xb = x + (long)b * H * W * C + c0;
+    const T* gb = g + (long)b * H * W * C + c0;
+    for (int r = 0; r < ROWS; ++r) {
+      const int yy = rg * ROWS + r;
+      if (yy >= H) break;
+      float gv[PPT][8];
+#pragma unroll
+      for (int p = 0; p < PPT; ++p) {
+        if (xs + p < W) {
+          Vec8<T>::load(gb + ((long)yy * W + xs + p) * C, gv[p]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) gv[p][k] = 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) accb[k] += gv[p][k];
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int iy = yy + i - 1;
+        if (iy < 0 || iy >= H) continue;
+        const T* row = xb + (long)iy * W * C;
+#pragma unroll
+        for (int q = 0; q < PPT + 2; ++q) {
+          const int ix = xs + q - 1;
+          if (ix < 0 || ix >= W) continue;
+          float v[8];
+          Vec8<T>::load(row + (long)ix * C, v);
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const int p = q - j;  // output pixel xs+p sees input column ix through tap j
+            if (p < 0 || p >= PPT) continue;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k][i * 3 + j] = fmaf(gv[p][k], v[k], acc[k][i * 3 + j]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+#pragma unroll
+      for (int tt = 0; tt < 9; ++tt) atomicAdd(&red[k * 9 + tt][lane_cg], acc[k][tt]);
+      atomicAdd(&red[72 + k][lane_cg], accb[k]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 80 * WG_CG; i += WG_CG * WG_PL) {
+    const int e = i / WG_CG, l = i % WG_CG;
+    const int gcg = blockIdx.x * WG_CG + l;
+    if (gcg >= CG) continue;
+    const float v = red[e][l];
+    if (e < 72) {
+      atomicAdd(dw + (long)(gcg * DW_VEC + e / 9) * 9 + e % 9, v);
+    } else if (db != nullptr) {
+      atomicAdd(db + gcg * DW_VEC + (e - 72), v);
+    }
+  }
+}
+
 template <typename T, int MODE>
 static int launch_dw(const void* x, const float* w, const float* bias, const void* aux, void* y, int B, int H, int W,
                      int C, int dil, int act, cudaStream_t st, const char* name) {
@@ -371,6 +464,21 @@ extern "C" int rf_dwconv3x3_nhwc_bwd_weight(const void* x, const void* grad_pre,
   const long npix = (long)B * H * W;
   const int CG = C / DW_VEC;
   const int gx = (CG + WG_CG - 1) / WG_CG;
+  if (dilation == 1) {
+    constexpr int PPT = 8, ROWS = 4;
+    const int WX = (W + PPT - 1) / PPT, SG = (WX + WG_PL - 1) / WG_PL, RG = (H + ROWS - 1) / ROWS;
+    const long gy = (long)B * RG * SG;
+    RF_REQUIRE(gy <= 65535, "rf_dwconv3x3_nhwc_bwd_weight: too many tiles (%ld)", gy);
+    dim3 grid((unsigned)gx, (unsigned)gy);
+    if (dtype == 1)
+      dwconv3x3_d1_wgrad_kernel<__nv_bfloat16, PPT, ROWS><<<grid, WG_CG * WG_PL, 0, st>>>(
+          (const __nv_bfloat16*)x, (const __nv_bfloat16*)grad_pre, grad_weight, grad_bias, B, H, W, C);
+    else
+      dwconv3x3_d1_wgrad_kernel<float, PPT, ROWS><<<grid, WG_CG * WG_PL, 0, st>>>(
+          (const float*)x, (const float*)grad_pre, grad_weight, grad_bias, B, H, W, C);
+    RF_CHECK_LAUNCH("dwconv3x3_d1_wgrad_kernel");
+    return RF_OK;
+  }
   // pixel strips per CTA: ~8 CTAs per SM over the machine, 64..1024 pixels each
   long strip = npix * gx / ((long)kNumSMs * 8);
   if (strip < 64) strip = 64;

@@ -136,8 +136,8 @@ global_corr_finish_kernel(float* __restrict__ out, const float* __restrict__ row
     for (long s = threadIdx.y; s < Ns; s += GC2_SY) O[s * Nt + t] = O[s * Nt + t] / d;
 }
 
-int global_corr_umma(const float* src, const float* trg, float* out, float* rowmax, float* colmax, int B, int C,
-                     long Ns, long Nt, cudaStream_t st);  // global_corr_umma.cu
+int global_corr_umma(const float* src, const float* trg, float* out, float* rowmax, float* colmax, float* normsq,
+                     int B, int C, long Ns, long Nt, int mode, cudaStream_t st);  // global_corr_umma.cu
 bool global_corr_umma_supported(int C, long Ns, long Nt, const void* a, const void* b, const void* c);
 
 }  // namespace rf
@@ -145,7 +145,7 @@ bool global_corr_umma_supported(int C, long Ns, long Nt, const void* a, const vo
 using namespace rf;
 
 extern "C" int64_t rf_global_corr_workspace_bytes(int B, int64_t Ns, int64_t Nt) {
-  return (int64_t)sizeof(float) * B * (Ns + Nt);
+  return (int64_t)sizeof(float) * B * (Ns + 2 * Nt);  // row maxima, column maxima, column norms
 }
 
 extern "C" int rf_global_corr_fwd(const float* src, const float* trg, float* out, void* workspace, int B, int C,
@@ -163,11 +163,14 @@ extern "C" int rf_global_corr_fwd(const float* src, const float* trg, float* out
   }
   const bool can_tc = global_corr_umma_supported(C, Ns, Nt, src, trg, out);
   RF_REQUIRE(use_tensor_cores != 1 || can_tc,
-             "rf_global_corr_fwd: tcgen05 path needs C%%32==0, Ns%%128==0, Nt%%128==0 and 16B-aligned pointers");
-  if (use_tensor_cores == 1 || (use_tensor_cores < 0 && can_tc)) {
-    int rc = global_corr_umma(src, trg, out, rowmax, colmax, B, C, Ns, Nt, st);
-    if (rc != RF_OK) return rc;
-  } else {
+             "rf_global_corr_fwd: tcgen05 path needs C%%32==0, Ns%%4==0, Nt%%4==0 and 16B-aligned pointers");
+  // automatic choice: the tensor-core path pays off once the volume no longer fits a handful of CTAs
+  if (use_tensor_cores == 1 || (use_tensor_cores < 0 && can_tc && Ns * Nt >= (1l << 20))) {
+    RF_REQUIRE(workspace != nullptr, "rf_global_corr_fwd: the tcgen05 path needs the workspace");
+    float* ws = (float*)workspace;
+    return global_corr_umma(src, trg, out, ws, ws + (long)B * Ns, ws + (long)B * (Ns + Nt), B, C, Ns, Nt, mode, st);
+  }
+  {
     dim3 grid((unsigned)ceil_div(Nt, GC_TT), (unsigned)ceil_div(Ns, GC_TS), B);
     global_corr_ffma_kernel<<<grid, 256, 0, st>>>(src, trg, out, rowmax, colmax, C, Ns, Nt);
     RF_CHECK_LAUNCH("global_corr_ffma_kernel");

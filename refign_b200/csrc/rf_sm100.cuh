@@ -136,9 +136,20 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt_ab, uint32_t M, u
 //                      one MMA consumes 32 bytes of K -> advance the start address by 32 B per k-step
 //   MN-major operand : SBO = 1024 (between 8-row groups along K), LBO = byte distance between
 //                      128-byte column blocks along M/N; advance by (rows per MMA) * 128 B per k-step
-__device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                               uint32_t layout_type) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((uint64_t)layout_type << 61);
+}
+__device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return make_sdesc(smem_addr, lbo_bytes, sbo_bytes, 2);
+}
+// MN-major operands of 32-bit element types (tf32) only exist in the "128-byte swizzle, 32-byte atom"
+// layout (layout type 1; TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of 128 bytes along M/N, FOUR
+// K rows per swizzle group (SBO = 512 between groups), LBO = distance between 128-byte column blocks.
+__device__ __forceinline__ uint64_t make_sdesc_sw128_base32(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                            uint32_t sbo_bytes) {
+  return make_sdesc(smem_addr, lbo_bytes, sbo_bytes, 1);
 }
 
 // ---------------------------------------------------------------- tcgen05: TMEM <-> registers
@@ -186,6 +197,7 @@ rf_encode_tiled_fn get_encode_tiled();  // tensormap.cu; nullptr on failure (err
 
 // rank-3 row-major tensor [d2][d1][d0] (d0 contiguous), box [1][box1][box0], 128-byte swizzle, zero OOB fill
 int make_tmap_3d(CUtensorMap* out, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t d0, uint64_t d1,
-                 uint64_t d2, uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1);
+                 uint64_t d2, uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1,
+                 CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B);
 
 }  // namespace rf

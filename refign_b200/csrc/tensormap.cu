@@ -21,7 +21,8 @@ rf_encode_tiled_fn get_encode_tiled() {
 }
 
 int make_tmap_3d(CUtensorMap* out, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t d0, uint64_t d1,
-                 uint64_t d2, uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1) {
+                 uint64_t d2, uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1,
+                 CUtensorMapSwizzle swizzle) {
   rf_encode_tiled_fn enc = get_encode_tiled();
   if (enc == nullptr) return RF_ECUDA;
   RF_REQUIRE(((uintptr_t)base & 15) == 0, "tensor map: base address must be 16-byte aligned");
@@ -32,7 +33,7 @@ int make_tmap_3d(CUtensorMap* out, CUtensorMapDataType dt, int elem_bytes, const
   const cuuint32_t box[3] = {box0, box1, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(out, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (CUresult %d) for dims [%llu,%llu,%llu] box [%u,%u]", (int)r,
               (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, box0, box1);

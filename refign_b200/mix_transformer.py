@@ -61,11 +61,11 @@ class Mlp(nn.Module):
         self.drop = nn.Dropout(drop)
 
     def forward(self, x, H, W):
-        x = self.fc1(x)
+        x = ops.linear(x, self.fc1.weight, self.fc1.bias)
         x = ops.dwconv3x3_gelu(x, H, W, self.dwconv.dwconv.weight, self.dwconv.dwconv.bias) \
             if ops.FUSED_DWCONV and isinstance(self.act, nn.GELU) else self.act(self.dwconv(x, H, W))
         x = self.drop(x)
-        x = self.fc2(x)
+        x = ops.linear(x, self.fc2.weight, self.fc2.bias)
         return self.drop(x)
 
 
@@ -92,18 +92,18 @@ class Attention(nn.Module):
     def forward(self, x, H, W):
         B, N, C = x.shape
         h, d = self.num_heads, C // self.num_heads
-        q = self.q(x)                                        # [B, N, h*d]   (read strided per head)
+        q = ops.linear(x, self.q.weight, self.q.bias)        # [B, N, h*d]   (read strided per head)
         if self.sr_ratio > 1:
             x_ = _tokens(self.sr(_nhwc_view(x, H, W)))
             x_ = ops.layer_norm(x_, self.norm)
         else:
             x_ = x
-        kv = self.kv(x_)                                     # [B, M, 2*h*d]: k = [..., :C], v = [..., C:]
+        kv = ops.linear(x_, self.kv.weight, self.kv.bias)    # [B, M, 2*h*d]: k = [..., :C], v = [..., C:]
         if self.attn_drop.p > 0 and self.training:
             raise NotImplementedError("attention dropout is not supported by the fused kernel "
                                       "(attn_drop_rate is 0 in every Refign config)")
         o = ops.sr_attention(q, kv, h, self.scale)           # [B, N, h*d]
-        return self.proj_drop(self.proj(o))
+        return self.proj_drop(ops.linear(o, self.proj.weight, self.proj.bias))
 
 
 class Block(nn.Module):

@@ -106,7 +106,7 @@ class MLP(nn.Module):
         self.proj = nn.Linear(input_dim, embed_dim)
 
     def forward(self, x):
-        return self.proj(x.flatten(2).transpose(1, 2))
+        return ops.linear(x.flatten(2).transpose(1, 2), self.proj.weight, self.proj.bias)
 
 
 class DropPath(nn.Module):

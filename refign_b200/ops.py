@@ -9,6 +9,7 @@ import ctypes
 import threading
 
 import torch
+import torch.nn.functional as F
 from torch.nn.modules.utils import _pair
 
 from . import _lib
@@ -397,6 +398,101 @@ def adamw_step_dev_(param, grad, exp_avg, exp_avg_sq, seg_end, seg_wd, beta1, be
     return param
 
 
+@torch.no_grad()
+def cast_bf16_(dst_bf16, src_f32):
+    """dst <- bf16(src) over flat buffers (refresh of the bf16 shadow weights)."""
+    require_cuda(dst_bf16, src_f32)
+    assert dst_bf16.dtype == torch.bfloat16 and src_f32.dtype == torch.float32
+    assert dst_bf16.numel() == src_f32.numel() and dst_bf16.is_contiguous() and src_f32.is_contiguous()
+    with torch.cuda.device(src_f32.device):
+        _run("rf_cast_bf16", ptr(src_f32), ptr(dst_bf16), src_f32.numel(), _stream(),
+             work=(6 * src_f32.numel(), 0))
+    return dst_bf16
+
+
+def colsum(g2d):
+    """fp32 column sums of a contiguous [rows, cols] tensor (bias gradient of a Linear layer)."""
+    require_cuda(g2d)
+    rows, cols = g2d.shape
+    out = torch.empty(cols, device=g2d.device, dtype=torch.float32)
+    with torch.cuda.device(g2d.device):
+        _run("rf_colsum", ptr(g2d), ptr(out), rows, cols, _dt_code(g2d), _stream(),
+             work=(g2d.numel() * g2d.element_size(), g2d.numel()))
+    return out
+
+
+def _bf16_autocast():
+    return torch.is_autocast_enabled() and torch.get_autocast_dtype('cuda') == torch.bfloat16
+
+
+class _LinearShadow(torch.autograd.Function):
+    """y = x W^T + b on the tensor cores (library GEMM) reading the bf16 SHADOW of the fp32 master
+    weight (refreshed once per step by the runtime) instead of an autocast cast per call; the backward
+    returns fp32 weight / bias gradients (bias gradient by rf_colsum)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, wb, bb):
+        with torch.autocast('cuda', enabled=False):
+            xb = x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
+            y = F.linear(xb, wb, bb)
+        ctx.save_for_backward(xb, wb)
+        ctx.x_dtype = x.dtype
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, go):
+        xb, wb = ctx.saved_tensors
+        with torch.autocast('cuda', enabled=False):
+            go2 = go.reshape(-1, go.shape[-1])
+            if go2.dtype != torch.bfloat16:
+                go2 = go2.to(torch.bfloat16)
+            if not go2.is_contiguous():
+                go2 = go2.contiguous()
+            x2 = xb.reshape(-1, xb.shape[-1])
+            dx = dw = db = None
+            if ctx.needs_input_grad[0]:
+                dx = (go2 @ wb).view(xb.shape)
+                if dx.dtype != ctx.x_dtype:
+                    dx = dx.to(ctx.x_dtype)
+            if ctx.needs_input_grad[1]:
+                dw = _mm_f32(go2.t(), x2)
+            if ctx.has_bias and ctx.needs_input_grad[2]:
+                db = colsum(go2) if go2.shape[1] % 8 == 0 else go2.float().sum(0)
+        return dx, dw, db, None, None
+
+
+_MM_OUT_DTYPE = None
+
+
+def _mm_f32(a, b):
+    """bf16 x bf16 -> fp32 GEMM (fp32 output straight from the accumulator when the library supports
+    ``out_dtype``; otherwise bf16 output widened afterwards)."""
+    global _MM_OUT_DTYPE
+    if _MM_OUT_DTYPE is None:
+        try:
+            torch.mm(a[:8, :8].contiguous(), b[:8, :8].contiguous(), out_dtype=torch.float32)
+            _MM_OUT_DTYPE = True
+        except Exception:
+            _MM_OUT_DTYPE = False
+    if _MM_OUT_DTYPE:
+        return torch.mm(a, b, out_dtype=torch.float32)
+    return torch.mm(a, b).float()
+
+
+def linear(x, weight, bias=None):
+    """``F.linear`` for the MiT / DAFormer Linear layers.  When the runtime has attached bf16 shadow
+    weights (``weight._rf_bf16``) and bf16 autocast is on, the GEMM reads the shadow directly."""
+    wb = getattr(weight, '_rf_bf16', None)
+    if wb is None or not x.is_cuda or not _bf16_autocast():
+        return F.linear(x, weight, bias)
+    bb = getattr(bias, '_rf_bf16', None) if bias is not None else None
+    if bias is not None and bb is None:
+        return F.linear(x, weight, bias)
+    return _LinearShadow.apply(x, weight, bias, wb, bb)
+
+
 # --------------------------------------------------------------------------
 # MiT operators (reference: models/backbones/mix_transformer.py)
 # --------------------------------------------------------------------------
@@ -564,7 +660,7 @@ def dwconv3x3_nhwc(x, weight, bias=None, dilation=1):
 def _ln_out_dtype(x):
     """LayerNorm output dtype: bf16 under bf16 autocast (it feeds a tensor-core GEMM that would cast it
     anyway), else the input dtype."""
-    if torch.is_autocast_enabled() and torch.get_autocast_gpu_dtype() == torch.bfloat16:
+    if torch.is_autocast_enabled() and torch.get_autocast_dtype('cuda') == torch.bfloat16:
         return torch.bfloat16
     return x.dtype
 

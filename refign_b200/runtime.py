@@ -49,6 +49,18 @@ class FlatParams:
                 if with_grad:
                     p.grad = self.grad[o:o + n].view(p.shape)
 
+    def attach_shadow(self):
+        """Flat bf16 copy of the buffer; every parameter gets ``p._rf_bf16`` = its bf16 view (read by
+        refign_b200.ops.linear under bf16 autocast).  ``refresh_shadow()`` must follow every update."""
+        self.shadow = torch.empty(self.data.numel(), dtype=torch.bfloat16, device=self.data.device)
+        for p, o in zip(self.params, self.offsets):
+            p._rf_bf16 = self.shadow[o:o + p.numel()].view(p.shape)
+        self.refresh_shadow()
+
+    def refresh_shadow(self):
+        if getattr(self, 'shadow', None) is not None:
+            ops.cast_bf16_(self.shadow, self.data)
+
     def rebind_grads(self):
         """(Re)attach the flat gradient views (after anything that reset ``p.grad`` to None)."""
         for p, o in zip(self.params, self.offsets):
@@ -119,6 +131,7 @@ class FlatAdamW:
             ops.adamw_step_(self.flat.data, self.flat.grad, self.exp_avg, self.exp_avg_sq, self.seg_end, self.seg_lr,
                             self.seg_wd, self.betas[0], self.betas[1], self.eps, self.step_count + 1,
                             grad_scale=1.0 / self.world_size)
+        self.flat.refresh_shadow()
 
     def step(self):
         self.launch_step()

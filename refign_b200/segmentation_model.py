@@ -160,6 +160,14 @@ class DomainAdaptationSegmentationModel(_Base):
             ema.append(ema_by_name['m_' + n])
         flat_live = runtime.FlatParams(live, with_grad=True)
         flat_ema = runtime.FlatParams(ema, with_grad=False)
+        if self.precision == 'bf16' and flat_live.data.is_cuda:
+            # bf16 shadow weights for the tensor-core GEMMs (no per-call autocast casts): refreshed after
+            # AdamW (student) and the EMA update (teacher); the frozen ImageNet copy is cast once
+            flat_live.attach_shadow()
+            flat_ema.attach_shadow()
+            if self.enable_fdist:
+                for p in self.imnet_backbone.parameters():
+                    p._rf_bf16 = p.detach().to(torch.bfloat16)
         init = self.optimizer_init.get('init_args', {})
         opt = runtime.FlatAdamW(flat_live, seg_end, seg_lr, seg_wd, betas=tuple(init.get('betas', betas)),
                                 eps=init.get('eps', eps), process_group=process_group, world_size=world_size)
@@ -378,6 +386,18 @@ class DomainAdaptationSegmentationModel(_Base):
         from .mix_transformer import resolve_checkpoint
         ckpt = torch.load(resolve_checkpoint(pretrain_path), map_location='cpu')
         self.load_state_dict(ckpt['state_dict'] if 'state_dict' in ckpt else ckpt, strict=True)
+        self.refresh_shadows()
+
+    def refresh_shadows(self):
+        """Re-derive the bf16 shadow weights after the fp32 masters were changed from outside the
+        runtime (checkpoint load, manual edits)."""
+        if getattr(self, '_rt', None) is not None:
+            self._rt['live'].refresh_shadow()
+            self._rt['ema'].refresh_shadow()
+            if self.enable_fdist:
+                for p in self.imnet_backbone.parameters():
+                    if getattr(p, '_rf_bf16', None) is not None:
+                        p._rf_bf16.copy_(p.detach())
 
     # ---- Refign: refine / eta / align --------------------------------------------------------------
     @torch.no_grad()
@@ -502,8 +522,10 @@ class DomainAdaptationSegmentationModel(_Base):
         m = runtime.ema_momentum(self.global_step, self.ema_momentum)
         if self._rt is not None and self._rt['opt'].hyper is not None:
             ops.ema_update_dev_(self._rt['ema'].data, self._rt['live'].data, self._rt['opt'].hyper)
+            self._rt['ema'].refresh_shadow()
         elif self._rt is not None:
             ops.ema_update_(self._rt['ema'].data, self._rt['live'].data, m)
+            self._rt['ema'].refresh_shadow()
         else:  # no runtime installed (e.g. under Lightning without setup_runtime): per-tensor kernel launches
             for p, pm in zip(self.live_parameters(), self.ema_parameters()):
                 ops.ema_update_(pm.data.view(-1), p.data.contiguous().view(-1), m)

@@ -169,6 +169,28 @@ def test_global_corr_golden(golden):
     close(ops.global_correlation(s, t, cyclic_consistency=False, use_tensor_cores=0), T(g["glob_nomm"]), atol=2e-6)
 
 
+@pytest.mark.parametrize("shape", [(1, 128, 64, 64, 64, 64), (2, 256, 32, 32, 32, 32), (1, 128, 36, 28, 20, 52),
+                                   (1, 32, 16, 12, 128, 128)])
+@pytest.mark.parametrize("mm", [True, False])
+def test_global_corr_tcgen05_vs_oracle(shape, mm):
+    """tcgen05 kind::tf32 path: the operands are read as TF32 (10-bit mantissa) with fp32 accumulation,
+    so a correlation of unit vectors carries ~2e-4 absolute error; mutual matching cubes the value
+    (x3 relative error).  Tolerance: raw volume 1e-3 absolute; finished volume 2e-2 relative + 3e-3 of
+    the largest entry.  (The model's own 16x16 case runs the exact-fp32 FFMA path; `-1` picks this
+    path only for volumes of >= 2^20 entries.)"""
+    B, C, Hs, Ws, Ht, Wt = shape
+    torch.manual_seed(sum(shape) + 1)
+    s, t = unit(torch.randn(B, C, Hs, Ws)), unit(torch.randn(B, C, Ht, Wt))
+    raw = ops.global_correlation(s.to(DEV), t.to(DEV), cyclic_consistency=False, normalise=False, use_tensor_cores=1)
+    close(raw, oracle.global_corr(s, t, mutual=False, normalise=False), atol=1e-3, rtol=0)
+    want = oracle.global_corr(s, t, mutual=mm)
+    got = ops.global_correlation(s.to(DEV), t.to(DEV), cyclic_consistency=mm, use_tensor_cores=1)
+    close(got, want, atol=3e-3 * float(want.abs().max()), rtol=2e-2)
+    # size-independent property: every target column of the finished volume has unit (or zero) norm
+    n = got.norm(dim=1)
+    assert bool(((n - 1).abs() < 1e-4).logical_or(n == 0).all())
+
+
 # ----------------------------------------------------------------------------- warp
 def test_warp_golden_and_oracle(golden):
     g = golden("ops_warp")

@@ -94,6 +94,12 @@ def main():
             nn_ = N * N
             report("global_corr(ffma)+mm+relu_l2norm", [B, C, N, N], time_op(lambda: ops.global_correlation(s, t, use_tensor_cores=0), args.iters),
                    4 * B * (C * 2 * nn_ + nn_ * nn_), 2 * B * nn_ * nn_ * C)
+    if want("global_tc"):
+        for (B, C, N) in [(1, 128, 64), (1, 128, 128), (2, 128, 128), (1, 128, 192)]:
+            s, t = unit(torch.randn(B, C, N, N, device=dev)), unit(torch.randn(B, C, N, N, device=dev))
+            nn_ = N * N
+            report("global_corr(tcgen05 tf32)+mm+relu_l2norm", [B, C, N, N], time_op(lambda: ops.global_correlation(s, t, use_tensor_cores=1), args.iters),
+                   4 * B * (C * 2 * nn_ + nn_ * nn_), 3 * 2 * B * nn_ * nn_ * C)
     if want("warp"):
         for (B, C, H) in [(2, 19, 512), (2, 19, 1024), (2, 128, 256), (2, 256, 128)]:
             x, f = torch.randn(B, C, H, H, device=dev), torch.randn(B, 2, H, H, device=dev) * 4
