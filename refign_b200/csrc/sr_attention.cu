@@ -19,6 +19,7 @@
 // Bound: MUFU (exp2) -- 256 tensor flops per exponential at head_dim 64; reported against the bf16
 // tensor peak, see DESIGN.md.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "rf_common.cuh"
 #include "rf_sm100.cuh"
@@ -116,7 +117,7 @@ sr_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       for (int i = 0; i < 32; ++i)
         if (c * 32 + i < kvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
     }
-    const float alpha = exp2f((m_run - mx) * scale_log2);  // 0 on the first chunk (m_run = -inf)
+    const float alpha = fast_exp2((m_run - mx) * scale_log2);  // 0 on the first chunk (m_run = -inf)
     const float mneg = -mx * scale_log2;
     l_run *= alpha;
     if (j > 0) {
@@ -152,8 +153,8 @@ sr_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       uint32_t pk[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        float p0 = exp2f(fmaf(__uint_as_float(v[2 * i]), scale_log2, mneg));
-        float p1 = exp2f(fmaf(__uint_as_float(v[2 * i + 1]), scale_log2, mneg));
+        float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), scale_log2, mneg));
+        float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), scale_log2, mneg));
         if (c * 32 + 2 * i >= kvalid) p0 = 0.f;
         if (c * 32 + 2 * i + 1 >= kvalid) p1 = 0.f;
         rs += p0 + p1;
@@ -208,6 +209,304 @@ sr_attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   if (warp == 0) tmem_dealloc<256>(tmem);
 }
 
+// Row maximum of this lane's 128 fp32 scores in TMEM (four independent partial maxima for ILP).
+template <bool MASK>
+__device__ __forceinline__ float attn_row_max(uint32_t tS, int kvalid) {
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t v[32];
+    tmem_ld32(tS + c * 32, v);
+    tc_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      if (!MASK || c * 32 + i + 0 < kvalid) m0 = fmaxf(m0, __uint_as_float(v[i + 0]));
+      if (!MASK || c * 32 + i + 1 < kvalid) m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
+      if (!MASK || c * 32 + i + 2 < kvalid) m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
+      if (!MASK || c * 32 + i + 3 < kvalid) m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
+    }
+  }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+
+// P = exp2(s * scale_log2 + mneg) for this lane's 128 scores, packed to bf16 into TMEM; returns the row sum.
+template <bool MASK>
+__device__ __forceinline__ float attn_exp_pack(uint32_t tS, uint32_t tP, float scale_log2, float mneg, int kvalid) {
+  float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t v[32];
+    tmem_ld32(tS + c * 32, v);
+    tc_wait_ld();
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+      float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 0]), scale_log2, mneg));
+      float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), scale_log2, mneg));
+      float p2 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 2]), scale_log2, mneg));
+      float p3 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 3]), scale_log2, mneg));
+      if (MASK) {
+        if (c * 32 + 2 * i + 0 >= kvalid) p0 = 0.f;
+        if (c * 32 + 2 * i + 1 >= kvalid) p1 = 0.f;
+        if (c * 32 + 2 * i + 2 >= kvalid) p2 = 0.f;
+        if (c * 32 + 2 * i + 3 >= kvalid) p3 = 0.f;
+      }
+      r0 += p0;
+      r1 += p1;
+      r2 += p2;
+      r3 += p3;
+      const __nv_bfloat162 h0 = __floats2bfloat162_rn(p0, p1), h1 = __floats2bfloat162_rn(p2, p3);
+      pk[i] = *reinterpret_cast<const uint32_t*>(&h0);
+      pk[i + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+    }
+    tmem_st16(tP + c * 16, pk);
+  }
+  return (r0 + r1) + (r2 + r3);
+}
+
+// Single pass over this lane's 128 scores: TMEM read bandwidth (64 B/clk/SM) is the scarcest resource
+// of a head_dim-64 softmax, so S is read ONCE into registers; row maximum (partial maxima for ILP),
+// lazy-rescale decision by the caller through `decide`, then P = exp2(s * scale_log2 - m * scale_log2)
+// packed to bf16 into TMEM.  Returns the row sum; `mx_out` receives the chunk maximum.
+struct AttnRow {
+  uint32_t v[4][32];
+};
+template <bool MASK>
+__device__ __forceinline__ float attn_load_max(uint32_t tS, int kvalid, AttnRow& row) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) tmem_ld32(tS + c * 32, row.v[c]);
+  tc_wait_ld();
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      if (!MASK || c * 32 + i + 0 < kvalid) m0 = fmaxf(m0, __uint_as_float(row.v[c][i + 0]));
+      if (!MASK || c * 32 + i + 1 < kvalid) m1 = fmaxf(m1, __uint_as_float(row.v[c][i + 1]));
+      if (!MASK || c * 32 + i + 2 < kvalid) m2 = fmaxf(m2, __uint_as_float(row.v[c][i + 2]));
+      if (!MASK || c * 32 + i + 3 < kvalid) m3 = fmaxf(m3, __uint_as_float(row.v[c][i + 3]));
+    }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+template <bool MASK>
+__device__ __forceinline__ float attn_exp_pack_regs(const AttnRow& row, uint32_t tP, float scale_log2, float mneg,
+                                                    int kvalid) {
+  float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+      float p0 = fast_exp2(fmaf(__uint_as_float(row.v[c][2 * i + 0]), scale_log2, mneg));
+      float p1 = fast_exp2(fmaf(__uint_as_float(row.v[c][2 * i + 1]), scale_log2, mneg));
+      float p2 = fast_exp2(fmaf(__uint_as_float(row.v[c][2 * i + 2]), scale_log2, mneg));
+      float p3 = fast_exp2(fmaf(__uint_as_float(row.v[c][2 * i + 3]), scale_log2, mneg));
+      if (MASK) {
+        if (c * 32 + 2 * i + 0 >= kvalid) p0 = 0.f;
+        if (c * 32 + 2 * i + 1 >= kvalid) p1 = 0.f;
+        if (c * 32 + 2 * i + 2 >= kvalid) p2 = 0.f;
+        if (c * 32 + 2 * i + 3 >= kvalid) p3 = 0.f;
+      }
+      r0 += p0;
+      r1 += p1;
+      r2 += p2;
+      r3 += p3;
+      const __nv_bfloat162 h0 = __floats2bfloat162_rn(p0, p1), h1 = __floats2bfloat162_rn(p2, p3);
+      pk[i] = *reinterpret_cast<const uint32_t*>(&h0);
+      pk[i + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+    }
+    tmem_st16(tP + c * 16, pk);
+  }
+  return (r0 + r1) + (r2 + r3);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Warp-specialised "ping-pong" forward: one CTA per SM works on TWO 128-query tiles at once.
+//   warps 0-3  softmax warpgroup of tile A     warps 4-7  softmax warpgroup of tile B
+//   warp 8     MMA issuer (one elected lane)    warp 9     TMA producer (one elected lane)
+// The MMA warp interleaves the tiles -- PV_A(j), S_A(j+1), PV_B(j), S_B(j+1), ... -- so the tensor core
+// works on one tile while the other tile's warpgroup runs its softmax, and both tiles share every K / V
+// chunk that TMA brings in (3-stage ring).  The O accumulator is rescaled lazily: the running maximum a
+// row normalises by is only moved when the new maximum exceeds it by 2^8 (exact: the final 1/l uses the
+// same stale maximum), which removes almost all TMEM round trips of O.
+// TMEM (all 512 columns): tile t at column 256 t: S [0,128) | O [128,192) | P [192,256).
+// mbarriers: q_full, kv_full[3] (TMA tx), kv_free[3] (tcgen05.commit), s_full[2] (commit),
+//            p_full[2] (128 thread arrivals), o_full[2] (commit).
+constexpr int AT2_STAGES = 3;
+constexpr int AT2_THREADS = 320;
+constexpr int AT2_SMEM = (2 + 2 * AT2_STAGES) * AT_TILE_BYTES + 1024 + 256;
+
+struct __align__(8) Attn2Bars {
+  uint64_t q_full, kv_full[AT2_STAGES], kv_free[AT2_STAGES], s_full[2], p_full[2], o_full[2], s_free[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(AT2_THREADS, 1)
+sr_attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+                           __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int N, int M, int heads,
+                           float scale_log2) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;                                   // 2 tiles
+  uint8_t* ring = smem + 2 * AT_TILE_BYTES;             // stage s: K at ring + 2 s T, V right after
+  Attn2Bars* bars = reinterpret_cast<Attn2Bars*>(smem + (2 + 2 * AT2_STAGES) * AT_TILE_BYTES);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = blockIdx.x * 2 * AT_BM, head = blockIdx.y, b = blockIdx.z;
+  const int C = heads * AT_D;
+  const int nchunks = (M + AT_BN - 1) / AT_BN;
+
+  if (tid == 0) {
+    mbar_init(&bars->q_full, 1);
+    for (int s = 0; s < AT2_STAGES; ++s) {
+      mbar_init(&bars->kv_full[s], 1);
+      mbar_init(&bars->kv_free[s], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&bars->s_full[t], 1);
+      mbar_init(&bars->p_full[t], 128);
+      mbar_init(&bars->o_full[t], 1);
+      mbar_init(&bars->s_free[t], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc<512>(&bars->tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  constexpr uint32_t IDESC_S = make_idesc(FMT_BF16, 128, 128, 0, 0);
+  constexpr uint32_t IDESC_O = make_idesc(FMT_BF16, 128, 64, 0, 1);
+
+  if (warp == 9) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_q);
+      tma_prefetch_desc(&tm_kv);
+      mbar_expect_tx(&bars->q_full, 2 * AT_TILE_BYTES);
+      tma_load_3d(sQ, &tm_q, &bars->q_full, head * AT_D, q0, b);
+      tma_load_3d(sQ + AT_TILE_BYTES, &tm_q, &bars->q_full, head * AT_D, q0 + AT_BM, b);
+      for (int j = 0; j < nchunks; ++j) {
+        const int st = j % AT2_STAGES;
+        if (j >= AT2_STAGES) mbar_wait(&bars->kv_free[st], ((j / AT2_STAGES) - 1) & 1);
+        uint8_t* sK = ring + st * 2 * AT_TILE_BYTES;
+        mbar_expect_tx(&bars->kv_full[st], 2 * AT_TILE_BYTES);
+        tma_load_3d(sK, &tm_kv, &bars->kv_full[st], head * AT_D, j * AT_BN, b);
+        tma_load_3d(sK + AT_TILE_BYTES, &tm_kv, &bars->kv_full[st], C + head * AT_D, j * AT_BN, b);
+      }
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint64_t descQ[2] = {make_sdesc_sw128(smem_u32(sQ), 16, 1024),
+                                 make_sdesc_sw128(smem_u32(sQ + AT_TILE_BYTES), 16, 1024)};
+      auto issue_s = [&](int t, int j) {
+        const uint64_t descK = make_sdesc_sw128(smem_u32(ring + (j % AT2_STAGES) * 2 * AT_TILE_BYTES), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < AT_D / 16; ++k)
+          mma_f16_ss(tmem + t * 256, descQ[t] + (uint64_t)(k * 2), descK + (uint64_t)(k * 2), IDESC_S, k > 0 ? 1u : 0u);
+        tc_commit(&bars->s_full[t]);
+      };
+      mbar_wait(&bars->q_full, 0);
+      mbar_wait(&bars->kv_full[0], 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      issue_s(1, 0);
+      for (int j = 0; j < nchunks; ++j) {
+        const int st = j % AT2_STAGES;
+        const uint64_t descV =
+            make_sdesc_sw128(smem_u32(ring + st * 2 * AT_TILE_BYTES + AT_TILE_BYTES), 8192, 1024);
+        if (j + 1 < nchunks) mbar_wait(&bars->kv_full[(j + 1) % AT2_STAGES], ((j + 1) / AT2_STAGES) & 1);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&bars->p_full[t], j & 1);   // warpgroup t has consumed S(j) and written P(j)
+          tc_fence_after();
+          if (j + 1 < nchunks) issue_s(t, j + 1);   // next scores first: the warpgroup is waiting for them
+#pragma unroll
+          for (int k = 0; k < AT_BN / 16; ++k)
+            mma_f16_ts(tmem + t * 256 + 128, tmem + t * 256 + 192 + k * 8, descV + (uint64_t)(k * 128), IDESC_O,
+                       (j > 0 || k > 0) ? 1u : 0u);
+          tc_commit(&bars->o_full[t]);
+        }
+        tc_commit(&bars->kv_free[st]);   // K_j / V_j fully consumed by both tiles (S(j) was committed earlier)
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warpgroups
+    const int t = warp >> 2;                         // tile handled by this warpgroup
+    const int r = tid & 127;                         // row inside the tile == TMEM lane
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem + t * 256 + lane_off, tO = tS + 128, tP = tS + 192;
+    float m_run = -INFINITY, l_run = 0.f;            // m_run: the (possibly stale) maximum rows are normalised by
+    for (int j = 0; j < nchunks; ++j) {
+      mbar_wait(&bars->s_full[t], j & 1);
+      tc_fence_after();
+      const int kvalid = M - j * AT_BN;
+      const bool full = kvalid >= AT_BN;               // only the last chunk of a ragged M needs masking
+      const float mx = full ? attn_row_max<false>(tS, kvalid) : attn_row_max<true>(tS, kvalid);
+      // lazy rescale: move the reference maximum only when it is exceeded by more than 2^8
+      const bool move = (mx - m_run) * scale_log2 > 8.f;   // true on the first chunk (m_run = -inf)
+      if (j > 0) {   // PV(j-1) must have consumed P(j-1) (and landed in O) before P / O are touched again
+        mbar_wait(&bars->o_full[t], (j - 1) & 1);
+        tc_fence_after();
+      }
+      if (__any_sync(0xffffffffu, move)) {
+        const float m_new = move ? mx : m_run;
+        const float alpha = fast_exp2((m_run - m_new) * scale_log2);   // 0 on the first chunk, 1 for rows that stay
+        m_run = m_new;
+        l_run *= alpha;
+        if (j > 0) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tO + c * 32, v);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st32(tO + c * 32, v);
+          }
+        }
+      }
+      const float mneg = -m_run * scale_log2;
+      const float rs = full ? attn_exp_pack<false>(tS, tP, scale_log2, mneg, kvalid)
+                            : attn_exp_pack<true>(tS, tP, scale_log2, mneg, kvalid);
+      l_run += rs;
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&bars->p_full[t]);
+    }
+    mbar_wait(&bars->o_full[t], (nchunks - 1) & 1);
+    tc_fence_after();
+    const int row = q0 + t * AT_BM + r;
+    const float inv_l = 1.f / l_run;
+    uint32_t packed[32];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tO + c * 32, v);
+      tc_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const __nv_bfloat162 h =
+            __floats2bfloat162_rn(__uint_as_float(v[2 * i]) * inv_l, __uint_as_float(v[2 * i + 1]) * inv_l);
+        packed[c * 16 + i] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+    }
+    if (row < N) {
+      uint4* dst = reinterpret_cast<uint4*>(out + ((long)b * N + row) * C + head * AT_D);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+      if (lse != nullptr)
+        lse[((long)b * heads + head) * N + row] = m_run * scale_log2 * 0.69314718055994531f + __logf(l_run);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc<512>(tmem);
+}
+
 }  // namespace rf
 
 using namespace rf;
@@ -228,10 +527,19 @@ extern "C" int rf_sr_attention_fwd(const void* q, const void* kv, void* out, flo
   static bool attr_set = false;
   if (!attr_set) {
     RF_CUDA(cudaFuncSetAttribute(sr_attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+    RF_CUDA(cudaFuncSetAttribute(sr_attention_fwd_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_SMEM));
     attr_set = true;
   }
-  dim3 grid((unsigned)((N + AT_BM - 1) / AT_BM), (unsigned)heads, (unsigned)B);
   const float scale_log2 = scale * 1.44269504088896341f;
+  static const int variant = getenv("RF_ATTN_FWD") ? atoi(getenv("RF_ATTN_FWD")) : 2;
+  if (variant == 2 && N > AT_BM) {   // two query tiles per CTA, warp-specialised
+    dim3 grid((unsigned)((N + 2 * AT_BM - 1) / (2 * AT_BM)), (unsigned)heads, (unsigned)B);
+    sr_attention_fwd_pp_kernel<<<grid, AT2_THREADS, AT2_SMEM, (cudaStream_t)stream>>>(tq, tkv, (__nv_bfloat16*)out, lse,
+                                                                                     N, M, heads, scale_log2);
+    RF_CHECK_LAUNCH("sr_attention_fwd_pp_kernel");
+    return RF_OK;
+  }
+  dim3 grid((unsigned)((N + AT_BM - 1) / AT_BM), (unsigned)heads, (unsigned)B);
   sr_attention_fwd_kernel<<<grid, 128, AT_SMEM, (cudaStream_t)stream>>>(tq, tkv, (__nv_bfloat16*)out, lse, N, M, heads,
                                                                           scale_log2);
   RF_CHECK_LAUNCH("sr_attention_fwd_kernel");

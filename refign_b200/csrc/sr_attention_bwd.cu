@@ -16,6 +16,8 @@
 // Both kernels: 128 threads, thread t owns TMEM lane t, 4-stage TMA ring, 2 CTAs per SM.
 #include <cuda_bf16.h>
 
+#include <type_traits>
+
 #include "rf_common.cuh"
 #include "rf_sm100.cuh"
 
@@ -145,25 +147,33 @@ sr_attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
     }
     __syncwarp();
     const int kvalid = M - j * 64;
+    auto softmax_grad = [&](auto masked) {
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t sv[32], dv[32];
-      tmem_ld32(tS + c * 32, sv);
-      tmem_ld32(tdP + c * 32, dv);
-      tc_wait_ld();
-      uint32_t pk[16];
+      for (int c = 0; c < 2; ++c) {
+        uint32_t sv[32], dv[32];
+        tmem_ld32(tS + c * 32, sv);
+        tmem_ld32(tdP + c * 32, dv);
+        tc_wait_ld();
+        uint32_t pk[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float p0 = exp2f(fmaf(__uint_as_float(sv[2 * i]), scale_log2, -lse2));
-        float p1 = exp2f(fmaf(__uint_as_float(sv[2 * i + 1]), scale_log2, -lse2));
-        if (c * 32 + 2 * i >= kvalid) p0 = 0.f;
-        if (c * 32 + 2 * i + 1 >= kvalid) p1 = 0.f;
-        const float d0 = p0 * (__uint_as_float(dv[2 * i]) - Drow) * scale;
-        const float d1 = p1 * (__uint_as_float(dv[2 * i + 1]) - Drow) * scale;
-        pk[i] = pack_bf16(d0, d1);
+        for (int i = 0; i < 16; ++i) {
+          float p0 = fast_exp2(fmaf(__uint_as_float(sv[2 * i]), scale_log2, -lse2));
+          float p1 = fast_exp2(fmaf(__uint_as_float(sv[2 * i + 1]), scale_log2, -lse2));
+          if constexpr (decltype(masked)::value) {   // only the last chunk of a ragged M
+            if (c * 32 + 2 * i >= kvalid) p0 = 0.f;
+            if (c * 32 + 2 * i + 1 >= kvalid) p1 = 0.f;
+          }
+          const float d0 = p0 * (__uint_as_float(dv[2 * i]) - Drow) * scale;
+          const float d1 = p1 * (__uint_as_float(dv[2 * i + 1]) - Drow) * scale;
+          pk[i] = pack_bf16(d0, d1);
+        }
+        tmem_st16(tdS + c * 16, pk);
       }
-      tmem_st16(tdS + c * 16, pk);
-    }
+    };
+    if (kvalid >= 64)
+      softmax_grad(std::false_type{});
+    else
+      softmax_grad(std::true_type{});
     tc_wait_st();
     tc_fence_before();
     __syncthreads();
@@ -206,10 +216,10 @@ __device__ __forceinline__ void dkv_half(const uint32_t (&sv)[32], const uint32_
 #pragma unroll
   for (int g = 0; g < 8; ++g) {
     const float4 l = l4[g], dd = d4[g];
-    const float p0 = exp2f(fmaf(__uint_as_float(sv[4 * g + 0]), scale_log2, -l.x));
-    const float p1 = exp2f(fmaf(__uint_as_float(sv[4 * g + 1]), scale_log2, -l.y));
-    const float p2 = exp2f(fmaf(__uint_as_float(sv[4 * g + 2]), scale_log2, -l.z));
-    const float p3 = exp2f(fmaf(__uint_as_float(sv[4 * g + 3]), scale_log2, -l.w));
+    const float p0 = fast_exp2(fmaf(__uint_as_float(sv[4 * g + 0]), scale_log2, -l.x));
+    const float p1 = fast_exp2(fmaf(__uint_as_float(sv[4 * g + 1]), scale_log2, -l.y));
+    const float p2 = fast_exp2(fmaf(__uint_as_float(sv[4 * g + 2]), scale_log2, -l.z));
+    const float p3 = fast_exp2(fmaf(__uint_as_float(sv[4 * g + 3]), scale_log2, -l.w));
     pp[2 * g] = pack_bf16(p0, p1);
     pp[2 * g + 1] = pack_bf16(p2, p3);
     pd[2 * g] = pack_bf16(p0 * (__uint_as_float(dv[4 * g + 0]) - dd.x) * scale,
