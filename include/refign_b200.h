@@ -197,6 +197,16 @@ int rf_sr_attention_bwd(const void* q, const void* kv, const void* out, const vo
                         const float* lse, void* grad_q, float* grad_kv_f32, void* workspace,
                         int B, int N, int M, int heads, float scale, void* stream);
 
+/* ---- stage-1 OverlapPatchEmbed: 7x7/s4 conv (3 -> 32|64 channels) + LayerNorm ---- */
+/* Replaces OverlapPatchEmbed.forward for patch_embed1 (models/backbones/mix_transformer.py:236-242,
+ * LayerNorm eps 1e-5 :234): conv + NCHW->NLC transpose + LayerNorm in one pass.
+ *   x : f32 [B,3,H,W];  weight : f32 [cout,3,7,7];  bias, gamma, beta : f32 [cout]
+ *   y : f32 [B, Ho*Wo, cout] tokens (Ho = (H-1)/4 + 1);  pre_norm : f32 same shape or NULL (the
+ *   convolution output before the LayerNorm, needed by the backward);  mean, rstd : f32 [B*Ho*Wo] or NULL. */
+int rf_patch_embed_ln_fwd(const float* x, const float* weight, const float* bias, const float* gamma,
+                          const float* beta, float* pre_norm, float* y, float* mean, float* rstd,
+                          int B, int H, int W, int cout, float eps, void* stream);
+
 /* ---- residual add + LayerNorm ------------------------------------------- */
 /* Replaces the LayerNorms of the MiT encoder and the residual adds in front of
  * them (models/backbones/mix_transformer.py:203-207 Block.forward, :135/:148 SR

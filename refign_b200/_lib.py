@@ -35,6 +35,7 @@ _SIGNATURES = {
     "rf_dwconv3x3_nhwc_bwd_input": (c_int, [c_p, c_p, c_p] + [c_int] * 6 + [c_p]),
     "rf_dwconv3x3_gelu_bwd_pre": (c_int, [c_p] * 5 + [c_int] * 6 + [c_p]),
     "rf_dwconv3x3_nhwc_bwd_weight": (c_int, [c_p] * 4 + [c_int] * 6 + [c_p]),
+    "rf_patch_embed_ln_fwd": (c_int, [c_p] * 9 + [c_int, c_int, c_int, c_int, c_f32, c_p]),
     "rf_add_layernorm_fwd": (c_int, [c_p] * 9 + [c_i64, c_int, c_i64, c_f32, c_int, c_int, c_int, c_p]),
     "rf_add_layernorm_bwd": (c_int, [c_p] * 11 + [c_i64, c_int, c_i64, c_int, c_int, c_int, c_p]),
     "rf_sr_attention_fwd": (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_f32, c_p]),

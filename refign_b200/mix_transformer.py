@@ -153,9 +153,8 @@ class OverlapPatchEmbed(nn.Module):
         self.norm = nn.LayerNorm(embed_dim)
 
     def forward(self, x):
-        fused = (ops.FUSED_PATCH_EMBED and x.is_cuda and not torch.is_grad_enabled()
-                 and self.proj.in_channels == 3 and self.patch_size == (7, 7) and self.stride == 4
-                 and self.proj.out_channels == 64)
+        fused = (ops.FUSED_PATCH_EMBED and self.proj.in_channels == 3 and self.patch_size == (7, 7)
+                 and self.stride == 4 and self.proj.out_channels in (32, 64) and self.proj.bias is not None)
         if fused:
             return ops.patch_embed_ln(x, self.proj.weight, self.proj.bias, self.norm.weight, self.norm.bias,
                                       self.norm.eps)

@@ -498,7 +498,7 @@ def linear(x, weight, bias=None):
 # --------------------------------------------------------------------------
 FUSED_ATTENTION = True
 FUSED_DWCONV = True
-FUSED_PATCH_EMBED = False
+FUSED_PATCH_EMBED = True
 
 
 def _sr_attention_library(q, kv, heads, scale):
@@ -771,5 +771,54 @@ def add_layer_norm(x, branch, scale, norm, out_dtype=None):
     return _AddLayerNorm.apply(x, branch, scale, norm.weight, norm.bias, norm.eps, out_dtype or _ln_out_dtype(x))
 
 
+class _PatchEmbedLN(torch.autograd.Function):
+    """conv 7x7/s4/p3 (3 -> C) + LayerNorm in one kernel; the backward runs the LayerNorm backward kernel
+    on the saved pre-norm activations and library convolution-weight / bias gradients (the image
+    needs no gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, conv_w, conv_b, ln_w, ln_b, eps):
+        require_cuda(x, conv_w, conv_b, ln_w, ln_b)
+        xf = _f32c(x)
+        B, _, H, W = xf.shape
+        C = conv_w.shape[0]
+        Ho, Wo = (H - 1) // 4 + 1, (W - 1) // 4 + 1
+        need = any(ctx.needs_input_grad[1:5])
+        y = torch.empty(B, Ho * Wo, C, device=x.device, dtype=torch.float32)
+        pre = torch.empty_like(y) if need else None
+        mean = torch.empty(B * Ho * Wo, device=x.device, dtype=torch.float32) if need else None
+        rstd = torch.empty_like(mean) if need else None
+        w, b, g, be = _f32c(conv_w), _f32c(conv_b), _f32c(ln_w), _f32c(ln_b)
+        with torch.cuda.device(x.device):
+            _run("rf_patch_embed_ln_fwd", ptr(xf), ptr(w), ptr(b), ptr(g), ptr(be), ptr(pre), ptr(y), ptr(mean),
+                 ptr(rstd), B, H, W, C, float(eps), _stream(),
+                 work=(4 * (xf.numel() + y.numel() * (2 if need else 1)), 2 * y.numel() * 147), tag="patch_embed_ln_fwd")
+        if need:
+            ctx.save_for_backward(xf, pre, g, mean, rstd)
+            ctx.geom = (Ho, Wo, conv_w.shape)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        xf, pre, g, mean, rstd = ctx.saved_tensors
+        Ho, Wo, wshape = ctx.geom
+        B, N, C = pre.shape
+        dy = dy.contiguous()
+        dpre = torch.empty_like(pre)
+        dg = torch.empty(C, device=pre.device, dtype=torch.float32)
+        db = torch.empty(C, device=pre.device, dtype=torch.float32)
+        with torch.cuda.device(pre.device):
+            _run("rf_add_layernorm_bwd", ptr(pre), ptr(dy), None, ptr(mean), ptr(rstd), ptr(g), None, ptr(dpre), None,
+                 ptr(dg), ptr(db), B * N, C, B * N, 0, _dt_code(dy), 0, _stream(), tag="layernorm_bwd")
+        with torch.autocast('cuda', enabled=False):
+            gconv = dpre.view(B, Ho, Wo, C).permute(0, 3, 1, 2)
+            dw = torch.nn.grad.conv2d_weight(xf, wshape, gconv, stride=4, padding=3)
+            dbias = colsum(dpre.view(B * N, C)) if C % 8 == 0 else dpre.sum((0, 1))
+        return None, dw, dbias, dg, db, None
+
+
 def patch_embed_ln(x, conv_w, conv_b, ln_w, ln_b, eps):
-    raise NotImplementedError("fused patch-embed kernel not built")
+    """Stage-1 OverlapPatchEmbed (reference mix_transformer.py:236-242): returns (tokens f32 [B,N,C], H/4, W/4)."""
+    y = _PatchEmbedLN.apply(x, conv_w, conv_b, ln_w, ln_b, float(eps))
+    return y, (x.shape[2] - 1) // 4 + 1, (x.shape[3] - 1) // 4 + 1

@@ -74,7 +74,14 @@ def _adamw_dev(param, grad, exp_avg, exp_avg_sq, seg_end, seg_wd, beta1, beta2, 
     return param
 
 
+def _patch_embed_ln(x, conv_w, conv_b, ln_w, ln_b, eps):
+    y = F.conv2d(x, conv_w, conv_b, stride=4, padding=3)
+    H, W = y.shape[2:]
+    return F.layer_norm(y.flatten(2).transpose(1, 2), (y.shape[1],), ln_w, ln_b, eps), H, W
+
+
 _PATCH = {
+    "patch_embed_ln": _patch_embed_ln,
     "ema_update_dev_": _ema_dev,
     "adamw_step_dev_": _adamw_dev,
     "layer_norm": _layer_norm,

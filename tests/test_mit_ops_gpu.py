@@ -243,3 +243,37 @@ def test_graphed_train_step_matches_eager():
         assert abs(l0[k] - l1[k]) <= 2e-2 * max(1.0, abs(l0[k])), (k, l0[k], l1[k])
     _close(p1, p0, 2e-3, 2e-3, "parameters")
     _close(e1, e0, 2e-3, 2e-3, "ema parameters")
+
+
+@pytest.mark.parametrize("spec", [(2, 64, 64, 64), (1, 64, 100, 76), (2, 32, 40, 56), (1, 64, 7, 9)])
+def test_patch_embed_ln_fwd_bwd(spec):
+    """Fused 7x7/s4 conv (3 -> C) + LayerNorm(eps 1e-5) vs torch conv2d + layer_norm in fp32 (TF32 off).
+    fp32 arithmetic on both sides: 1e-3 relative (north_star), observed ~1e-5."""
+    B, C, H, W = spec
+    torch.manual_seed(sum(spec))
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        x = torch.randn(B, 3, H, W, device=DEV)
+        conv = torch.nn.Conv2d(3, C, 7, 4, 3).to(DEV)
+        ln = torch.nn.LayerNorm(C).to(DEV)
+        with torch.no_grad():
+            ln.weight.uniform_(0.5, 1.5)
+            ln.bias.uniform_(-0.5, 0.5)
+        ref = F.layer_norm(conv(x).flatten(2).transpose(1, 2), (C,), ln.weight, ln.bias, ln.eps)
+        gy = torch.randn_like(ref)
+        ref.backward(gy)
+        want = [p.grad.clone() for p in (conv.weight, conv.bias, ln.weight, ln.bias)]
+        for p in (conv.weight, conv.bias, ln.weight, ln.bias):
+            p.grad = None
+        y, Ho, Wo = ops.patch_embed_ln(x, conv.weight, conv.bias, ln.weight, ln.bias, ln.eps)
+        assert (Ho, Wo) == ((H - 1) // 4 + 1, (W - 1) // 4 + 1) and y.shape == ref.shape
+        _close(y, ref, 1e-3, 1e-4, "tokens")
+        y.backward(gy)
+        for name, p, w_ in zip(("dW", "db", "dgamma", "dbeta"), (conv.weight, conv.bias, ln.weight, ln.bias), want):
+            _close(p.grad, w_, 1e-3, 1e-3 * max(1.0, float(w_.abs().max())), name)
+        with torch.no_grad():
+            y2, _, _ = ops.patch_embed_ln(x, conv.weight, conv.bias, ln.weight, ln.bias, ln.eps)
+        assert torch.equal(y2, y.detach())
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
