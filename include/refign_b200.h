@@ -253,6 +253,32 @@ int rf_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_av
                   const float* seg_wd, float beta1, float beta2, float eps, int step,
                   float grad_scale, void* stream);
 
+/* ---- training-mode BatchNorm (+ ReLU), channels-last ----------------------- */
+/* Replaces the BatchNorm2d / SyncBatchNorm + ReLU that follows every convolution of the DAFormer head
+ * (models/modules.py:16-56 ConvModule, models/heads/daformer.py:26-35,102-108) on [rows = B*H*W, C]
+ * channels-last activations (dtype 0 = f32, 1 = bf16; C % 8 == 0; statistics and parameters f32).
+ *   rf_bn_stats      sums[0..C) = sum x, sums[C..2C) = sum x^2            (zeroed by the call)
+ *   -- SyncBatchNorm: the caller all-reduces `sums` and passes the global sample count --
+ *   rf_bn_finalize   mean, rstd, scale = gamma * rstd, shift = beta - mean * scale; running statistics
+ *                    (momentum update with the unbiased variance) when running_mean/var != NULL
+ *   rf_bn_apply      y = x * scale + shift, then ReLU when relu != 0
+ *   rf_bn_bwd_reduce sums[0..C) = sum g, sums[C..2C) = sum g * xhat, g = grad_y * (ReLU mask recomputed
+ *                    from x); these are also the bias / weight gradients         (zeroed by the call)
+ *   -- SyncBatchNorm: all-reduce `sums` --
+ *   rf_bn_bwd_apply  grad_x = scale * (g - sums[c]/count - xhat * sums[C+c]/count) */
+int rf_bn_stats(const void* x, float* sums, int64_t rows, int C, int dtype, void* stream);
+int rf_bn_finalize(const float* sums, const float* gamma, const float* beta, float* mean, float* rstd,
+                   float* scale, float* shift, float* running_mean, float* running_var, int C,
+                   double count, float eps, float momentum, void* stream);
+int rf_bn_apply(const void* x, const float* scale, const float* shift, void* y, int64_t rows, int C,
+                int relu, int dtype, void* stream);
+int rf_bn_bwd_reduce(const void* x, const void* grad_y, const float* mean, const float* rstd,
+                     const float* scale, const float* shift, float* sums, int64_t rows, int C,
+                     int relu, int dtype, void* stream);
+int rf_bn_bwd_apply(const void* x, const void* grad_y, const float* mean, const float* rstd,
+                    const float* scale, const float* shift, const float* sums, void* grad_x,
+                    int64_t rows, int C, double count, int relu, int dtype, void* stream);
+
 /* ---- helpers around the library GEMMs of the Linear layers ----------------- */
 /* Bias gradient of a Linear layer (autograd of nn.Linear in mix_transformer.py / modules.py:59-68):
  * out[c] = sum_r g[r,c];  g: [rows,cols] dtype 0 = f32 / 1 = bf16, cols % 8 == 0; out f32 [cols]

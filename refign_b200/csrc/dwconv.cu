@@ -57,11 +57,33 @@ struct Vec8<float> {
   }
 };
 
-__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
+// Exact-erf GELU (nn.GELU default, reference mix_transformer.py:85) with erf evaluated by the
+// Abramowitz-Stegun 7.1.26 rational form (|error| <= 1.5e-7, i.e. fp32-erff accuracy) on one MUFU.RCP and
+// one MUFU.EX2 instead of libdevice's branchy erff: these kernels are issue-bound, not HBM-bound.
+//   erf(z) = 1 - (a1 t + a2 t^2 + a3 t^3 + a4 t^4 + a5 t^5) exp(-z^2),  t = 1 / (1 + p z),  z >= 0
+// exp(-z^2) with z = |v| / sqrt(2) equals exp(-v^2 / 2), the Gaussian the derivative needs as well.
+__device__ __forceinline__ void gelu_parts(float v, float& cdf, float& gauss) {
+  const float z = fabsf(v) * 0.70710678118654752f;
+  float t, den = fmaf(0.3275911f, z, 1.0f);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(den));
+  const float e = -0.72134752044448170f * v * v;     // log2(e) * (-v^2 / 2)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(gauss) : "f"(e));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = fmaf(-poly * t, gauss, 1.0f);
+  cdf = 0.5f * (1.0f + copysignf(erf_abs, v));
+}
+__device__ __forceinline__ float gelu_erf(float v) {
+  float cdf, g;
+  gelu_parts(v, cdf, g);
+  return v * cdf;
+}
 __device__ __forceinline__ float gelu_erf_grad(float v) {
-  const float cdf = 0.5f * (1.0f + erff(v * 0.70710678118654752f));
-  const float pdf = 0.39894228040143268f * __expf(-0.5f * v * v);
-  return cdf + v * pdf;
+  float cdf, g;
+  gelu_parts(v, cdf, g);
+  return fmaf(v * 0.39894228040143268f, g, cdf);
 }
 
 // weights of 8 consecutive channels: native layout [C][9] -> w[k][tap]; 72 contiguous floats
@@ -286,6 +308,190 @@ dwconv3x3_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ g, float* 
   }
 }
 
+// Dilated (ASPP, d = 6 / 12 / 18) variants.  Neighbouring pixels share no taps, but pixels d apart do:
+// a thread owns 8 channels of a 4 x 2 block of outputs on the dilated lattice
+//   (y0 + a d, x0 + b d), a < 4, b < 2,
+// whose taps are the 6 x 4 lattice points (y0 + (a-1) d, x0 + (b-1) d): 24 vector loads for 8 outputs
+// (3 per output instead of 9), which is what bounds these kernels (L2 -> SM traffic).
+constexpr int DL_A = 4, DL_B = 2;
+struct DilGeom {
+  int yblocks, xblocks;   // lattice blocks per image: d * ceil(ceil(H/d) / DL_A), d * ceil(ceil(W/d) / DL_B)
+};
+__host__ __device__ inline DilGeom dil_geom(int H, int W, int d) {
+  DilGeom g;
+  g.yblocks = d * (((H + d - 1) / d + DL_A - 1) / DL_A);
+  g.xblocks = d * (((W + d - 1) / d + DL_B - 1) / DL_B);
+  return g;
+}
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(128)
+dwconv3x3_dil_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                     T* __restrict__ y, int B, int H, int W, int C, int dil, int act) {
+  const int CG = C / DW_VEC;
+  const DilGeom g = dil_geom(H, W, dil);
+  const long total = (long)B * g.yblocks * g.xblocks * CG;
+  const long gid = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int cg = (int)(gid % CG);
+  long r = gid / CG;
+  const int xb = (int)(r % g.xblocks);
+  r /= g.xblocks;
+  const int yb = (int)(r % g.yblocks);
+  const int b = (int)(r / g.yblocks);
+  const int y0 = (yb % dil) + (yb / dil) * DL_A * dil;
+  const int x0 = (xb % dil) + (xb / dil) * DL_B * dil;
+  const int c0 = cg * DW_VEC;
+  float wr[8][9];
+  load_w72(w, c0, wr);
+  float acc[DL_A][DL_B][8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float bk = (MODE != 1 && bias != nullptr) ? __ldg(bias + c0 + k) : 0.f;
+#pragma unroll
+    for (int a = 0; a < DL_A; ++a)
+#pragma unroll
+      for (int bb = 0; bb < DL_B; ++bb) acc[a][bb][k] = bk;
+  }
+  const T* xbase = x + (long)b * H * W * C + c0;
+#pragma unroll
+  for (int p = 0; p < DL_A + 2; ++p) {
+    const int iy = y0 + (p - 1) * dil;
+    if (iy < 0 || iy >= H) continue;
+#pragma unroll
+    for (int q = 0; q < DL_B + 2; ++q) {
+      const int ix = x0 + (q - 1) * dil;
+      if (ix < 0 || ix >= W) continue;
+      float v[8];
+      Vec8<T>::load(xbase + ((long)iy * W + ix) * C, v);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int a = p - i;
+        if (a < 0 || a >= DL_A) continue;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const int bb = q - j;
+          if (bb < 0 || bb >= DL_B) continue;
+          const int tap = (MODE == 1) ? (8 - (i * 3 + j)) : (i * 3 + j);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[a][bb][k] = fmaf(v[k], wr[k][tap], acc[a][bb][k]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < DL_A; ++a) {
+    const int yy = y0 + a * dil;
+    if (yy >= H) continue;
+#pragma unroll
+    for (int bb = 0; bb < DL_B; ++bb) {
+      const int xx = x0 + bb * dil;
+      if (xx >= W) continue;
+      if (MODE == 0 && act) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[a][bb][k] = gelu_erf(acc[a][bb][k]);
+      }
+      Vec8<T>::store(y + (((long)b * H + yy) * W + xx) * C + c0, acc[a][bb]);
+    }
+  }
+}
+
+// Dilated weight gradient on the same 4 x 2 lattice blocks (24 + 8 loads per 8 pixels instead of 80);
+// CTA = 32 channel groups x 8 block lanes, shared-memory + one red.global per (channel, tap) per CTA.
+template <typename T>
+__global__ void __launch_bounds__(WG_CG * WG_PL)
+dwconv3x3_dil_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ g, float* __restrict__ dw,
+                           float* __restrict__ db, int B, int H, int W, int C, int dil, int blocks_per_cta) {
+  __shared__ float red[80][WG_CG];
+  const int CG = C / DW_VEC;
+  const int lane_cg = threadIdx.x % WG_CG, pl = threadIdx.x / WG_CG;
+  const int cg = blockIdx.x * WG_CG + lane_cg;
+  const bool live = cg < CG;
+  const int c0 = cg * DW_VEC;
+  const DilGeom geo = dil_geom(H, W, dil);
+  const long nblk = (long)B * geo.yblocks * geo.xblocks;
+  for (int i = threadIdx.x; i < 80 * WG_CG; i += WG_CG * WG_PL) (&red[0][0])[i] = 0.f;
+  __syncthreads();
+  if (live) {
+    float acc[8][9];
+    float accb[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      accb[k] = 0.f;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) acc[k][t] = 0.f;
+    }
+    const long n0 = (long)blockIdx.y * blocks_per_cta;
+    const long n1 = (n0 + blocks_per_cta < nblk) ? n0 + blocks_per_cta : nblk;
+    for (long n = n0 + pl; n < n1; n += WG_PL) {
+      const int xb = (int)(n % geo.xblocks);
+      const int yb = (int)((n / geo.xblocks) % geo.yblocks);
+      const int b = (int)(n / ((long)geo.xblocks * geo.yblocks));
+      const int y0 = (yb % dil) + (yb / dil) * DL_A * dil;
+      const int x0 = (xb % dil) + (xb / dil) * DL_B * dil;
+      const T* xbase = x + (long)b * H * W * C + c0;
+      const T* gbase = g + (long)b * H * W * C + c0;
+      float gv[DL_A][DL_B][8];
+#pragma unroll
+      for (int a = 0; a < DL_A; ++a)
+#pragma unroll
+        for (int bb = 0; bb < DL_B; ++bb) {
+          const int yy = y0 + a * dil, xx = x0 + bb * dil;
+          if (yy < H && xx < W) {
+            Vec8<T>::load(gbase + ((long)yy * W + xx) * C, gv[a][bb]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) gv[a][bb][k] = 0.f;
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) accb[k] += gv[a][bb][k];
+        }
+#pragma unroll
+      for (int p = 0; p < DL_A + 2; ++p) {
+        const int iy = y0 + (p - 1) * dil;
+        if (iy < 0 || iy >= H) continue;
+#pragma unroll
+        for (int q = 0; q < DL_B + 2; ++q) {
+          const int ix = x0 + (q - 1) * dil;
+          if (ix < 0 || ix >= W) continue;
+          float v[8];
+          Vec8<T>::load(xbase + ((long)iy * W + ix) * C, v);
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const int a = p - i;
+            if (a < 0 || a >= DL_A) continue;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              const int bb = q - j;
+              if (bb < 0 || bb >= DL_B) continue;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) acc[k][i * 3 + j] = fmaf(gv[a][bb][k], v[k], acc[k][i * 3 + j]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) atomicAdd(&red[k * 9 + t][lane_cg], acc[k][t]);
+      atomicAdd(&red[72 + k][lane_cg], accb[k]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 80 * WG_CG; i += WG_CG * WG_PL) {
+    const int e = i / WG_CG, l = i % WG_CG;
+    const int gcg = blockIdx.x * WG_CG + l;
+    if (gcg >= CG) continue;
+    const float v = red[e][l];
+    if (e < 72) {
+      atomicAdd(dw + (long)(gcg * DW_VEC + e / 9) * 9 + e % 9, v);
+    } else if (db != nullptr) {
+      atomicAdd(db + gcg * DW_VEC + (e - 72), v);
+    }
+  }
+}
+
 // Dilation-1 weight gradient: a thread owns 8 channels of PPT consecutive pixels of ROWS rows and slides
 // the 3 x (PPT+2) input window like the forward, so each input vector is loaded once per thread
 // ((3*(PPT+2) + PPT) / PPT = 4.75 loads per pixel instead of 10).  CTA = 32 channel groups x 8 pixel
@@ -392,6 +598,15 @@ static int launch_dw(const void* x, const float* w, const float* bias, const voi
     RF_CHECK_LAUNCH(name);
     return RF_OK;
   }
+  if (MODE != 2 && dil >= 2) {
+    const DilGeom g = dil_geom(H, W, dil);
+    const long total = (long)B * g.yblocks * g.xblocks * (C / DW_VEC);
+    const long blocks = (total + 127) / 128;
+    RF_REQUIRE(blocks < (1l << 31), "%s: grid too large", name);
+    dwconv3x3_dil_kernel<T, MODE><<<(unsigned)blocks, 128, 0, st>>>((const T*)x, w, bias, (T*)y, B, H, W, C, dil, act);
+    RF_CHECK_LAUNCH(name);
+    return RF_OK;
+  }
   constexpr int PPT = 4;
   const long total = (long)B * H * ((W + PPT - 1) / PPT) * (C / DW_VEC);
   const long blocks = (total + 255) / 256;
@@ -477,6 +692,24 @@ extern "C" int rf_dwconv3x3_nhwc_bwd_weight(const void* x, const void* grad_pre,
       dwconv3x3_d1_wgrad_kernel<float, PPT, ROWS><<<grid, WG_CG * WG_PL, 0, st>>>(
           (const float*)x, (const float*)grad_pre, grad_weight, grad_bias, B, H, W, C);
     RF_CHECK_LAUNCH("dwconv3x3_d1_wgrad_kernel");
+    return RF_OK;
+  }
+  if (dilation >= 2) {
+    const DilGeom geo = dil_geom(H, W, dilation);
+    const long nblk = (long)B * geo.yblocks * geo.xblocks;
+    long per = nblk * gx / ((long)kNumSMs * 8);   // lattice blocks per CTA: ~8 CTAs per SM
+    if (per < 16) per = 16;
+    if (per > 512) per = 512;
+    const long gy = (nblk + per - 1) / per;
+    RF_REQUIRE(gy <= 65535, "rf_dwconv3x3_nhwc_bwd_weight: too many block strips");
+    dim3 grid((unsigned)gx, (unsigned)gy);
+    if (dtype == 1)
+      dwconv3x3_dil_wgrad_kernel<__nv_bfloat16><<<grid, WG_CG * WG_PL, 0, st>>>(
+          (const __nv_bfloat16*)x, (const __nv_bfloat16*)grad_pre, grad_weight, grad_bias, B, H, W, C, dilation, (int)per);
+    else
+      dwconv3x3_dil_wgrad_kernel<float><<<grid, WG_CG * WG_PL, 0, st>>>(
+          (const float*)x, (const float*)grad_pre, grad_weight, grad_bias, B, H, W, C, dilation, (int)per);
+    RF_CHECK_LAUNCH("dwconv3x3_dil_wgrad_kernel");
     return RF_OK;
   }
   // pixel strips per CTA: ~8 CTAs per SM over the machine, 64..1024 pixels each

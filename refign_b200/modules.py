@@ -92,10 +92,25 @@ class ConvBNReLU(nn.Module):
             else:
                 x = conv(x)
             if self.use_norm:
+                if self._fused_bn_ok(x):
+                    # training-mode BN (+ ReLU) in one channels-last sweep per pass (SyncBN-aware)
+                    relu = self.use_activation and isinstance(self.activation, nn.ReLU)
+                    x = ops.batch_norm_act(x, self.bn, relu)
+                    if relu or not self.use_activation:
+                        return x
+                    return self.activation(x)
                 x = self.bn(x)
         if self.use_activation:
             x = self.activation(x)
         return x
+
+    def _fused_bn_ok(self, x):
+        bn = self.bn
+        return (isinstance(bn, (nn.BatchNorm2d, nn.SyncBatchNorm)) and bn.training and bn.momentum is not None
+                and x.is_cuda and x.dim() == 4 and x.shape[1] % 8 == 0
+                and x.dtype in (torch.float32, torch.bfloat16) and bn.running_mean is not None
+                and bn.running_mean.dtype == torch.float32
+                and (bn.weight is None or bn.weight.dtype == torch.float32))
 
 
 class MLP(nn.Module):

@@ -398,6 +398,91 @@ def adamw_step_dev_(param, grad, exp_avg, exp_avg_sq, seg_end, seg_wd, beta1, be
     return param
 
 
+# --------------------------------------------------------------------------
+# training-mode BatchNorm (+ ReLU), channels-last (reference: models/modules.py:16-56)
+# --------------------------------------------------------------------------
+class _BatchNormAct(torch.autograd.Function):
+    """y = act(batch_norm(x)) on a contiguous [B,H,W,C] tensor with batch statistics (training mode);
+    ``group`` != None all-reduces the statistics (SyncBatchNorm semantics).  Updates the running
+    statistics in place like nn.BatchNorm2d."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, relu, group, world):
+        require_cuda(x, weight, bias)
+        C = x.shape[-1]
+        rows = x.numel() // C
+        dt = _dt_code(x)
+        dev = x.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        sums = torch.empty(2 * C, **f32)
+        stats = torch.empty(4, C, **f32)                     # mean, rstd, scale, shift
+        y = torch.empty_like(x)
+        w = None if weight is None else _f32c(weight)
+        b = None if bias is None else _f32c(bias)
+        nbytes = x.numel() * x.element_size()
+        with torch.cuda.device(dev):
+            _run("rf_bn_stats", ptr(x), ptr(sums), rows, C, dt, _stream(), work=(nbytes, 3 * x.numel()), tag="bn_stats")
+            count = rows
+            if group is not None and world > 1:
+                torch.distributed.all_reduce(sums, group=group)
+                count = rows * world
+            _run("rf_bn_finalize", ptr(sums), ptr(w), ptr(b), ptr(stats[0]), ptr(stats[1]), ptr(stats[2]),
+                 ptr(stats[3]), ptr(running_mean), ptr(running_var), C, float(count), float(eps), float(momentum),
+                 _stream(), tag="bn_finalize")
+            _run("rf_bn_apply", ptr(x), ptr(stats[2]), ptr(stats[3]), ptr(y), rows, C, int(bool(relu)), dt, _stream(),
+                 work=(2 * nbytes, 2 * x.numel()), tag="bn_apply")
+        ctx.save_for_backward(x, stats)
+        ctx.cfg = (bool(relu), group, world, count, weight is not None, bias is not None)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        x, stats = ctx.saved_tensors
+        relu, group, world, count, has_w, has_b = ctx.cfg
+        C = x.shape[-1]
+        rows = x.numel() // C
+        dt = _dt_code(x)
+        gy = gy.contiguous()
+        if gy.dtype != x.dtype:
+            gy = gy.to(x.dtype)
+        sums = torch.empty(2 * C, device=x.device, dtype=torch.float32)
+        gx = torch.empty_like(x)
+        nbytes = x.numel() * x.element_size()
+        with torch.cuda.device(x.device):
+            _run("rf_bn_bwd_reduce", ptr(x), ptr(gy), ptr(stats[0]), ptr(stats[1]), ptr(stats[2]), ptr(stats[3]),
+                 ptr(sums), rows, C, int(relu), dt, _stream(), work=(2 * nbytes, 6 * x.numel()), tag="bn_bwd_reduce")
+            # local sums are the parameter gradients (the runtime all-reduces all gradients at the end)
+            gb = sums[:C].clone() if has_b else None
+            gw = sums[C:].clone() if has_w else None
+            if group is not None and world > 1:
+                torch.distributed.all_reduce(sums, group=group)
+            _run("rf_bn_bwd_apply", ptr(x), ptr(gy), ptr(stats[0]), ptr(stats[1]), ptr(stats[2]), ptr(stats[3]),
+                 ptr(sums), ptr(gx), rows, C, float(count), int(relu), dt, _stream(),
+                 work=(3 * nbytes, 8 * x.numel()), tag="bn_bwd_apply")
+        return gx, gw, gb, None, None, None, None, None, None, None
+
+
+def batch_norm_act(x, bn, relu):
+    """Training-mode ``relu(bn(x))`` (or ``bn(x)``) for a logical-NCHW tensor held channels-last; ``bn`` is an
+    nn.BatchNorm2d / nn.SyncBatchNorm in training mode with a fixed momentum.  Returns the same kind of
+    tensor.  Replaces ATen's channels-last batch-norm kernels + the separate ReLU (reference
+    models/modules.py:16-56)."""
+    xh = x.permute(0, 2, 3, 1)
+    if not xh.is_contiguous():
+        xh = xh.contiguous()
+    group, world = None, 1
+    if isinstance(bn, torch.nn.SyncBatchNorm) and torch.distributed.is_available() and torch.distributed.is_initialized():
+        group = bn.process_group if bn.process_group is not None else torch.distributed.group.WORLD
+        world = torch.distributed.get_world_size(group)
+    rm = bn.running_mean if bn.track_running_stats else None
+    rv = bn.running_var if bn.track_running_stats else None
+    y = _BatchNormAct.apply(xh, bn.weight, bn.bias, rm, rv, bn.momentum, bn.eps, relu, group, world)
+    if bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    return y.permute(0, 3, 1, 2)
+
+
 @torch.no_grad()
 def cast_bf16_(dst_bf16, src_f32):
     """dst <- bf16(src) over flat buffers (refresh of the bf16 shadow weights)."""

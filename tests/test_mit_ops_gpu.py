@@ -277,3 +277,38 @@ def test_patch_embed_ln_fwd_bwd(spec):
         assert torch.equal(y2, y.detach())
     finally:
         torch.backends.cudnn.allow_tf32 = old
+
+
+@pytest.mark.parametrize("spec", [(2, 16, 12, 64, True), (3, 9, 7, 256, False), (2, 32, 32, 1024, True)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_batch_norm_relu_fwd_bwd(spec, dtype):
+    """Training-mode BatchNorm (+ ReLU) on channels-last activations vs nn.BatchNorm2d + ReLU in fp32 on the
+    same (rounded) inputs, including the running-statistics update.  fp32: 1e-3 relative; bf16 I/O: two
+    bf16 ulps of the output scale."""
+    B, H, W, C, relu = spec
+    torch.manual_seed(sum(spec[:4]))
+    x = (torch.randn(B, C, H, W, device=DEV) * 1.7 + 0.4).to(dtype).contiguous(memory_format=torch.channels_last)
+    gy = torch.randn(B, C, H, W, device=DEV).to(dtype).contiguous(memory_format=torch.channels_last)
+    ref_bn = torch.nn.BatchNorm2d(C).to(DEV).train()
+    with torch.no_grad():
+        ref_bn.weight.uniform_(0.5, 1.5)
+        ref_bn.bias.uniform_(-0.5, 0.5)
+    import copy
+    my_bn = copy.deepcopy(ref_bn)
+    xr = x.detach().clone().float().requires_grad_(True)
+    yr = ref_bn(xr)
+    if relu:
+        yr = torch.relu(yr)
+    yr.backward(gy.float())
+    xm = x.detach().clone().requires_grad_(True)
+    ym = ops.batch_norm_act(xm, my_bn, relu)
+    assert ym.dtype == dtype and ym.shape == x.shape
+    ym.backward(gy)
+    rt, at = (1e-3, 1e-4) if dtype == torch.float32 else (2 * 2 ** -8, 2 * 2 ** -8)
+    _close(ym, yr, rt, at * max(1.0, float(yr.abs().max())), "y")
+    _close(xm.grad, xr.grad, rt, (1e-4 if dtype == torch.float32 else 3e-2) * max(1.0, float(xr.grad.abs().max())), "dx")
+    _close(my_bn.weight.grad, ref_bn.weight.grad, 1e-3, 2e-3 * max(1.0, float(ref_bn.weight.grad.abs().max())), "dgamma")
+    _close(my_bn.bias.grad, ref_bn.bias.grad, 1e-3, 2e-3 * max(1.0, float(ref_bn.bias.grad.abs().max())), "dbeta")
+    _close(my_bn.running_mean, ref_bn.running_mean, 1e-4, 1e-5, "running_mean")
+    _close(my_bn.running_var, ref_bn.running_var, 1e-4, 1e-5, "running_var")
+    assert int(my_bn.num_batches_tracked) == 1
