@@ -121,6 +121,14 @@ class ClockSampler:
         return out
 
 
+# DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of one launch from the `ncu --set full` captures
+# summarised in profiles/r01_ncu_full_kernel_metrics.json, at the 1024x1024 stage-1 shape (B2 N65536 M1024, 1 head)
+NCU_TRAFFIC = {
+    "sr_attention_bwd": {"bytes": 51.41e6 + 0.73e6 + 36.21e6, "shape": "B2 N65536 M1024 h1 (dq + dkv kernels)",
+                         "algorithmic_bytes": 2 * (4 * 2 * 65536 * 64 + 2 * 2 * 1024 * 128)},
+}
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -253,7 +261,8 @@ def main():
         h2d = sum(v.numel() * v.element_size() for v in host.values())
 
         def e2e_step(i):
-            b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+            # graph mode: training_step copies the pinned host tensors straight into its static device inputs
+            b = host if not args.no_graphs else {k: v.to(dev, non_blocking=True) for k, v in host.items()}
             model.training_step(b, i)
             return float(model._logged["train_loss_uda_trg"])  # 4-byte D2H read of the step's result
 
@@ -283,8 +292,12 @@ def main():
         tensor_bound = name.startswith("sr_attention") or name.startswith("global_corr_umma")
         if tensor_bound:
             ach = d["flops"] / d["calls"] / (per_ms * 1e-3) / 1e12
+            t = NCU_TRAFFIC.get(name)
             roof = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": tf, "unit": "TFLOP/s",
-                    "frac": ach / tf, "traffic": None}
+                    "frac": ach / tf, "traffic": t["bytes"] if t else None}
+            if t:
+                roof["traffic_note"] = ("ncu dram bytes of ONE launch at %s; algorithmic bytes of that launch %.1f MB"
+                                        % (t["shape"], t["algorithmic_bytes"] / 1e6))
         else:
             ach = d["bytes"] / d["calls"] / (per_ms * 1e-3) / 1e9
             roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",

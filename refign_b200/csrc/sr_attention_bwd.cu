@@ -439,9 +439,10 @@ extern "C" int rf_sr_attention_bwd(const void* q, const void* kv, const void* ou
     RF_CUDA(cudaMemsetAsync(grad_kv_f32, 0, sizeof(float) * (size_t)B * M * 2 * C, st));
     const int kvchunks = (M + 127) / 128;
     const int ntiles = (N + 63) / 64;
-    // enough query splits for ~2 CTAs per SM, at least 4 tiles each
+    // query splits so that ONE wave of CTAs (2 per SM) covers the work -- rounding up would leave a few
+    // CTAs for a second wave and nearly double the kernel time; at least 4 tiles per split
     long base = (long)B * heads * kvchunks;
-    int splits = (int)((2l * kNumSMs + base - 1) / base);
+    int splits = (int)((2l * kNumSMs) / base);
     if (splits > ntiles / 4) splits = ntiles / 4;
     if (splits < 1) splits = 1;
     const int tps = (ntiles + splits - 1) / splits;
