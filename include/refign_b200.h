@@ -169,11 +169,13 @@ int rf_dwconv3x3_nhwc_bwd_input(const void* grad_y, const float* weight, void* g
 int rf_dwconv3x3_gelu_bwd_pre(const void* x, const float* weight, const float* bias,
                               const void* grad_out, void* grad_pre, int B, int H, int W,
                               int C, int dilation, int dtype, void* stream);
-/* grad_weight f32 [C,1,3,3] and grad_bias f32 [C] (or NULL); both are zeroed
- * by the call and then accumulated with fp32 atomics. */
+/* grad_weight f32 [C,1,3,3] and grad_bias f32 [C] (or NULL), accumulated with fp32 atomics.
+ * accumulate == 0: both are zeroed by the call first (autograd's "fresh gradient" contract);
+ * accumulate != 0: the sums are added to what the buffers hold -- the runtime passes views of
+ * its flat gradient buffer, which replaces the reference's per-parameter AccumulateGrad adds. */
 int rf_dwconv3x3_nhwc_bwd_weight(const void* x, const void* grad_pre, float* grad_weight,
                                  float* grad_bias, int B, int H, int W, int C, int dilation,
-                                 int dtype, void* stream);
+                                 int dtype, int accumulate, void* stream);
 
 /* ---- MiT spatial-reduction attention core (tcgen05 / TMEM / TMA) --------- */
 /* Replaces the attention core of Attention.forward
@@ -224,13 +226,15 @@ int rf_add_layernorm_fwd(const void* x, const void* branch, const float* scale,
                          int64_t rows_per_sample, float eps, int x_dtype, int branch_dtype,
                          int y_dtype, void* stream);
 /* Backward: dxn = dxn_in (or 0 when NULL) + LN'(dy);  dbranch = scale * dxn (or NULL);
- * dgamma, dbeta: f32 [C], zeroed by the call then accumulated with fp32 atomics.
+ * dgamma, dbeta: f32 [C], zeroed by the call (unless accumulate != 0, see
+ * rf_dwconv3x3_nhwc_bwd_weight) then accumulated with fp32 atomics.
  * xn: the forward's xn (dtype xn_dtype), dy dtype dy_dtype, dbranch dtype branch_dtype. */
 int rf_add_layernorm_bwd(const void* xn, const void* dy, const float* dxn_in,
                          const float* mean, const float* rstd, const float* gamma,
                          const float* scale, float* dxn, void* dbranch, float* dgamma,
                          float* dbeta, int64_t rows, int C, int64_t rows_per_sample,
-                         int xn_dtype, int dy_dtype, int branch_dtype, void* stream);
+                         int xn_dtype, int dy_dtype, int branch_dtype, int accumulate,
+                         void* stream);
 
 /* ---- optimiser-side multi-tensor ops on flat buffers ------------------- */
 /* Replaces update_momentum_encoder (segmentation_model.py:680-689):
@@ -282,8 +286,9 @@ int rf_bn_bwd_apply(const void* x, const void* grad_y, const float* mean, const 
 /* ---- helpers around the library GEMMs of the Linear layers ----------------- */
 /* Bias gradient of a Linear layer (autograd of nn.Linear in mix_transformer.py / modules.py:59-68):
  * out[c] = sum_r g[r,c];  g: [rows,cols] dtype 0 = f32 / 1 = bf16, cols % 8 == 0; out f32 [cols]
- * (zeroed by the call). */
-int rf_colsum(const void* g, float* out, int64_t rows, int cols, int dtype, void* stream);
+ * (zeroed by the call unless accumulate != 0). */
+int rf_colsum(const void* g, float* out, int64_t rows, int cols, int dtype, int accumulate,
+              void* stream);
 /* fp32 -> bf16 copy of a flat parameter buffer (the bf16 shadow weights read by the tensor-core
  * GEMMs; replaces the per-tensor autocast casts of the reference's AMP path). */
 int rf_cast_bf16(const float* src, void* dst, int64_t n, void* stream);

@@ -366,6 +366,37 @@ static inline float orc_log_pos(float x) {
   return r;
 }
 
+
+/* exp(max(x, -86)) for x <= 0 (softmax arguments); the clamp keeps the result normal so
+ * 2^n is applied on the exponent field; rint via the 1.5*2^23 magic constant.  Mirrors
+ * exact_exp_nonpos / exact_exp_nonpos2 in refign_b200/csrc/refine.cu step for step. */
+static inline float orc_exp_nonpos(float x) {
+  x = fmaxf(x, -86.0f);
+  const float t = x * 1.44269504088896341f;
+  const float m = t + 12582912.0f;
+  const float n = m - 12582912.0f;
+  float r = __builtin_fmaf(n, -0.693359375f, x);
+  r = __builtin_fmaf(n, 2.12194440e-4f, r);
+  float p = 1.9875691500e-4f;
+  p = __builtin_fmaf(p, r, 1.3981999507e-3f);
+  p = __builtin_fmaf(p, r, 8.3334519073e-3f);
+  p = __builtin_fmaf(p, r, 4.1665795894e-2f);
+  p = __builtin_fmaf(p, r, 1.6666665459e-1f);
+  p = __builtin_fmaf(p, r, 5.0000001201e-1f);
+  const float r2 = r * r;
+  float y = __builtin_fmaf(p, r2, r);
+  y = y + 1.0f;
+  return bits_to_float(float_to_bits(y) + (float_to_bits(m) << 23));
+}
+
+/* a / b given r = RN(1/b): q0 = RN(a r), rem = fma(-q0, b, a), q = fma(rem, r, q0)
+ * (mirrors exact_div_by in refine.cu). */
+static inline float orc_div_by(float a, float b, float r) {
+  const float q0 = a * r;
+  const float rem = __builtin_fmaf(-q0, b, a);
+  return __builtin_fmaf(rem, r, q0);
+}
+
 #define ORC_MAXK 64
 #define ORC_ENT_SCALE 1099511627776.0 /* 2^40 */
 
@@ -383,18 +414,16 @@ void orc_refine_entropy(const float *logits_trg, int64_t *ent_fix, int B,
       const float *p = logits_trg + (long)b * K * HW + i;
       float mx = p[0];
       for (int k = 1; k < K; ++k) mx = p[k * HW] > mx ? p[k * HW] : mx;
-      float e[ORC_MAXK], sum = 0.0f;
+      /* H = lse - (sum_k e_k v_k) / sum with v_k = x_k - max, e_k = exp(v_k) */
+      float sum = 0.0f, dot = 0.0f;
       for (int k = 0; k < K; ++k) {
-        e[k] = orc_expf(p[k * HW] - mx);
-        sum = sum + e[k];
+        const float vk = fmaxf(p[k * HW] - mx, -86.0f);
+        const float ek = orc_exp_nonpos(vk);
+        sum = sum + ek;
+        dot = __builtin_fmaf(ek, vk, dot);
       }
       const float lse = orc_log_pos(sum);
-      float ent = 0.0f;
-      for (int k = 0; k < K; ++k) {
-        const float pk = e[k] / sum;
-        const float lp = (p[k * HW] - mx) - lse;
-        ent = ent - pk * lp;
-      }
+      float ent = lse - dot / sum;
       ent = ent * inv_logk;
       total += (int64_t)llrint((double)ent * ORC_ENT_SCALE);
     }
@@ -439,16 +468,17 @@ void orc_refine_mix(const float *logits_trg, const float *logits_ref,
     }
     float st = 0.0f, sr = 0.0f;
     for (int k = 0; k < K; ++k) {
-      et[k] = orc_expf(pt[k * HW] - mt);
+      et[k] = orc_exp_nonpos(pt[k * HW] - mt);
       st = st + et[k];
-      er[k] = orc_expf(pr[k * HW] - mr);
+      er[k] = orc_exp_nonpos(pr[k * HW] - mr);
       sr = sr + er[k];
     }
+    const float rt = 1.0f / st, rr = 1.0f / sr;
     int at = 0, ar = 0;
     float bt = -1.0f, br = -1.0f;
     for (int k = 0; k < K; ++k) {
-      et[k] = et[k] / st;
-      er[k] = er[k] / sr;
+      et[k] = orc_div_by(et[k], st, rt);
+      er[k] = orc_div_by(er[k], sr, rr);
       if (et[k] > bt) { bt = et[k]; at = k; }
       if (er[k] > br) { br = er[k]; ar = k; }
     }

@@ -34,10 +34,10 @@ _SIGNATURES = {
     "rf_dwconv3x3_nhwc_fwd": (c_int, [c_p, c_p, c_p, c_p] + [c_int] * 7 + [c_p]),
     "rf_dwconv3x3_nhwc_bwd_input": (c_int, [c_p, c_p, c_p] + [c_int] * 6 + [c_p]),
     "rf_dwconv3x3_gelu_bwd_pre": (c_int, [c_p] * 5 + [c_int] * 6 + [c_p]),
-    "rf_dwconv3x3_nhwc_bwd_weight": (c_int, [c_p] * 4 + [c_int] * 6 + [c_p]),
+    "rf_dwconv3x3_nhwc_bwd_weight": (c_int, [c_p] * 4 + [c_int] * 7 + [c_p]),
     "rf_patch_embed_ln_fwd": (c_int, [c_p] * 9 + [c_int, c_int, c_int, c_int, c_f32, c_p]),
     "rf_add_layernorm_fwd": (c_int, [c_p] * 9 + [c_i64, c_int, c_i64, c_f32, c_int, c_int, c_int, c_p]),
-    "rf_add_layernorm_bwd": (c_int, [c_p] * 11 + [c_i64, c_int, c_i64, c_int, c_int, c_int, c_p]),
+    "rf_add_layernorm_bwd": (c_int, [c_p] * 11 + [c_i64, c_int, c_i64, c_int, c_int, c_int, c_int, c_p]),
     "rf_sr_attention_fwd": (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_f32, c_p]),
     "rf_sr_attention_bwd_workspace_bytes": (c_i64, [c_int, c_int, c_int, c_int]),
     "rf_sr_attention_bwd": (c_int, [c_p] * 8 + [c_int, c_int, c_int, c_int, c_f32, c_p]),
@@ -47,7 +47,7 @@ _SIGNATURES = {
     "rf_bn_apply": (c_int, [c_p, c_p, c_p, c_p, c_i64, c_int, c_int, c_int, c_p]),
     "rf_bn_bwd_reduce": (c_int, [c_p] * 7 + [c_i64, c_int, c_int, c_int, c_p]),
     "rf_bn_bwd_apply": (c_int, [c_p] * 8 + [c_i64, c_int, ctypes.c_double, c_int, c_int, c_p]),
-    "rf_colsum": (c_int, [c_p, c_p, c_i64, c_int, c_int, c_p]),
+    "rf_colsum": (c_int, [c_p, c_p, c_i64, c_int, c_int, c_int, c_p]),
     "rf_cast_bf16": (c_int, [c_p, c_p, c_i64, c_p]),
     "rf_ema_update_dev": (c_int, [c_p, c_p, c_i64, c_p, c_p]),
     "rf_adamw_step_dev": (c_int, [c_p, c_p, c_p, c_p, c_i64, c_int, ctypes.POINTER(c_i64), ctypes.POINTER(c_f32),

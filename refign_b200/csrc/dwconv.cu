@@ -14,6 +14,7 @@
 // Arithmetic is fp32; weights/bias are the fp32 parameters in their native [C,1,3,3] layout
 // (72 contiguous floats per thread), so no per-call weight transposes or casts are launched.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "rf_common.cuh"
 
@@ -585,9 +586,347 @@ dwconv3x3_d1_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ g, floa
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Shared-memory tiled dilation-1 kernels for bf16 (the Mix-FFN DWConv of every MiT block: the largest
+// HBM-streaming share of the train step).  These kernels are ISSUE-bound on B200, not bandwidth-bound: at
+// 6.5 TB/s one SM has ~22 issue slots per bf16 element streamed in and out, and a 3x3 depthwise tap set plus an
+// exact-erf GELU costs more than that in scalar fp32.  So the design minimises instructions per element:
+//   * the (8+2) x (TW+2) x 64-channel input tile (128 B per pixel) is staged once with 16-byte cp.async
+//     (zero-fill outside the image = the conv padding), which replaces the 3.75x re-read through L1 with
+//     conflict-free LDS.128 and puts the whole tile's bytes in flight at once;
+//   * all arithmetic is packed f32x2 (FFMA2/FMUL2/FADD2, sm_100): a bf16x2 word unpacks to one channel pair
+//     and the weights are staged as [tap][channel] so that a pair of adjacent channels is one 64-bit operand;
+//   * GELU for bf16 outputs uses Phi(-t) = 2^Q(t), t = min(|v|, 6), Q a degree-6 minimax fit of
+//     log2(0.5 erfc(t / sqrt 2)): gelu(v) = relu(v) - t * 2^Q(t), one MUFU.EX2 per element and
+//     |error| <= 7e-6 absolute / 5e-5 relative (bf16 rounding is 2e-3 relative); the fp32 instantiations used
+//     by the fp32 parity runs keep the 1.5e-7-accurate erf above.
+// Thread map (TW * 8 threads): chunk = tid & 7 owns 8 channels (16 bytes), run = tid >> 3 owns 8 consecutive
+// output pixels of one tile row; a quarter-warp reads the 128 contiguous bytes of one pixel.
+constexpr int DT_TH = 8;    // tile rows
+constexpr int DT_TC = 64;   // channels per tile (bf16: 128 bytes per pixel)
+constexpr int DT_RUN = 8;   // pixels per thread
+
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 f2s(float a) { return make_float2(a, a); }
+
+// bf16x2 word -> (lo, hi) channel pair in fp32: one shift and one mask
+__device__ __forceinline__ float2 bf2_unpack(unsigned u) {
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+__device__ __forceinline__ unsigned bf2_pack(float2 v) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
+  return *reinterpret_cast<const unsigned*>(&h);
+}
+
+// e = Phi(-t) = 0.5 erfc(t / sqrt 2) for the lane-wise clamped magnitudes t = min(|v|, 6)
+__device__ __forceinline__ float2 normal_tail2(float2 t) {
+  float2 q = f2s(2.2999249267741106e-05f);
+  q = __ffma2_rn(q, t, f2s(-0.0006114901625551283f));
+  q = __ffma2_rn(q, t, f2s(0.007200188934803009f));
+  q = __ffma2_rn(q, t, f2s(-0.05120821297168732f));
+  q = __ffma2_rn(q, t, f2s(-0.46122226119041443f));
+  q = __ffma2_rn(q, t, f2s(-1.150214433670044f));
+  q = __ffma2_rn(q, t, f2s(-1.000058889389038f));
+  float2 e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(q.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(q.y));
+  return e;
+}
+// gelu(v) = relu(v) - t * Phi(-t)
+__device__ __forceinline__ float2 gelu_fast2(float2 v) {
+  const float2 t = f2(fminf(fabsf(v.x), 6.0f), fminf(fabsf(v.y), 6.0f));
+  const float2 e = normal_tail2(t);
+  const float2 r = f2(fmaxf(v.x, 0.0f), fmaxf(v.y, 0.0f));
+  return __ffma2_rn(f2(-t.x, -t.y), e, r);
+}
+// gelu'(v) = Phi(v) + v phi(v),  Phi(v) = 0.5 + copysign(0.5 - Phi(-t), v),  phi(v) = exp(-v^2/2) / sqrt(2 pi)
+__device__ __forceinline__ float2 gelu_fast_grad2(float2 v) {
+  const float2 t = f2(fminf(fabsf(v.x), 6.0f), fminf(fabsf(v.y), 6.0f));
+  const float2 e = normal_tail2(t);
+  const float2 h = __fadd2_rn(f2s(0.5f), f2(-e.x, -e.y));
+  const float2 cdf = __fadd2_rn(f2s(0.5f), f2(copysignf(h.x, v.x), copysignf(h.y, v.y)));
+  const float2 a = __fmul2_rn(__fmul2_rn(v, v), f2s(-0.72134752044448170f));
+  float2 g;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g.x) : "f"(a.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g.y) : "f"(a.y));
+  return __ffma2_rn(__fmul2_rn(v, f2s(0.39894228040143268f)), g, cdf);
+}
+
+// Stage ROWS rows x (TW + 2 * HALO) columns x 8 chunks of a channels-last bf16 image into shared memory with
+// 16-byte cp.async, zero-filling outside the image.  Thread (chunk = tid & 7, slot = tid >> 3) copies tile column
+// `slot` of every row (plus one of the 2 * HALO extra columns for the first slots): no div / mod in the loop.
+template <int TW, int ROWS, int HALO>
+__device__ __forceinline__ void stage_tile(uint4* tile, const __nv_bfloat16* __restrict__ img, int x0, int y0, int Hs,
+                                           int Ws, long pix_pitch, long row_pitch, int tid) {
+  constexpr int IW = TW + 2 * HALO;
+  const int chunk = tid & 7, slot = tid >> 3;
+  const int ix = x0 + slot - HALO, ix2 = x0 + TW + slot - HALO;
+  const bool okx = ix >= 0 && ix < Ws, okx2 = slot < 2 * HALO && ix2 < Ws;
+  const __nv_bfloat16* col = img + ix * pix_pitch + chunk * 8;
+  const __nv_bfloat16* col2 = img + ix2 * pix_pitch + chunk * 8;
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    const int iy = y0 + r - HALO;
+    const bool oky = iy >= 0 && iy < Hs;
+    const long ro = iy * row_pitch;
+    cp_async16(&tile[(r * IW + slot) * 8 + chunk], (oky && okx) ? col + ro : img, (oky && okx) ? 16 : 0);
+    if (slot < 2 * HALO)
+      cp_async16(&tile[(r * IW + TW + slot) * 8 + chunk], (oky && okx2) ? col2 + ro : img, (oky && okx2) ? 16 : 0);
+  }
+}
+
+// A dilation-d 3x3 depthwise conv is d*d independent dilation-1 convs, one per residue class
+// (y mod d, x mod d): the pixels of a class form a sub-image of ceil((H-ry)/d) x ceil((W-rx)/d) pixels with
+// pixel pitch d*C and row pitch d*W*C.  The tile kernels below walk sub-images, so the ASPP branches
+// (d = 6 / 12 / 18) run through the same shared-memory tiles as the Mix-FFN conv (d = 1: one class).
+struct SubImage {
+  int Hs, Ws;               // sub-image size
+  long pix_pitch, row_pitch;
+  long origin;              // element offset of sub-image pixel (0, 0) channel 0 within the batch image
+};
+__device__ __forceinline__ SubImage sub_image(int H, int W, int C, int dil, int ry, int rx) {
+  SubImage s;
+  s.Hs = (H - ry + dil - 1) / dil;
+  s.Ws = (W - rx + dil - 1) / dil;
+  s.pix_pitch = (long)dil * C;
+  s.row_pitch = (long)dil * W * C;
+  s.origin = ((long)ry * W + rx) * C;
+  return s;
+}
+
+template <int MODE, int TW>
+__global__ void __launch_bounds__(TW * 8, 64 / TW)
+dwconv3x3_tile_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                      const float* __restrict__ bias, const __nv_bfloat16* __restrict__ aux,
+                      __nv_bfloat16* __restrict__ y, int B, int H, int W, int C, int dil, int act) {
+  constexpr int NT = TW * 8;
+  constexpr int IW = TW + 2, IH = DT_TH + 2;
+  __shared__ __align__(16) uint4 tile[IH * IW * 8];      // [row][col][chunk], 16 bytes = 8 bf16 channels
+  __shared__ __align__(16) float wsm[10][DT_TC];         // [tap][channel]; row 9 = bias
+  const int tid = threadIdx.x;
+  const int c0 = blockIdx.x * DT_TC;
+  const int tiles_x = ((W + dil - 1) / dil + TW - 1) / TW, tiles_y = ((H + dil - 1) / dil + DT_TH - 1) / DT_TH;
+  int t = blockIdx.y;
+  const int tx = t % tiles_x;
+  t /= tiles_x;
+  const int ty = t % tiles_y;
+  t /= tiles_y;
+  const SubImage si = sub_image(H, W, C, dil, t / dil, t % dil);
+  const int b = blockIdx.z;
+  const int x0 = tx * TW, y0 = ty * DT_TH;
+  const __nv_bfloat16* xb = x + (long)b * H * W * C + si.origin + c0;
+  // ---- stage the input tile (zero-fill = padding) ------------------------------------------------------
+  stage_tile<TW, IH, 1>(tile, xb, x0, y0, si.Hs, si.Ws, si.pix_pitch, si.row_pitch, tid);
+  cp_async_commit();
+  // ---- weights [C][9] -> [tap][channel] (taps flipped for the input gradient), bias -------------------
+  for (int i = tid; i < DT_TC * 9; i += NT) {
+    const int ch = i / 9, tap = i % 9;
+    wsm[MODE == 1 ? 8 - tap : tap][ch] = __ldg(w + (long)c0 * 9 + i);
+  }
+  if (tid < DT_TC) wsm[9][tid] = (MODE != 1 && bias != nullptr) ? __ldg(bias + c0 + tid) : 0.f;
+  cp_async_wait<0>();
+  __syncthreads();
+  // ---- compute -------------------------------------------------------------------------------------
+  const int chunk = tid & 7, run = tid >> 3;
+  const int row = run / (TW / DT_RUN), col0 = (run % (TW / DT_RUN)) * DT_RUN;
+  float2 acc[DT_RUN][4];
+  {
+    const float4 b0 = *reinterpret_cast<const float4*>(&wsm[9][chunk * 8]);
+    const float4 b1 = *reinterpret_cast<const float4*>(&wsm[9][chunk * 8 + 4]);
+#pragma unroll
+    for (int p = 0; p < DT_RUN; ++p) {
+      acc[p][0] = f2(b0.x, b0.y); acc[p][1] = f2(b0.z, b0.w);
+      acc[p][2] = f2(b1.x, b1.y); acc[p][3] = f2(b1.z, b1.w);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float2 wr[3][4];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&wsm[i * 3 + j][chunk * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&wsm[i * 3 + j][chunk * 8 + 4]);
+      wr[j][0] = f2(a0.x, a0.y); wr[j][1] = f2(a0.z, a0.w);
+      wr[j][2] = f2(a1.x, a1.y); wr[j][3] = f2(a1.z, a1.w);
+    }
+    const uint4* trow = &tile[((row + i) * IW + col0) * 8 + chunk];
+#pragma unroll
+    for (int q = 0; q < DT_RUN + 2; ++q) {
+      const uint4 u = trow[q * 8];
+      const float2 v0 = bf2_unpack(u.x), v1 = bf2_unpack(u.y), v2 = bf2_unpack(u.z), v3 = bf2_unpack(u.w);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int p = q - j;  // output pixel col0+p reads input column col0+p+j-1, tile column col0+p+j == col0+q
+        if (p < 0 || p >= DT_RUN) continue;
+        acc[p][0] = __ffma2_rn(v0, wr[j][0], acc[p][0]);
+        acc[p][1] = __ffma2_rn(v1, wr[j][1], acc[p][1]);
+        acc[p][2] = __ffma2_rn(v2, wr[j][2], acc[p][2]);
+        acc[p][3] = __ffma2_rn(v3, wr[j][3], acc[p][3]);
+      }
+    }
+  }
+  // ---- epilogue ------------------------------------------------------------------------------------
+  const int oy = y0 + row;
+  if (oy >= si.Hs) return;
+  const long obase = (long)b * H * W * C + si.origin + oy * si.row_pitch + (x0 + col0) * si.pix_pitch + c0 + chunk * 8;
+#pragma unroll
+  for (int p = 0; p < DT_RUN; ++p) {
+    if (x0 + col0 + p >= si.Ws) break;
+    if (MODE == 0) {
+      if (act) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[p][k] = gelu_fast2(acc[p][k]);
+      }
+    } else if (MODE == 2) {
+      const uint4 g = __ldg(reinterpret_cast<const uint4*>(aux + obase + p * si.pix_pitch));
+      acc[p][0] = __fmul2_rn(bf2_unpack(g.x), gelu_fast_grad2(acc[p][0]));
+      acc[p][1] = __fmul2_rn(bf2_unpack(g.y), gelu_fast_grad2(acc[p][1]));
+      acc[p][2] = __fmul2_rn(bf2_unpack(g.z), gelu_fast_grad2(acc[p][2]));
+      acc[p][3] = __fmul2_rn(bf2_unpack(g.w), gelu_fast_grad2(acc[p][3]));
+    }
+    uint4 o;
+    o.x = bf2_pack(acc[p][0]); o.y = bf2_pack(acc[p][1]); o.z = bf2_pack(acc[p][2]); o.w = bf2_pack(acc[p][3]);
+    *reinterpret_cast<uint4*>(y + obase + p * si.pix_pitch) = o;
+  }
+}
+
+template <int MODE>
+static int launch_dw_tile(const void* x, const float* w, const float* bias, const void* aux, void* y, int B, int H,
+                          int W, int C, int dil, int act, cudaStream_t st, const char* name) {
+  const int Ws = (W + dil - 1) / dil, Hs = (H + dil - 1) / dil;   // largest residue-class sub-image
+  const bool narrow = dil > 1 || ((Ws % 32 != 0) && (Ws <= 16 || Ws % 32 <= 16));
+  const int TW = narrow ? 16 : 32;
+  const long tiles = (long)((Ws + TW - 1) / TW) * ((Hs + DT_TH - 1) / DT_TH) * dil * dil;
+  RF_REQUIRE(tiles <= 65535 && B <= 65535, "%s: grid too large", name);
+  dim3 grid((unsigned)(C / DT_TC), (unsigned)tiles, (unsigned)B);
+  if (narrow)
+    dwconv3x3_tile_kernel<MODE, 16><<<grid, 128, 0, st>>>((const __nv_bfloat16*)x, w, bias, (const __nv_bfloat16*)aux,
+                                                         (__nv_bfloat16*)y, B, H, W, C, dil, act);
+  else
+    dwconv3x3_tile_kernel<MODE, 32><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, w, bias, (const __nv_bfloat16*)aux,
+                                                         (__nv_bfloat16*)y, B, H, W, C, dil, act);
+  RF_CHECK_LAUNCH(name);
+  return RF_OK;
+}
+
+// Weight / bias gradient on the same tiles: dw[c][tap] = sum_p g[p,c] x[p + off(tap), c], db[c] = sum_p g[p,c].
+// One CTA (128 threads = 8 chunks x 16 runs, tile 8 x 16 pixels x 64 channels) walks a strided list of tiles of
+// one 64-channel block with its 9 x 8 + 8 partial sums in registers (packed f32x2), staging the x tile (with
+// halo) and the g tile with cp.async; 3 CTAs per SM overlap each other's staging.  At the end the 16 runs are
+// combined by warp shuffles + shared memory and the CTA issues one red.global per (channel, tap).
+constexpr int WT_TW = 16;
+__global__ void __launch_bounds__(128, 3)
+dwconv3x3_tile_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ g,
+                            float* __restrict__ dw, float* __restrict__ db, int B, int H, int W, int C, int dil,
+                            int tiles_x, int tiles_y) {
+  constexpr int TW = WT_TW;
+  constexpr int IW = TW + 2, IH = DT_TH + 2;
+  __shared__ __align__(16) uint4 xt[IH * IW * 8];
+  __shared__ __align__(16) uint4 gt[DT_TH * TW * 8];
+  float (*red)[80][8] = reinterpret_cast<float (*)[80][8]>(xt);   // [warp][tap*8 + k | 72 + k][chunk], reuses xt
+  const int tid = threadIdx.x;
+  const int c0 = blockIdx.x * DT_TC;
+  const int chunk = tid & 7, run = tid >> 3;
+  const int row = run / (TW / DT_RUN), col0 = (run % (TW / DT_RUN)) * DT_RUN;
+  float2 wacc[9][4], bacc[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    bacc[k] = f2s(0.f);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wacc[t][k] = f2s(0.f);
+  }
+  const int ntiles = tiles_x * tiles_y * dil * dil * B;
+  for (int t = blockIdx.y; t < ntiles; t += gridDim.y) {
+    int u = t;
+    const int tx = u % tiles_x;
+    u /= tiles_x;
+    const int ty = u % tiles_y;
+    u /= tiles_y;
+    const int res = u % (dil * dil), b = u / (dil * dil);
+    const SubImage si = sub_image(H, W, C, dil, res / dil, res % dil);
+    const int x0 = tx * TW, y0 = ty * DT_TH;
+    const __nv_bfloat16* xb = x + (long)b * H * W * C + si.origin + c0;
+    const __nv_bfloat16* gb = g + (long)b * H * W * C + si.origin + c0;
+    __syncthreads();   // the previous tile's readers are done
+    stage_tile<TW, IH, 1>(xt, xb, x0, y0, si.Hs, si.Ws, si.pix_pitch, si.row_pitch, tid);
+    stage_tile<TW, DT_TH, 0>(gt, gb, x0, y0, si.Hs, si.Ws, si.pix_pitch, si.row_pitch, tid);   // outside: g = 0
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    float2 gv[DT_RUN][4];
+#pragma unroll
+    for (int p = 0; p < DT_RUN; ++p) {
+      const uint4 u = gt[((row * TW) + col0 + p) * 8 + chunk];
+      gv[p][0] = bf2_unpack(u.x); gv[p][1] = bf2_unpack(u.y); gv[p][2] = bf2_unpack(u.z); gv[p][3] = bf2_unpack(u.w);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) bacc[k] = __fadd2_rn(bacc[k], gv[p][k]);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const uint4* trow = &xt[((row + i) * IW + col0) * 8 + chunk];
+#pragma unroll
+      for (int q = 0; q < DT_RUN + 2; ++q) {
+        const uint4 u = trow[q * 8];
+        const float2 v0 = bf2_unpack(u.x), v1 = bf2_unpack(u.y), v2 = bf2_unpack(u.z), v3 = bf2_unpack(u.w);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const int p = q - j;
+          if (p < 0 || p >= DT_RUN) continue;
+          wacc[i * 3 + j][0] = __ffma2_rn(gv[p][0], v0, wacc[i * 3 + j][0]);
+          wacc[i * 3 + j][1] = __ffma2_rn(gv[p][1], v1, wacc[i * 3 + j][1]);
+          wacc[i * 3 + j][2] = __ffma2_rn(gv[p][2], v2, wacc[i * 3 + j][2]);
+          wacc[i * 3 + j][3] = __ffma2_rn(gv[p][3], v3, wacc[i * 3 + j][3]);
+        }
+      }
+    }
+  }
+  // ---- combine the 16 runs: lanes (chunk, run & 3) -> shuffle over the run bits, then the 4 warps in smem ----
+  __syncthreads();   // xt is reused as the reduction buffer
+  const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+  for (int t = 0; t < 10; ++t) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float2 v = (t < 9) ? wacc[t][k] : bacc[k];
+      v.x += __shfl_xor_sync(0xffffffffu, v.x, 8);
+      v.y += __shfl_xor_sync(0xffffffffu, v.y, 8);
+      v.x += __shfl_xor_sync(0xffffffffu, v.x, 16);
+      v.y += __shfl_xor_sync(0xffffffffu, v.y, 16);
+      if (lane < 8) {
+        red[warp][t * 8 + 2 * k][lane] = v.x;
+        red[warp][t * 8 + 2 * k + 1][lane] = v.y;
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < 80 * 8; i += 128) {
+    const int e = i >> 3, ch = i & 7;        // e = tap * 8 + k  (or 72 + k), channel = c0 + ch * 8 + k
+    const float v = red[0][e][ch] + red[1][e][ch] + red[2][e][ch] + red[3][e][ch];
+    const int k = e & 7, tap = e >> 3;
+    const int c = c0 + ch * 8 + k;
+    if (tap < 9) {
+      atomicAdd(dw + (long)c * 9 + tap, v);
+    } else if (db != nullptr) {
+      atomicAdd(db + c, v);
+    }
+  }
+}
+
+// RF_DWCONV_IMPL=direct selects the register-window kernels for A/B measurements (read once)
+static bool dw_use_tile() {
+  static const bool v = [] {
+    const char* e = getenv("RF_DWCONV_IMPL");
+    return !(e && e[0] == 'd');
+  }();
+  return v;
+}
+
 template <typename T, int MODE>
 static int launch_dw(const void* x, const float* w, const float* bias, const void* aux, void* y, int B, int H, int W,
                      int C, int dil, int act, cudaStream_t st, const char* name) {
+  if (sizeof(T) == 2 && C % DT_TC == 0 && dw_use_tile() && dil <= H && dil <= W &&
+      (long)dil * dil * (((W + dil - 1) / dil + 15) / 16) * (((H + dil - 1) / dil + 7) / 8) <= 65535)
+    return launch_dw_tile<MODE>(x, w, bias, aux, y, B, H, W, C, dil, act, st, name);
   if (dil == 1) {
     constexpr int PPT = 8;
     const long total = (long)B * H * ((W + PPT - 1) / PPT) * (C / DW_VEC);
@@ -670,15 +1009,33 @@ extern "C" int rf_dwconv3x3_gelu_bwd_pre(const void* x, const float* weight, con
 }
 
 extern "C" int rf_dwconv3x3_nhwc_bwd_weight(const void* x, const void* grad_pre, float* grad_weight, float* grad_bias,
-                                            int B, int H, int W, int C, int dilation, int dtype, void* stream) {
+                                            int B, int H, int W, int C, int dilation, int dtype, int accumulate,
+                                            void* stream) {
   int rc = check_dw(x, grad_pre, grad_weight, B, H, W, C, dilation, dtype, "rf_dwconv3x3_nhwc_bwd_weight");
   if (rc != RF_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  RF_CUDA(cudaMemsetAsync(grad_weight, 0, sizeof(float) * 9 * (size_t)C, st));
-  if (grad_bias) RF_CUDA(cudaMemsetAsync(grad_bias, 0, sizeof(float) * (size_t)C, st));
+  if (!accumulate) {
+    RF_CUDA(cudaMemsetAsync(grad_weight, 0, sizeof(float) * 9 * (size_t)C, st));
+    if (grad_bias) RF_CUDA(cudaMemsetAsync(grad_bias, 0, sizeof(float) * (size_t)C, st));
+  }
   const long npix = (long)B * H * W;
   const int CG = C / DW_VEC;
   const int gx = (CG + WG_CG - 1) / WG_CG;
+  if (dtype == 1 && C % DT_TC == 0 && dw_use_tile() && dilation <= H && dilation <= W) {
+    const int tiles_x = ((W + dilation - 1) / dilation + WT_TW - 1) / WT_TW;
+    const int tiles_y = ((H + dilation - 1) / dilation + DT_TH - 1) / DT_TH;
+    const long ntiles = (long)tiles_x * tiles_y * dilation * dilation * B;
+    RF_REQUIRE(ntiles < (1l << 31), "rf_dwconv3x3_nhwc_bwd_weight: too many tiles");
+    const long cblocks = C / DT_TC;
+    long gy = ((long)kNumSMs * 3 + cblocks - 1) / cblocks;   // ~3 CTAs per SM over all channel blocks
+    if (gy > ntiles) gy = ntiles;
+    if (gy < 1) gy = 1;
+    dim3 grid((unsigned)cblocks, (unsigned)gy);
+    dwconv3x3_tile_wgrad_kernel<<<grid, 128, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)grad_pre,
+                                                       grad_weight, grad_bias, B, H, W, C, dilation, tiles_x, tiles_y);
+    RF_CHECK_LAUNCH("dwconv3x3_tile_wgrad_kernel");
+    return RF_OK;
+  }
   if (dilation == 1) {
     constexpr int PPT = 8, ROWS = 4;
     const int WX = (W + PPT - 1) / PPT, SG = (WX + WG_PL - 1) / WG_PL, RG = (H + ROWS - 1) / ROWS;

@@ -320,14 +320,16 @@ extern "C" int rf_add_layernorm_bwd(const void* xn, const void* dy, const float*
                                     const float* rstd, const float* gamma, const float* scale, float* dxn,
                                     void* dbranch, float* dgamma, float* dbeta, int64_t rows, int C,
                                     int64_t rows_per_sample, int xn_dtype, int dy_dtype, int branch_dtype,
-                                    void* stream) {
+                                    int accumulate, void* stream) {
   RF_REQUIRE(xn && dy && mean && rstd && gamma && dxn && dgamma && dbeta, "rf_add_layernorm_bwd: null pointer");
   RF_REQUIRE(rows > 0 && C > 0 && C % 32 == 0 && C <= 32 * LN_MAXV, "rf_add_layernorm_bwd: C=%d must be a multiple of 32, <= %d",
              C, 32 * LN_MAXV);
   RF_REQUIRE(rows_per_sample > 0, "rf_add_layernorm_bwd: rows_per_sample must be positive");
   cudaStream_t st = (cudaStream_t)stream;
-  RF_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * C, st));
-  RF_CUDA(cudaMemsetAsync(dbeta, 0, sizeof(float) * C, st));
+  if (!accumulate) {
+    RF_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * C, st));
+    RF_CUDA(cudaMemsetAsync(dbeta, 0, sizeof(float) * C, st));
+  }
   const int key = (xn_dtype << 2) | (dy_dtype << 1) | (dbranch ? branch_dtype : 0);
   switch (key) {
     case 0: return ln_bwd_dispatch<float, float, float>(xn, dy, dxn_in, mean, rstd, gamma, scale, dxn, dbranch, dgamma, dbeta, rows, C, rows_per_sample, st);

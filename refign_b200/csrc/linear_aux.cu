@@ -11,7 +11,9 @@
 
 namespace rf {
 
-constexpr int CS_CG = 32, CS_RL = 8;  // 32 column groups (8 columns each) x 8 row lanes per CTA
+// CTA = 8 column groups (8 columns each: one 128-byte line of bf16 per row) x 32 row lanes, so narrow
+// matrices (the 64-column stage-1 Linears) keep every lane busy; four rows are in flight per thread.
+constexpr int CS_CG = 8, CS_RL = 32, CS_UNROLL = 4;
 
 template <typename T>
 __device__ __forceinline__ void cs_load8(const T* p, float (&v)[8]);
@@ -37,30 +39,41 @@ __device__ __forceinline__ void cs_load8<float>(const float* p, float (&v)[8]) {
 template <typename T>
 __global__ void __launch_bounds__(CS_CG * CS_RL)
 colsum_kernel(const T* __restrict__ g, float* __restrict__ out, long rows, int cols, long strip) {
-  __shared__ float red[8][CS_CG];
+  __shared__ float red[CS_RL][CS_CG * 8 + 1];
   const int lane_cg = threadIdx.x % CS_CG, rl = threadIdx.x / CS_CG;
   const int cg = blockIdx.x * CS_CG + lane_cg;
   const bool live = cg * 8 < cols;
-  for (int i = threadIdx.x; i < 8 * CS_CG; i += CS_CG * CS_RL) (&red[0][0])[i] = 0.f;
-  __syncthreads();
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (live) {
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long r0 = (long)blockIdx.y * strip;
     const long r1 = (r0 + strip < rows) ? r0 + strip : rows;
-    for (long r = r0 + rl; r < r1; r += CS_RL) {
+    const T* p = g + cg * 8;
+    long r = r0 + rl;
+    for (; r + (CS_UNROLL - 1) * CS_RL < r1; r += CS_UNROLL * CS_RL) {
+      float v[CS_UNROLL][8];
+#pragma unroll
+      for (int u = 0; u < CS_UNROLL; ++u) cs_load8<T>(p + (r + u * CS_RL) * cols, v[u]);
+#pragma unroll
+      for (int u = 0; u < CS_UNROLL; ++u)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += v[u][k];
+    }
+    for (; r < r1; r += CS_RL) {
       float v[8];
-      cs_load8<T>(g + r * cols + cg * 8, v);
+      cs_load8<T>(p + r * cols, v);
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[k] += v[k];
     }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) atomicAdd(&red[k][lane_cg], acc[k]);
   }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[rl][lane_cg * 8 + k] = acc[k];
   __syncthreads();
-  for (int i = threadIdx.x; i < 8 * CS_CG; i += CS_CG * CS_RL) {
-    const int k = i / CS_CG, l = i % CS_CG;
-    const int c = (blockIdx.x * CS_CG + l) * 8 + k;
-    if (c < cols) atomicAdd(out + c, red[k][l]);
+  if (threadIdx.x < CS_CG * 8) {
+    float t = 0.f;
+#pragma unroll 8
+    for (int i = 0; i < CS_RL; ++i) t += red[i][threadIdx.x];
+    const int c = blockIdx.x * CS_CG * 8 + threadIdx.x;
+    if (c < cols) atomicAdd(out + c, t);
   }
 }
 
@@ -86,17 +99,18 @@ cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
 
 using namespace rf;
 
-extern "C" int rf_colsum(const void* g, float* out, int64_t rows, int cols, int dtype, void* stream) {
+extern "C" int rf_colsum(const void* g, float* out, int64_t rows, int cols, int dtype, int accumulate,
+                         void* stream) {
   RF_REQUIRE(g && out && rows > 0 && cols > 0, "rf_colsum: bad argument");
   RF_REQUIRE(cols % 8 == 0, "rf_colsum: cols=%d must be a multiple of 8", cols);
   RF_REQUIRE(((uintptr_t)g & 15) == 0, "rf_colsum: input must be 16-byte aligned");
   RF_REQUIRE(dtype == 0 || dtype == 1, "rf_colsum: dtype must be 0 (f32) or 1 (bf16)");
   cudaStream_t st = (cudaStream_t)stream;
-  RF_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, st));
+  if (!accumulate) RF_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, st));
   const int gx = (cols / 8 + CS_CG - 1) / CS_CG;
-  long strip = rows * gx / ((long)kNumSMs * 4);
-  if (strip < 64) strip = 64;
-  if (strip > 4096) strip = 4096;
+  long strip = rows * gx / ((long)kNumSMs * 4);   // ~4 CTAs per SM, at least 8 rows per thread
+  if (strip < CS_RL * 8) strip = CS_RL * 8;
+  if (strip > 8192) strip = 8192;
   const long gy = (rows + strip - 1) / strip;
   RF_REQUIRE(gy <= 65535, "rf_colsum: too many row strips");
   dim3 grid((unsigned)gx, (unsigned)gy);

@@ -495,13 +495,30 @@ def cast_bf16_(dst_bf16, src_f32):
     return dst_bf16
 
 
-def colsum(g2d):
-    """fp32 column sums of a contiguous [rows, cols] tensor (bias gradient of a Linear layer)."""
+def grad_target(p):
+    """Where a backward may ACCUMULATE the gradient of parameter ``p`` directly: its ``.grad`` when the
+    runtime has bound it to the flat gradient buffer (``p._rf_direct_grad``, see runtime.FlatParams), else
+    None (autograd's default: return a fresh gradient).  With a target the backward adds into the buffer
+    and returns None for that input, which removes the per-parameter AccumulateGrad add (and the memset of
+    the fresh gradient) -- ~3 000 + ~2 000 tiny launches per train step."""
+    if p is None or not getattr(p, '_rf_direct_grad', False) or not p.requires_grad:
+        return None
+    g = p.grad
+    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or not g.is_cuda:
+        return None
+    return g
+
+
+def colsum(g2d, out=None):
+    """fp32 column sums of a contiguous [rows, cols] tensor (bias gradient of a Linear layer); with
+    ``out`` the sums are accumulated into it."""
     require_cuda(g2d)
     rows, cols = g2d.shape
-    out = torch.empty(cols, device=g2d.device, dtype=torch.float32)
+    acc = out is not None
+    if not acc:
+        out = torch.empty(cols, device=g2d.device, dtype=torch.float32)
     with torch.cuda.device(g2d.device):
-        _run("rf_colsum", ptr(g2d), ptr(out), rows, cols, _dt_code(g2d), _stream(),
+        _run("rf_colsum", ptr(g2d), ptr(out), rows, cols, _dt_code(g2d), int(acc), _stream(),
              work=(g2d.numel() * g2d.element_size(), g2d.numel()))
     return out
 
@@ -516,13 +533,14 @@ class _LinearShadow(torch.autograd.Function):
     returns fp32 weight / bias gradients (bias gradient by rf_colsum)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, wb, bb):
+    def forward(ctx, x, weight, bias, wb, bb, gw_t=None, gb_t=None):
         with torch.autocast('cuda', enabled=False):
             xb = x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
             y = F.linear(xb, wb, bb)
         ctx.save_for_backward(xb, wb)
         ctx.x_dtype = x.dtype
         ctx.has_bias = bias is not None
+        ctx.targets = (gw_t, gb_t)
         return y
 
     @staticmethod
@@ -541,11 +559,20 @@ class _LinearShadow(torch.autograd.Function):
                 dx = (go2 @ wb).view(xb.shape)
                 if dx.dtype != ctx.x_dtype:
                     dx = dx.to(ctx.x_dtype)
+            gw_t, gb_t = ctx.targets
             if ctx.needs_input_grad[1]:
-                dw = _mm_f32(go2.t(), x2)
+                if gw_t is not None:
+                    _mm_f32_acc(gw_t, go2.t(), x2)
+                else:
+                    dw = _mm_f32(go2.t(), x2)
             if ctx.has_bias and ctx.needs_input_grad[2]:
-                db = colsum(go2) if go2.shape[1] % 8 == 0 else go2.float().sum(0)
-        return dx, dw, db, None, None
+                if go2.shape[1] % 8 != 0:
+                    db = go2.float().sum(0)
+                elif gb_t is not None:
+                    colsum(go2, out=gb_t)
+                else:
+                    db = colsum(go2)
+        return dx, dw, db, None, None, None, None
 
 
 _MM_OUT_DTYPE = None
@@ -566,6 +593,27 @@ def _mm_f32(a, b):
     return torch.mm(a, b).float()
 
 
+_MM_ACC_MODE = None
+
+
+def _mm_f32_acc(acc, a, b):
+    """acc += a @ b with bf16 operands and the fp32 accumulator added in the GEMM epilogue (beta = 1) when
+    the library takes mixed dtypes; otherwise one fp32 GEMM + one add."""
+    global _MM_ACC_MODE
+    if _MM_ACC_MODE is None:
+        try:
+            t = torch.zeros(8, 8, device=a.device, dtype=torch.float32)
+            torch.addmm(t, a[:8, :8].contiguous(), b[:8, :8].contiguous(), out_dtype=torch.float32, out=t)
+            _MM_ACC_MODE = 1
+        except Exception:
+            _MM_ACC_MODE = 0
+    if _MM_ACC_MODE == 1:
+        torch.addmm(acc, a, b, out_dtype=torch.float32, out=acc)
+    else:
+        acc.add_(_mm_f32(a, b))
+    return acc
+
+
 def linear(x, weight, bias=None):
     """``F.linear`` for the MiT / DAFormer Linear layers.  When the runtime has attached bf16 shadow
     weights (``weight._rf_bf16``) and bf16 autocast is on, the GEMM reads the shadow directly."""
@@ -575,7 +623,7 @@ def linear(x, weight, bias=None):
     bb = getattr(bias, '_rf_bf16', None) if bias is not None else None
     if bias is not None and bb is None:
         return F.linear(x, weight, bias)
-    return _LinearShadow.apply(x, weight, bias, wb, bb)
+    return _LinearShadow.apply(x, weight, bias, wb, bb, grad_target(weight), grad_target(bias))
 
 
 # --------------------------------------------------------------------------
@@ -679,7 +727,7 @@ class _DwConv3x3(torch.autograd.Function):
     bias and fused exact-erf GELU; fp32 parameters in their native [C,1,3,3] layout."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, dilation, gelu):
+    def forward(ctx, x, weight, bias, dilation, gelu, gw_t=None, gb_t=None):
         require_cuda(x, weight, bias)
         B, H, W, C = x.shape
         assert x.is_contiguous() and weight.numel() == 9 * C
@@ -693,6 +741,8 @@ class _DwConv3x3(torch.autograd.Function):
                  dt, _stream(), work=(nbytes, 18 * x.numel()), tag="dwconv3x3_fwd")
         ctx.save_for_backward(x, w, b)
         ctx.cfg = (int(dilation), bool(gelu), dt, bias is not None, weight.shape)
+        # direct accumulation needs every requested parameter gradient to have a target
+        ctx.targets = (gw_t, gb_t) if gw_t is not None and (bias is None or gb_t is not None) else None
         return y
 
     @staticmethod
@@ -718,17 +768,22 @@ class _DwConv3x3(torch.autograd.Function):
                 _run("rf_dwconv3x3_nhwc_bwd_input", ptr(g), ptr(w), ptr(gx), B, H, W, C, dil, dt, _stream(),
                      work=(2 * nbytes, 18 * x.numel()), tag="dwconv3x3_bwd_input")
             if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
-                gw = torch.empty(wshape, device=x.device, dtype=torch.float32)
-                gb = torch.empty(C, device=x.device, dtype=torch.float32) if has_bias else None
-                _run("rf_dwconv3x3_nhwc_bwd_weight", ptr(x), ptr(g), ptr(gw), ptr(gb), B, H, W, C, dil, dt, _stream(),
-                     work=(2 * nbytes, 18 * x.numel()), tag="dwconv3x3_bwd_weight")
-        return gx, gw, gb, None, None
+                if ctx.targets is not None:
+                    tw, tb = ctx.targets
+                    _run("rf_dwconv3x3_nhwc_bwd_weight", ptr(x), ptr(g), ptr(tw), ptr(tb), B, H, W, C, dil, dt, 1,
+                         _stream(), work=(2 * nbytes, 18 * x.numel()), tag="dwconv3x3_bwd_weight")
+                else:
+                    gw = torch.empty(wshape, device=x.device, dtype=torch.float32)
+                    gb = torch.empty(C, device=x.device, dtype=torch.float32) if has_bias else None
+                    _run("rf_dwconv3x3_nhwc_bwd_weight", ptr(x), ptr(g), ptr(gw), ptr(gb), B, H, W, C, dil, dt, 0,
+                         _stream(), work=(2 * nbytes, 18 * x.numel()), tag="dwconv3x3_bwd_weight")
+        return gx, gw, gb, None, None, None, None
 
 
 def dwconv3x3_gelu(x, H, W, weight, bias):
     """Mix-FFN ``act(dwconv(x))`` on tokens [B, H*W, C] (reference mix_transformer.py:96-103,556-568)."""
     B, N, C = x.shape
-    y = _DwConv3x3.apply(x.contiguous().view(B, H, W, C), weight, bias, 1, True)
+    y = _DwConv3x3.apply(x.contiguous().view(B, H, W, C), weight, bias, 1, True, grad_target(weight), grad_target(bias))
     return y.view(B, N, C)
 
 
@@ -738,7 +793,7 @@ def dwconv3x3_nhwc(x, weight, bias=None, dilation=1):
     xh = x.permute(0, 2, 3, 1)
     if not xh.is_contiguous():
         xh = xh.contiguous()
-    y = _DwConv3x3.apply(xh, weight, bias, int(dilation), False)
+    y = _DwConv3x3.apply(xh, weight, bias, int(dilation), False, grad_target(weight), grad_target(bias))
     return y.permute(0, 3, 1, 2)
 
 
@@ -750,12 +805,20 @@ def _ln_out_dtype(x):
     return x.dtype
 
 
+def _ln_param_grads(targets, C, device):
+    """(dgamma, dbeta, accumulate): the direct targets, or fresh buffers for autograd to accumulate."""
+    if targets is not None:
+        return targets[0], targets[1], 1
+    return (torch.empty(C, device=device, dtype=torch.float32), torch.empty(C, device=device, dtype=torch.float32), 0)
+
+
 class _LayerNorm(torch.autograd.Function):
     """y = LayerNorm(x) over the last dim of [..., C]; statistics and parameters fp32."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, eps, out_dtype):
+    def forward(ctx, x, gamma, beta, eps, out_dtype, gg_t=None, gb_t=None):
         require_cuda(x, gamma, beta)
+        ctx.targets = (gg_t, gb_t) if gg_t is not None and gb_t is not None else None
         C = x.shape[-1]
         xc = x.contiguous()
         rows = xc.numel() // C
@@ -781,22 +844,24 @@ class _LayerNorm(torch.autograd.Function):
         rows = xc.numel() // C
         dy = dy.contiguous()
         dx = torch.empty(xc.shape, device=xc.device, dtype=torch.float32)
-        dg = torch.empty(C, device=xc.device, dtype=torch.float32)
-        db = torch.empty(C, device=xc.device, dtype=torch.float32)
+        dg, db, acc = _ln_param_grads(ctx.targets, C, xc.device)
         with torch.cuda.device(xc.device):
             _run("rf_add_layernorm_bwd", ptr(xc), ptr(dy), None, ptr(mean), ptr(rstd), ptr(g), None, ptr(dx), None,
-                 ptr(dg), ptr(db), rows, C, rows, _dt_code(xc), _dt_code(dy), 0, _stream(),
+                 ptr(dg), ptr(db), rows, C, rows, _dt_code(xc), _dt_code(dy), 0, acc, _stream(),
                  work=(xc.numel() * (xc.element_size() + dy.element_size() + 4), 12 * xc.numel()),
                  tag="layernorm_bwd")
-        return (dx if xc.dtype == torch.float32 else dx.to(xc.dtype)), dg, db, None, None
+        if acc:
+            dg = db = None
+        return (dx if xc.dtype == torch.float32 else dx.to(xc.dtype)), dg, db, None, None, None, None
 
 
 class _AddLayerNorm(torch.autograd.Function):
     """(xn, y) = (x + scale[b] * branch, LayerNorm(xn)) for the pre-LN residual blocks; xn fp32."""
 
     @staticmethod
-    def forward(ctx, x, branch, scale, gamma, beta, eps, out_dtype):
+    def forward(ctx, x, branch, scale, gamma, beta, eps, out_dtype, gg_t=None, gb_t=None):
         require_cuda(x, branch, scale, gamma, beta)
+        ctx.targets = (gg_t, gb_t) if gg_t is not None and gb_t is not None else None
         assert x.dim() == 3 and branch.shape == x.shape
         B, N, C = x.shape
         xc, bc = _f32c(x), branch.contiguous()
@@ -829,31 +894,34 @@ class _AddLayerNorm(torch.autograd.Function):
         if dy is None:  # the normalised output was not used: pure residual pass-through
             dx = dxn
             dbr = dxn if sc is None else dxn * sc.view(-1, 1, 1)
-            return dx.to(xdtype), dbr.to(bdtype), None, None, None, None, None
+            return dx.to(xdtype), dbr.to(bdtype), None, None, None, None, None, None, None
         dy = dy.contiguous()
         dxi = None if dxn is None else _f32c(dxn)
         dx = torch.empty_like(xn)
         dbr = torch.empty(xn.shape, device=xn.device, dtype=bdtype)
-        dg = torch.empty(C, device=xn.device, dtype=torch.float32)
-        db = torch.empty(C, device=xn.device, dtype=torch.float32)
+        dg, db, acc = _ln_param_grads(ctx.targets, C, xn.device)
         with torch.cuda.device(xn.device):
             _run("rf_add_layernorm_bwd", ptr(xn), ptr(dy), ptr(dxi), ptr(mean), ptr(rstd), ptr(g), ptr(sc), ptr(dx),
-                 ptr(dbr), ptr(dg), ptr(db), rows, C, N, 0, _dt_code(dy), _dt_code(dbr), _stream(),
+                 ptr(dbr), ptr(dg), ptr(db), rows, C, N, 0, _dt_code(dy), _dt_code(dbr), acc, _stream(),
                  work=(xn.numel() * (4 + dy.element_size() + (4 if dxi is not None else 0) + 4 + dbr.element_size()),
                        14 * xn.numel()), tag="add_layernorm_bwd")
-        return (dx if xdtype == torch.float32 else dx.to(xdtype)), dbr, None, dg, db, None, None
+        if acc:
+            dg = db = None
+        return (dx if xdtype == torch.float32 else dx.to(xdtype)), dbr, None, dg, db, None, None, None, None
 
 
 def layer_norm(x, norm, out_dtype=None):
     """``norm(x)`` for an ``nn.LayerNorm`` over the last dimension (reference mix_transformer.py:135,234,
     304): one kernel, fp32 statistics, output dtype ``out_dtype`` (default: bf16 under bf16 autocast)."""
-    return _LayerNorm.apply(x, norm.weight, norm.bias, norm.eps, out_dtype or _ln_out_dtype(x))
+    return _LayerNorm.apply(x, norm.weight, norm.bias, norm.eps, out_dtype or _ln_out_dtype(x),
+                            grad_target(norm.weight), grad_target(norm.bias))
 
 
 def add_layer_norm(x, branch, scale, norm, out_dtype=None):
     """Residual add fused with the following LayerNorm: returns ``(x + scale[b] * branch, norm(...))``
     (reference mix_transformer.py:203-207; ``scale`` = per-sample drop-path factor or None)."""
-    return _AddLayerNorm.apply(x, branch, scale, norm.weight, norm.bias, norm.eps, out_dtype or _ln_out_dtype(x))
+    return _AddLayerNorm.apply(x, branch, scale, norm.weight, norm.bias, norm.eps, out_dtype or _ln_out_dtype(x),
+                               grad_target(norm.weight), grad_target(norm.bias))
 
 
 class _PatchEmbedLN(torch.autograd.Function):
@@ -895,7 +963,7 @@ class _PatchEmbedLN(torch.autograd.Function):
         db = torch.empty(C, device=pre.device, dtype=torch.float32)
         with torch.cuda.device(pre.device):
             _run("rf_add_layernorm_bwd", ptr(pre), ptr(dy), None, ptr(mean), ptr(rstd), ptr(g), None, ptr(dpre), None,
-                 ptr(dg), ptr(db), B * N, C, B * N, 0, _dt_code(dy), 0, _stream(), tag="layernorm_bwd")
+                 ptr(dg), ptr(db), B * N, C, B * N, 0, _dt_code(dy), 0, 0, _stream(), tag="layernorm_bwd")
         with torch.autocast('cuda', enabled=False):
             gconv = dpre.view(B, Ho, Wo, C).permute(0, 3, 1, 2)
             dw = torch.nn.grad.conv2d_weight(xf, wshape, gconv, stride=4, padding=3)

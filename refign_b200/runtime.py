@@ -48,6 +48,8 @@ class FlatParams:
                 p.data = self.data[o:o + n].view(p.shape)
                 if with_grad:
                     p.grad = self.grad[o:o + n].view(p.shape)
+                    # backward kernels may accumulate straight into this view (ops.grad_target)
+                    p._rf_direct_grad = bool(self.grad.is_cuda)
 
     def attach_shadow(self):
         """Flat bf16 copy of the buffer; every parameter gets ``p._rf_bf16`` = its bf16 view (read by

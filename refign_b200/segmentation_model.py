@@ -130,6 +130,7 @@ class DomainAdaptationSegmentationModel(_Base):
         self._logged = {}
         self._fused_pseudo = None             # (probs tensor, label, maxprob) handed from refine to get_dacs_mix
         self._graphs = None                   # CUDA-graph state installed by enable_cuda_graphs()
+        self.fuse_source_backward = True      # one backward for loss_src + feature distance (see _step_part_a)
         self.load_weights(pretrained)
 
     # ---- what Lightning would provide ---------------------------------------------------------------
@@ -240,15 +241,25 @@ class DomainAdaptationSegmentationModel(_Base):
                                        align_corners=False)
             loss_src = self.loss(logits_src, gt_src)
         self.log("train_loss_src", loss_src)
-        self.manual_backward(loss_src, retain_graph=self.enable_fdist)
-        del loss_src, logits_src
-
-        if self.enable_fdist:
+        if self.enable_fdist and self.fuse_source_backward:
+            # The reference runs two backward passes here (loss_src with retain_graph, then the feature
+            # distance: segmentation_model.py:172-192), i.e. it walks the backbone graph twice and sums the
+            # two gradients in .grad.  The gradient of a sum is the sum of the gradients, so one backward
+            # of (loss_src + loss_fd) leaves the same .grad -- and walks the 52 MiT blocks once.
             with self._autocast():
                 loss_fd = self.calc_feat_dist(images_src, gt_src, feats_src)
             self.log("train_loss_featdist_src", loss_fd)
-            self.manual_backward(loss_fd)
-            del loss_fd
+            self.manual_backward(loss_src + loss_fd.to(loss_src.dtype))
+            del loss_fd, loss_src, logits_src
+        else:
+            self.manual_backward(loss_src, retain_graph=self.enable_fdist)
+            del loss_src, logits_src
+            if self.enable_fdist:
+                with self._autocast():
+                    loss_fd = self.calc_feat_dist(images_src, gt_src, feats_src)
+                self.log("train_loss_featdist_src", loss_fd)
+                self.manual_backward(loss_fd)
+                del loss_fd
         del feats_src
 
         # ---- target (no grad) ------------------------------------------------------------------

@@ -31,6 +31,15 @@ DW_SPECS = [  # B, H, W, C, dilation, gelu, bias
     (1, 40, 40, 64, 12, False, False),
     (1, 40, 24, 16, 18, False, False),   # dilation close to the map size: most taps out of range
     (1, 5, 7, 8, 2, False, True),
+    # shared-memory tile kernels (bf16, C % 64 == 0): ragged row / column tiles, both tile widths, several
+    # channel blocks, with and without bias / GELU
+    (1, 9, 13, 64, 1, True, True),
+    (2, 20, 40, 128, 1, True, True),
+    (1, 12, 96, 64, 1, True, True),
+    (1, 16, 64, 192, 1, False, False),
+    (2, 33, 70, 64, 1, False, True),
+    (1, 50, 45, 64, 18, False, True),    # dilated lattice through the tile kernels (residue-class sub-images)
+    (2, 37, 41, 128, 6, False, False),
 ]
 
 
@@ -312,3 +321,39 @@ def test_batch_norm_relu_fwd_bwd(spec, dtype):
     _close(my_bn.running_mean, ref_bn.running_mean, 1e-4, 1e-5, "running_mean")
     _close(my_bn.running_var, ref_bn.running_var, 1e-4, 1e-5, "running_var")
     assert int(my_bn.num_batches_tracked) == 1
+
+
+def test_direct_param_grad_accumulation_matches_autograd():
+    """Backward kernels that accumulate straight into a bound ``.grad`` (runtime.FlatParams marks the
+    parameters ``_rf_direct_grad``) must give what autograd's AccumulateGrad gives over two backward
+    passes, for the Linear (shadow bf16 GEMM + colsum), LayerNorm / add+LayerNorm and depthwise-conv paths."""
+    import torch.nn as nn
+    torch.manual_seed(3)
+    B, H, W, C = 2, 16, 16, 64
+    lin, ln, ln2 = nn.Linear(C, 2 * C).to(DEV), nn.LayerNorm(C).to(DEV), nn.LayerNorm(C).to(DEV)
+    dw_w = nn.Parameter(torch.randn(2 * C, 1, 3, 3, device=DEV) * 0.3)
+    dw_b = nn.Parameter(torch.randn(2 * C, device=DEV) * 0.1)
+    params = [lin.weight, lin.bias, ln.weight, ln.bias, ln2.weight, ln2.bias, dw_w, dw_b]
+    for p in (lin.weight, lin.bias):
+        p._rf_bf16 = p.detach().to(torch.bfloat16)
+    xs = [torch.randn(B, H * W, C, device=DEV) for _ in range(2)]
+
+    def run(direct):
+        for p in params:
+            p.grad = torch.full_like(p, 0.25)      # pre-existing content must be added to, not overwritten
+            p._rf_direct_grad = direct
+        for x in xs:
+            with torch.autocast('cuda', dtype=torch.bfloat16):
+                xn, y = ops.add_layer_norm(x, x * 0.5, None, ln)
+                h = ops.linear(y, lin.weight, lin.bias)
+                h = ops.dwconv3x3_gelu(h, H, W, dw_w, dw_b)
+                z = ops.layer_norm(xn, ln2)
+            (h.float().square().mean() + z.float().sum() * 1e-3).backward()
+        return [p.grad.clone() for p in params]
+
+    want = run(False)
+    got = run(True)
+    for p in params:
+        p._rf_direct_grad = False
+    for g, w_, name in zip(got, want, ["lin.w", "lin.b", "ln.w", "ln.b", "ln2.w", "ln2.b", "dw.w", "dw.b"]):
+        _close(g, w_, 2e-3, 2e-3 * max(1.0, float(w_.abs().max())), name)

@@ -220,6 +220,32 @@ def test_warp_bit_exact_vs_oracle(shape):
     assert torch.equal(ops.warp(x.to(DEV), flo.to(DEV)).cpu(), wo)
 
 
+@pytest.mark.parametrize("kind", ["smooth", "noisy", "wild", "outside", "zero"])
+def test_warp_staged_tiles_bit_exact_vs_oracle(kind):
+    """Shapes large enough for the shared-memory staged kernel (>= 2 tiles per SM), ragged in both axes:
+    smooth flow (small source box), per-pixel noise (large box), wild flow (box overflow -> in-kernel direct
+    gathers), everything out of the image, and the zero-flow early exit."""
+    B, C, H, W = 3, 7, 181, 203
+    torch.manual_seed(len(kind))
+    x = torch.randn(B, C, H, W)
+    if kind == "smooth":
+        flo = torch.nn.functional.interpolate(torch.randn(B, 2, 6, 7) * 6, size=(H, W), mode="bilinear") + 1.3
+    elif kind == "noisy":
+        flo = torch.randn(B, 2, H, W) * 4 - 2.0
+    elif kind == "wild":
+        flo = torch.randn(B, 2, H, W) * 60
+    elif kind == "outside":
+        flo = torch.full((B, 2, H, W), 500.0)
+        flo[1] = -400.0
+        flo[2, :, :90] = torch.randn(2, 90, W)       # one image half valid
+    else:
+        flo = torch.zeros(B, 2, H, W)
+    wo, wm = oracle.warp(x, flo, return_mask=True)
+    go, gm = ops.warp(x.to(DEV), flo.to(DEV), return_mask=True)
+    assert torch.equal(gm.cpu(), wm)
+    assert torch.equal(go.cpu(), wo)
+
+
 def test_warp_backward_vs_grid_sample():
     torch.manual_seed(9)
     B, C, H, W = 2, 6, 20, 28

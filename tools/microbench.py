@@ -103,7 +103,12 @@ def main():
     if want("warp"):
         for (B, C, H) in [(2, 19, 512), (2, 19, 1024), (2, 128, 256), (2, 256, 128)]:
             x, f = torch.randn(B, C, H, H, device=dev), torch.randn(B, 2, H, H, device=dev) * 4
-            report("warp+mask", [B, C, H, H], time_op(lambda: ops.warp(x, f, return_mask=True), args.iters),
+            report("warp+mask(noise flow, sigma 4 px)", [B, C, H, H], time_op(lambda: ops.warp(x, f, return_mask=True), args.iters),
+                   4 * B * H * H * (2 * C + 2) + B * H * H, 8 * B * C * H * H)
+            # smooth flow (what the UAWarpC head produces: a 1/4-resolution field upsampled bilinearly)
+            fs = torch.nn.functional.interpolate(torch.randn(B, 2, H // 32, H // 32, device=dev) * 8, size=(H, H),
+                                                 mode="bilinear") + 3.0
+            report("warp+mask(smooth flow)", [B, C, H, H], time_op(lambda: ops.warp(x, fs, return_mask=True), args.iters),
                    4 * B * H * H * (2 * C + 2) + B * H * H, 8 * B * C * H * H)
     if want("refine"):
         for H in [512, 1024]:
