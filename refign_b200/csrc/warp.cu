@@ -17,9 +17,10 @@
 // arithmetic with its four IEEE divisions is done once per pixel); consecutive
 // threads = consecutive x, so the flow reads and the output writes are coalesced
 // and the four gathers of neighbouring pixels hit the same lines.  Eight channels
-// (32 gathers) are in flight per thread.
-#include <stdlib.h>
-
+// (32 gathers) are in flight per thread.  (A shared-memory staged variant -- bounding box of a tile's
+// samples copied with coalesced row loads, gathers from shared memory -- was measured on B200 and was 2-3x
+// SLOWER for both smooth and noisy flows: the per-channel-batch barriers serialise the copy latency, while
+// the direct gathers of a dense-correspondence flow already hit L1 lines shared by neighbouring pixels.)
 #include "rf_common.cuh"
 
 namespace rf {
@@ -124,117 +125,6 @@ warp_bilinear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ 
   }
 }
 
-// Shared-memory staged variant: a CTA owns an 8 x 32 output tile, computes the bounding box of the source
-// pixels its 256 threads sample, and -- when the box is at most four times the tile, i.e. the flow varies by a
-// few pixels inside a tile as dense-correspondence flows do -- copies that box into shared memory with coalesced row
-// loads, WT_CB channels at a time, so the four bilinear gathers per output become bank-level shared-memory
-// reads instead of up to 32-sector L1 gathers.  Tiles whose box is too large (wild flows) take the direct
-// path above, so the result is the same operation sequence on the same values either way.
-constexpr int WT_TH = 8, WT_TW = 32, WT_CB = 4, WT_MAXBOX = 1024;   // box <= 4x the tile: 4 x 1024 floats = 16 KB
-
-__global__ void __launch_bounds__(256)
-warp_bilinear_fwd_tile_kernel(const float* __restrict__ x, const float* __restrict__ flow, float* __restrict__ out,
-                              uint8_t* __restrict__ mask, const int32_t* __restrict__ zero_flag, int C, int H, int W) {
-  __shared__ float box[WT_CB * WT_MAXBOX];
-  __shared__ int sred[4][8];
-  const long plane = (long)H * W;
-  const int tiles_x = (W + WT_TW - 1) / WT_TW;
-  const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
-  const int b = blockIdx.z;
-  const int xx = tx * WT_TW + (threadIdx.x & 31), yy = ty * WT_TH + (threadIdx.x >> 5);
-  const bool live = xx < W && yy < H;
-  const long pix = (long)yy * W + xx;
-  const float* xb = x + (long)b * C * plane;
-  float* ob = out + (long)b * C * plane;
-  if (zero_flag != nullptr && *zero_flag != 0) {  // matching_utils.py:19-22
-    if (live) {
-      for (int c = 0; c < C; ++c) ob[c * plane + pix] = xb[c * plane + pix];
-      if (mask != nullptr) mask[(long)b * plane + pix] = 1;
-    }
-    return;
-  }
-  WarpCoord k;
-  k.x0 = -5; k.y0 = -5; k.vx0 = k.vx1 = k.vy0 = k.vy1 = false; k.inside = false;
-  k.w00 = k.w01 = k.w10 = k.w11 = 0.f;
-  if (live) {
-    const float fx = flow[((long)b * 2 + 0) * plane + pix];
-    const float fy = flow[((long)b * 2 + 1) * plane + pix];
-    k = warp_coord(fx, fy, xx, yy, H, W);
-    if (mask != nullptr) mask[(long)b * plane + pix] = k.inside ? 1 : 0;
-  }
-  const bool v00 = k.vy0 && k.vx0, v01 = k.vy0 && k.vx1, v10 = k.vy1 && k.vx0, v11 = k.vy1 && k.vx1;
-  // bounding box of the valid corners (image coordinates)
-  int xmin = W, xmax = -1, ymin = H, ymax = -1;
-  if (k.vx0) { xmin = min(xmin, k.x0); xmax = max(xmax, k.x0); }
-  if (k.vx1) { xmin = min(xmin, k.x0 + 1); xmax = max(xmax, k.x0 + 1); }
-  if (k.vy0) { ymin = min(ymin, k.y0); ymax = max(ymax, k.y0); }
-  if (k.vy1) { ymin = min(ymin, k.y0 + 1); ymax = max(ymax, k.y0 + 1); }
-  if (!(v00 || v01 || v10 || v11)) { xmin = W; xmax = -1; ymin = H; ymax = -1; }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
-    ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
-    xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
-    ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
-  }
-  if ((threadIdx.x & 31) == 0) {
-    sred[0][threadIdx.x >> 5] = xmin; sred[1][threadIdx.x >> 5] = xmax;
-    sred[2][threadIdx.x >> 5] = ymin; sred[3][threadIdx.x >> 5] = ymax;
-  }
-  __syncthreads();
-  xmin = sred[0][0]; xmax = sred[1][0]; ymin = sred[2][0]; ymax = sred[3][0];
-#pragma unroll
-  for (int i = 1; i < 8; ++i) {
-    xmin = min(xmin, sred[0][i]); xmax = max(xmax, sred[1][i]);
-    ymin = min(ymin, sred[2][i]); ymax = max(ymax, sred[3][i]);
-  }
-  const int bw = xmax - xmin + 1, bh = ymax - ymin + 1;
-  float* q = ob + pix;
-  if (bw <= 0 || bh <= 0) {            // nothing valid in this tile: all zeros
-    if (live) for (int c = 0; c < C; ++c) __stcs(q + c * plane, 0.f);
-    return;
-  }
-  if (bw * bh > WT_MAXBOX) {           // wild flow: direct gathers
-    if (!live) return;
-    const float* p = xb + (long)k.y0 * W + k.x0;
-    for (int c = 0; c < C; ++c) {
-      float acc = 0.f;
-      if (v00) acc = __fadd_rn(acc, __fmul_rn(__ldg(p), k.w00));
-      if (v01) acc = __fadd_rn(acc, __fmul_rn(__ldg(p + 1), k.w01));
-      if (v10) acc = __fadd_rn(acc, __fmul_rn(__ldg(p + W), k.w10));
-      if (v11) acc = __fadd_rn(acc, __fmul_rn(__ldg(p + W + 1), k.w11));
-      __stcs(q + c * plane, acc);
-      p += plane;
-    }
-    return;
-  }
-  const int s00 = (k.y0 - ymin) * bw + (k.x0 - xmin);   // only dereferenced under the v?? predicates
-  for (int cb = 0; cb < C; cb += WT_CB) {
-    const int nc = min(WT_CB, C - cb);
-    __syncthreads();                   // previous batch's gathers are done
-    for (int rowi = threadIdx.x >> 5; rowi < nc * bh; rowi += 8) {   // one box row per warp: coalesced in x
-      const int c = rowi / bh, ry = rowi - c * bh;
-      const float* src = xb + (long)(cb + c) * plane + (long)(ymin + ry) * W + xmin;
-      float* dst = box + c * WT_MAXBOX + ry * bw;
-      for (int rx = threadIdx.x & 31; rx < bw; rx += 32) dst[rx] = __ldg(src + rx);
-    }
-    __syncthreads();
-    if (live) {
-#pragma unroll
-      for (int c = 0; c < WT_CB; ++c) {
-        if (c >= nc) break;
-        const float* sp = box + c * WT_MAXBOX + s00;
-        float acc = 0.f;
-        if (v00) acc = __fadd_rn(acc, __fmul_rn(sp[0], k.w00));
-        if (v01) acc = __fadd_rn(acc, __fmul_rn(sp[1], k.w01));
-        if (v10) acc = __fadd_rn(acc, __fmul_rn(sp[bw], k.w10));
-        if (v11) acc = __fadd_rn(acc, __fmul_rn(sp[bw + 1], k.w11));
-        __stcs(q + (long)(cb + c) * plane, acc);
-      }
-    }
-  }
-}
-
 // Backward: grad wrt x is a scatter-add of the four bilinear weights; grad wrt
 // the flow is d(out)/d(ix) * d(ix)/d(flow_x) with d(ix)/d(flow_x) = 1 (the
 // normalise / un-normalise pair cancels for align_corners=True when W > 1).
@@ -320,17 +210,6 @@ extern "C" int rf_warp_bilinear_fwd(const float* x, const float* flow, float* ou
   RF_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "rf_warp_bilinear_fwd: empty tensor");
   RF_REQUIRE(B <= 65535, "rf_warp_bilinear_fwd: batch too large");
   const long plane = (long)H * W;
-  {
-    // staged path when the tile grid alone fills the machine and the row pitch allows 8 x 32 tiles
-    static const bool direct = [] { const char* e = getenv("RF_WARP_IMPL"); return e && e[0] == 'd'; }();
-    const long tiles = (long)((W + WT_TW - 1) / WT_TW) * ((H + WT_TH - 1) / WT_TH);
-    if (!direct && tiles * B >= kNumSMs * 2 && tiles <= 0x7fffffff) {
-      dim3 grid((unsigned)tiles, 1, B);
-      warp_bilinear_fwd_tile_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, flow, out, mask, all_zero_flag, C, H, W);
-      RF_CHECK_LAUNCH("warp_bilinear_fwd_tile_kernel");
-      return RF_OK;
-    }
-  }
   const long pblocks = (plane + 255) / 256;
   // channel chunks: as few as keep >= 8 CTAs per SM in flight (coordinates are recomputed per chunk)
   long chunks = ((long)kNumSMs * 8 + pblocks * B - 1) / (pblocks * B);

@@ -94,7 +94,7 @@ class Attention(nn.Module):
         h, d = self.num_heads, C // self.num_heads
         q = ops.linear(x, self.q.weight, self.q.bias)        # [B, N, h*d]   (read strided per head)
         if self.sr_ratio > 1:
-            x_ = _tokens(self.sr(_nhwc_view(x, H, W)))
+            x_ = ops.sr_conv(x, H, W, self.sr)
             x_ = ops.layer_norm(x_, self.norm)
         else:
             x_ = x

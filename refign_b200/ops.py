@@ -626,6 +626,108 @@ def linear(x, weight, bias=None):
     return _LinearShadow.apply(x, weight, bias, wb, bb, grad_target(weight), grad_target(bias))
 
 
+# ---- spatial-reduction conv of the MiT attention (kernel == stride, no padding) as a patch GEMM ----------
+# Derived bf16 weights: the conv weight [Co, Ci, s, s] re-laid as the Linear weight [Co, s*s*Ci] of the
+# space-to-depth tokens.  They are re-derived right after every refresh of the flat bf16 shadow
+# (runtime.FlatParams.refresh_shadow -> refresh_derived), i.e. inside the same captured graph.
+_DERIVED = []   # [source bf16 view, derived tensor]
+
+
+def _sr_weight_perm(weight):
+    wp = getattr(weight, '_rf_bf16_perm', None)
+    if wp is None:
+        src = weight._rf_bf16
+        Co = src.shape[0]
+        wp = src.permute(0, 2, 3, 1).reshape(Co, -1).contiguous()
+        weight._rf_bf16_perm = wp
+        _DERIVED.append((src, wp))
+    return wp
+
+
+def refresh_derived(flat_shadow=None):
+    """Re-derive the permuted weights whose source lives in ``flat_shadow`` (all of them when None)."""
+    if flat_shadow is not None:
+        lo = flat_shadow.data_ptr()
+        hi = lo + flat_shadow.numel() * flat_shadow.element_size()
+    for src, wp in _DERIVED:
+        if flat_shadow is None or lo <= src.data_ptr() < hi:
+            wp.view(src.shape[0], src.shape[2], src.shape[3], src.shape[1]).copy_(src.permute(0, 2, 3, 1))
+
+
+class _SrConvGemm(torch.autograd.Function):
+    """``Conv2d(C, Co, kernel_size=s, stride=s)`` on a token grid as space-to-depth + one tensor-core GEMM
+    (reference mix_transformer.py:133-134,147-149 run it as a cuDNN convolution between two layout
+    permutes).  Keeps the tokens [B,N,C] channels-last end to end: the input gradient comes back as a
+    contiguous [B,N,C] tensor (the cuDNN path returned an NCHW-strided one, which turned the following
+    gradient add into a generic strided kernel), the bias gradient is rf_colsum, the weight gradient a
+    GEMM accumulated into the flat gradient buffer."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, wperm, bias_b, H, W, s, gw_t, gb_t):
+        B, N, C = x.shape
+        Hs, Ws = H // s, W // s
+        with torch.autocast('cuda', enabled=False):
+            xb = x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
+            xs = xb.view(B, Hs, s, Ws, s, C).permute(0, 1, 3, 2, 4, 5).reshape(B * Hs * Ws, s * s * C)
+            y = F.linear(xs, wperm, bias_b)
+        ctx.save_for_backward(xs, wperm)
+        ctx.meta = (B, Hs, Ws, s, C, x.dtype, weight.shape)
+        ctx.targets = (gw_t, gb_t)
+        return y.view(B, Hs * Ws, -1)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, go):
+        xs, wperm = ctx.saved_tensors
+        B, Hs, Ws, s, C, xdtype, wshape = ctx.meta
+        gw_t, gb_t = ctx.targets
+        Co = wshape[0]
+        dx = dw = db = None
+        with torch.autocast('cuda', enabled=False):
+            go2 = go.reshape(-1, Co)
+            if go2.dtype != torch.bfloat16:
+                go2 = go2.to(torch.bfloat16)
+            if not go2.is_contiguous():
+                go2 = go2.contiguous()
+            if ctx.needs_input_grad[0]:
+                dxs = go2 @ wperm                                            # [B*M, s*s*C]
+                dx = dxs.view(B, Hs, Ws, s, s, C).permute(0, 1, 3, 2, 4, 5).reshape(B, Hs * s * Ws * s, C)
+                if dx.dtype != xdtype:
+                    dx = dx.to(xdtype)
+            if ctx.needs_input_grad[1]:
+                dwp = _mm_f32(go2.t(), xs).view(Co, s, s, C)                 # layout of wperm
+                if gw_t is not None:
+                    gw_t.permute(0, 2, 3, 1).add_(dwp)
+                else:
+                    dw = dwp.permute(0, 3, 1, 2)
+            if ctx.needs_input_grad[2]:
+                if Co % 8 != 0:
+                    db = go2.float().sum(0)
+                elif gb_t is not None:
+                    colsum(go2, out=gb_t)
+                else:
+                    db = colsum(go2)
+        return dx, dw, db, None, None, None, None, None, None, None
+
+
+def sr_conv(x, H, W, conv):
+    """``tokens(conv(nchw(x)))`` for the spatial-reduction conv of an MiT attention block; x: [B, H*W, C]
+    tokens, returns [B, (H/s)*(W/s), Co] tokens.  Patch-GEMM path under bf16 autocast with shadow weights,
+    otherwise the library convolution on the channels-last view."""
+    s = conv.kernel_size[0]
+    wb = getattr(conv.weight, '_rf_bf16', None)
+    bb = getattr(conv.bias, '_rf_bf16', None) if conv.bias is not None else None
+    ok = (x.is_cuda and _bf16_autocast() and wb is not None and conv.bias is not None and bb is not None
+          and conv.kernel_size == conv.stride and conv.kernel_size[0] == conv.kernel_size[1]
+          and conv.padding == (0, 0) and conv.groups == 1 and H % s == 0 and W % s == 0)
+    if not ok:
+        B, N, C = x.shape
+        y = conv(x.view(B, H, W, C).permute(0, 3, 1, 2))
+        return y.permute(0, 2, 3, 1).reshape(B, -1, y.shape[1])
+    return _SrConvGemm.apply(x, conv.weight, conv.bias, _sr_weight_perm(conv.weight), bb, H, W, s,
+                             grad_target(conv.weight), grad_target(conv.bias))
+
+
 # --------------------------------------------------------------------------
 # MiT operators (reference: models/backbones/mix_transformer.py)
 # --------------------------------------------------------------------------

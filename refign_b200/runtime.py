@@ -62,6 +62,7 @@ class FlatParams:
     def refresh_shadow(self):
         if getattr(self, 'shadow', None) is not None:
             ops.cast_bf16_(self.shadow, self.data)
+            ops.refresh_derived(self.shadow)      # permuted SR-conv weights follow their source
 
     def rebind_grads(self):
         """(Re)attach the flat gradient views (after anything that reset ``p.grad`` to None)."""

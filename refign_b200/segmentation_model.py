@@ -409,6 +409,8 @@ class DomainAdaptationSegmentationModel(_Base):
                 for p in self.imnet_backbone.parameters():
                     if getattr(p, '_rf_bf16', None) is not None:
                         p._rf_bf16.copy_(p.detach())
+                from . import ops as _ops
+                _ops.refresh_derived(None)
 
     # ---- Refign: refine / eta / align --------------------------------------------------------------
     @torch.no_grad()

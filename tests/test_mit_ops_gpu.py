@@ -357,3 +357,46 @@ def test_direct_param_grad_accumulation_matches_autograd():
         p._rf_direct_grad = False
     for g, w_, name in zip(got, want, ["lin.w", "lin.b", "ln.w", "ln.b", "ln2.w", "ln2.b", "dw.w", "dw.b"]):
         _close(g, w_, 2e-3, 2e-3 * max(1.0, float(w_.abs().max())), name)
+
+
+@pytest.mark.parametrize("spec", [(2, 32, 32, 64, 8), (1, 16, 24, 128, 4), (2, 8, 8, 320, 2)])
+def test_sr_conv_patch_gemm_matches_conv(spec):
+    """Spatial-reduction conv (kernel == stride) as space-to-depth + GEMM vs nn.Conv2d in fp32 on the same
+    bf16-rounded inputs / weights: forward, input / weight / bias gradients (direct accumulation too)."""
+    import torch.nn as nn
+    B, H, W, C, s = spec
+    torch.manual_seed(sum(spec))
+    conv = nn.Conv2d(C, C, kernel_size=s, stride=s).to(DEV)
+    with torch.no_grad():
+        conv.weight.mul_(3.0)
+    conv.weight._rf_bf16 = conv.weight.detach().to(torch.bfloat16)
+    conv.bias._rf_bf16 = conv.bias.detach().to(torch.bfloat16)
+    x = torch.randn(B, H * W, C, device=DEV).to(torch.bfloat16)
+    gy = torch.randn(B, (H // s) * (W // s), C, device=DEV).to(torch.bfloat16)
+    xr = x.float().view(B, H, W, C).permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    wr = conv.weight._rf_bf16.float().requires_grad_(True)
+    br = conv.bias._rf_bf16.float().requires_grad_(True)
+    ref = F.conv2d(xr, wr, br, stride=s)
+    ref.backward(gy.float().view(B, H // s, W // s, C).permute(0, 3, 1, 2))
+    for direct in (False, True):
+        conv.weight.grad = torch.zeros_like(conv.weight)
+        conv.bias.grad = torch.zeros_like(conv.bias)
+        conv.weight._rf_direct_grad = conv.bias._rf_direct_grad = direct
+        xm = x.clone().requires_grad_(True)
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            out = ops.sr_conv(xm, H, W, conv)
+        assert out.dtype == torch.bfloat16 and out.shape == gy.shape
+        out.backward(gy)
+        tol = 2 * 2 ** -8
+        _close(out, ref.permute(0, 2, 3, 1).reshape(gy.shape), tol, tol * float(ref.abs().max()), "forward")
+        _close(xm.grad, xr.grad.permute(0, 2, 3, 1).reshape(x.shape), tol, tol * float(xr.grad.abs().max()), "grad_input")
+        _close(conv.weight.grad, wr.grad, tol, tol * float(wr.grad.abs().max()), "grad_weight")
+        _close(conv.bias.grad, br.grad, tol, tol * float(br.grad.abs().max()), "grad_bias")
+    # a refresh of the shadow must be followed by the derived (permuted) weight
+    with torch.no_grad():
+        conv.weight._rf_bf16.mul_(0.5)
+    ops.refresh_derived(None)
+    with torch.autocast('cuda', dtype=torch.bfloat16):
+        out2 = ops.sr_conv(x, H, W, conv)
+    ref2 = F.conv2d(xr.detach(), conv.weight._rf_bf16.float(), br.detach(), stride=s)
+    _close(out2, ref2.permute(0, 2, 3, 1).reshape(gy.shape), 2 * 2 ** -8, 2 * 2 ** -8 * float(ref2.abs().max()), "refreshed")

@@ -221,10 +221,9 @@ def test_warp_bit_exact_vs_oracle(shape):
 
 
 @pytest.mark.parametrize("kind", ["smooth", "noisy", "wild", "outside", "zero"])
-def test_warp_staged_tiles_bit_exact_vs_oracle(kind):
-    """Shapes large enough for the shared-memory staged kernel (>= 2 tiles per SM), ragged in both axes:
-    smooth flow (small source box), per-pixel noise (large box), wild flow (box overflow -> in-kernel direct
-    gathers), everything out of the image, and the zero-flow early exit."""
+def test_warp_flow_families_bit_exact_vs_oracle(kind):
+    """Larger ragged shape (all channels per thread, one channel chunk): smooth flow, per-pixel noise, wild
+    flow, everything out of the image, and the zero-flow early exit."""
     B, C, H, W = 3, 7, 181, 203
     torch.manual_seed(len(kind))
     x = torch.randn(B, C, H, W)

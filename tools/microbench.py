@@ -116,6 +116,15 @@ def main():
             m, lv = torch.rand(2, H, H, device=dev) > 0.1, torch.randn(2, 1, H, H, device=dev)
             report("refine+cert+argmax", [2, 19, H, H], time_op(lambda: ops.refine_fused(lt, lr, m, logvar=lv), args.iters),
                    4 * 2 * H * H * (3 * 19 + 1) + 2 * H * H * (1 + 8 + 4), 0)
+    if want("patch_embed"):
+        import torch.nn as nn
+        for (B, H) in [(2, 1024), (4, 1024), (2, 512)]:
+            x = torch.randn(B, 3, H, H, device=dev)
+            conv = nn.Conv2d(3, 64, 7, 4, 3).to(dev)
+            ln = nn.LayerNorm(64).to(dev)
+            with torch.no_grad():
+                report("patch_embed(conv7x7s4+LN)", [B, 3, H, H], time_op(lambda: ops.patch_embed_ln(x, conv.weight, conv.bias, ln.weight, ln.bias, 1e-5), args.iters),
+                       4 * B * (3 * H * H + 64 * H * H // 16), 2 * B * (H * H // 16) * 64 * 147)
     if want("optim"):
         n = 85_160_000
         p, g, m, v, e = (torch.randn(n, device=dev) for _ in range(5))

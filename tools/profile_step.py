@@ -68,7 +68,7 @@ def main():
         ev = [e for e in prof.key_averages(group_by_input_shape=True, group_by_stack_n=6)
               if getattr(e, "self_device_time_total", 0) > 0 and e.device_type.name != "CUDA"]
         ev.sort(key=lambda e: -e.self_device_time_total)
-        for e in ev[:45]:
+        for e in ev[:140]:
             stack = [l for l in (e.stack or []) if "refign_b200" in l or "bench.py" in l]
             print("%8.3f ms x%-5d %-28s %s | %s" % (e.self_device_time_total / 1e3, e.count, e.key[:28],
                                                   str(e.input_shapes)[:90], (stack[0].split("/")[-1] if stack else "")[:70]))
