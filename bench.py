@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--size", type=int, default=1024, help="crop size (BASELINE metric: 1024)")
     ap.add_argument("--model", default="mit_b5")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--cpu-size", type=int, default=256, help="crop size of the bounded CPU sample")
+    ap.add_argument("--cpu-size", type=int, default=512, help="crop size of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="run the step eagerly instead of replaying CUDA graphs")

@@ -289,6 +289,35 @@ int rf_bn_bwd_apply(const void* x, const void* grad_y, const float* mean, const 
  * (zeroed by the call unless accumulate != 0). */
 int rf_colsum(const void* g, float* out, int64_t rows, int cols, int dtype, int accumulate,
               void* stream);
+/* Space-to-depth of a channels-last token grid for the MiT spatial-reduction conv
+ * (mix_transformer.py:133-134,147-149: Conv2d(dim, dim, kernel_size=sr, stride=sr), which the host side
+ * runs as one GEMM on the packed tokens):  packed[b,hs,ws,i,j,:] = img[b, hs*s+i, ws*s+j, :], rows of
+ * row_bytes bytes (C * element size, a multiple of 16).  inverse != 0 scatters packed -> img (the input
+ * gradient).  src and dst must not alias. */
+int rf_space_to_depth(const void* src, void* dst, int B, int H, int W, int row_bytes, int s,
+                      int inverse, void* stream);
+/* y = act(y + bias[channel]) in place for a conv output [N,C,H,W] held either channels-last
+ * (chan_inner = 1) or NCHW-contiguous (chan_inner = H*W): the bias add + activation that follow the frozen
+ * library convolutions of the alignment network (VGG.forward, models/backbones/vgg.py:108-120; the BN-folded
+ * ConvBNReLU blocks of models/modules.py:16-56).  act: 0 none, 1 ReLU, 2 LeakyReLU(slope).
+ * dtype 0 = f32 (4-element vectors) / 1 = bf16 (8-element vectors); a scalar kernel serves channel runs
+ * that are not a multiple of the vector width. */
+int rf_bias_act(void* y, const float* bias, int64_t numel, int C, int64_t chan_inner, int act,
+                float slope, int dtype, void* stream);
+
+/* ---- DAFormer head feature fusion -------------------------------------------------------------- */
+/* y[b, :, :, off_i : off_i + E_i] = bilinear(src_i, size = (H, W), align_corners = False) for the n <= 4
+ * embedded stage features src_i [B, h_i, w_i, E_i] (bf16, channels-last = the token layout [B, h_i*w_i, E_i]),
+ * written once as the concatenated channels-last tensor y [B, H, W, sum E_i] (bf16).  Restates the resize + cat
+ * of DAFormerHead.forward (models/heads/daformer.py:203-221: F.interpolate(..., mode='bilinear',
+ * align_corners=False) per stage, then torch.cat(dim=1)).  A source that already has the output size is copied.
+ * src / h / w / E are HOST arrays of n entries; E_i % 8 == 0. */
+int rf_upsample_concat_fwd(const void* const* src, const int* h, const int* w, const int* E, int n,
+                           void* y, int B, int H, int W, void* stream);
+/* Gradients of the sources from grad_y [B, H, W, sum E_i] (gather over the output pixels that read each source
+ * pixel, no atomics); grad_src[i] may be NULL to skip a source. */
+int rf_upsample_concat_bwd(const void* grad_y, void* const* grad_src, const int* h, const int* w,
+                           const int* E, int n, int B, int H, int W, void* stream);
 /* fp32 -> bf16 copy of a flat parameter buffer (the bf16 shadow weights read by the tensor-core
  * GEMMs; replaces the per-tensor autocast casts of the reference's AMP path). */
 int rf_cast_bf16(const float* src, void* dst, int64_t n, void* stream);

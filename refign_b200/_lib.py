@@ -49,6 +49,10 @@ _SIGNATURES = {
     "rf_bn_bwd_apply": (c_int, [c_p] * 8 + [c_i64, c_int, ctypes.c_double, c_int, c_int, c_p]),
     "rf_colsum": (c_int, [c_p, c_p, c_i64, c_int, c_int, c_int, c_p]),
     "rf_cast_bf16": (c_int, [c_p, c_p, c_i64, c_p]),
+    "rf_upsample_concat_fwd": (c_int, [c_p, c_p, c_p, c_p, c_int, c_p, c_int, c_int, c_int, c_p]),
+    "rf_upsample_concat_bwd": (c_int, [c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p]),
+    "rf_bias_act": (c_int, [c_p, c_p, c_i64, c_int, c_i64, c_int, c_f32, c_int, c_p]),
+    "rf_space_to_depth": (c_int, [c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
     "rf_ema_update_dev": (c_int, [c_p, c_p, c_i64, c_p, c_p]),
     "rf_adamw_step_dev": (c_int, [c_p, c_p, c_p, c_p, c_i64, c_int, ctypes.POINTER(c_i64), ctypes.POINTER(c_f32),
                                   c_f32, c_f32, c_f32, c_f32, c_p, c_p]),

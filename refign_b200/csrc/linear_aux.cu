@@ -95,6 +95,100 @@ cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
     dst[i] = __float2bfloat16_rn(src[i]);
 }
 
+// Space-to-depth of a channels-last token grid (and its inverse): the s x s patch of pixel rows that one
+// spatial-reduction conv output reads becomes one contiguous row of s*s*C values, so the conv is a plain GEMM.
+//   packed[b, hs, ws, i, j, :] = img[b, hs*s + i, ws*s + j, :]          (H = Hs*s, W = Ws*s)
+// One thread moves one 16-byte chunk; consecutive threads walk the chunks of a pixel row, so both sides are
+// accessed in contiguous C*elt-byte runs.
+__global__ void __launch_bounds__(256)
+space_to_depth_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long nchunks, int chunks_per_pixel,
+                      int Hs, int Ws, int s, int inverse) {
+  const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (idx >= nchunks) return;
+  const int c = (int)(idx % chunks_per_pixel);
+  long p = idx / chunks_per_pixel;             // packed pixel index: (((b*Hs + hs)*Ws + ws)*s + i)*s + j
+  const int j = (int)(p % s);
+  p /= s;
+  const int i = (int)(p % s);
+  p /= s;
+  const int ws = (int)(p % Ws);
+  p /= Ws;
+  const int hs = (int)(p % Hs);
+  const long b = p / Hs;
+  const long img = ((b * Hs * s + (long)hs * s + i) * ((long)Ws * s) + (long)ws * s + j) * chunks_per_pixel + c;
+  if (inverse)
+    dst[img] = __ldg(src + idx);
+  else
+    dst[idx] = __ldg(src + img);
+}
+
+// y = act(y + bias[channel]) in place, 16-byte vectors, for the frozen (no-grad) convolution stacks of the
+// alignment network (VGG conv + bias + ReLU, BN-folded decoder convs + LeakyReLU): the library convolution
+// leaves the bias to a broadcast add and the activation to another elementwise pass.
+//   chan_inner == 1: channels-last memory (channel = element index % C), C % VEC == 0
+//   chan_inner  > 1: NCHW memory (channel = (index / chan_inner) % C), chan_inner % VEC == 0
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+bias_act_kernel(T* __restrict__ y, const float* __restrict__ bias, long nvec, int C, long chan_inner, int act,
+                float slope) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
+    const long e0 = i * VEC;
+    float v[VEC];
+    if (sizeof(T) == 2) {
+      const uint4 u = *reinterpret_cast<const uint4*>(y + e0);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int k = 0; k < VEC / 2; ++k) {
+        const float2 f = __bfloat1622float2(h[k]);
+        v[2 * k] = f.x;
+        v[2 * k + 1] = f.y;
+      }
+    } else {
+      const float4 f = *reinterpret_cast<const float4*>(y + e0);
+      v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+    }
+    if (chan_inner == 1) {
+      const int c0 = (int)(e0 % C);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) v[k] += __ldg(bias + c0 + k);
+    } else {
+      const float b = __ldg(bias + (int)((e0 / chan_inner) % C));
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) v[k] += b;
+    }
+    if (act == 1) {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) v[k] = fmaxf(v[k], 0.f);
+    } else if (act == 2) {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) v[k] = v[k] > 0.f ? v[k] : v[k] * slope;
+    }
+    if (sizeof(T) == 2) {
+      uint4 u;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+      for (int k = 0; k < VEC / 2; ++k) h[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+      *reinterpret_cast<uint4*>(y + e0) = u;
+    } else {
+      *reinterpret_cast<float4*>(y + e0) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+}
+
+// scalar variant for channel runs that are not a multiple of the vector width (e.g. the 7 x 7 / 5 x 5 maps of
+// the uncertainty decoder's per-pixel patch CNN)
+template <typename T>
+__global__ void __launch_bounds__(256)
+bias_act_scalar_kernel(T* __restrict__ y, const float* __restrict__ bias, long n, int C, long chan_inner, int act,
+                       float slope) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float v = (float)y[i] + __ldg(bias + (int)((i / chan_inner) % C));
+    if (act == 1) v = fmaxf(v, 0.f);
+    else if (act == 2) v = v > 0.f ? v : v * slope;
+    y[i] = (T)v;
+  }
+}
+
 }  // namespace rf
 
 using namespace rf;
@@ -129,5 +223,51 @@ extern "C" int rf_cast_bf16(const float* src, void* dst, int64_t n, void* stream
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
   cast_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
   RF_CHECK_LAUNCH("cast_bf16_kernel");
+  return RF_OK;
+}
+
+extern "C" int rf_space_to_depth(const void* src, void* dst, int B, int H, int W, int row_bytes, int s, int inverse,
+                                 void* stream) {
+  RF_REQUIRE(src && dst && B > 0 && H > 0 && W > 0 && s > 0, "rf_space_to_depth: bad argument");
+  RF_REQUIRE(H % s == 0 && W % s == 0, "rf_space_to_depth: H=%d, W=%d must be multiples of s=%d", H, W, s);
+  RF_REQUIRE(row_bytes > 0 && row_bytes % 16 == 0, "rf_space_to_depth: row_bytes=%d must be a multiple of 16", row_bytes);
+  RF_REQUIRE((((uintptr_t)src | (uintptr_t)dst) & 15) == 0, "rf_space_to_depth: buffers must be 16-byte aligned");
+  const int cpp = row_bytes / 16;
+  const long nchunks = (long)B * H * W * cpp;
+  const long blocks = (nchunks + 255) / 256;
+  RF_REQUIRE(blocks < (1l << 31), "rf_space_to_depth: tensor too large");
+  space_to_depth_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)src, (uint4*)dst, nchunks, cpp,
+                                                                            H / s, W / s, s, inverse);
+  RF_CHECK_LAUNCH("space_to_depth_kernel");
+  return RF_OK;
+}
+
+extern "C" int rf_bias_act(void* y, const float* bias, int64_t numel, int C, int64_t chan_inner, int act, float slope,
+                           int dtype, void* stream) {
+  RF_REQUIRE(y && bias && numel > 0 && C > 0 && chan_inner > 0, "rf_bias_act: bad argument");
+  RF_REQUIRE(dtype == 0 || dtype == 1, "rf_bias_act: dtype must be 0 (f32) or 1 (bf16)");
+  RF_REQUIRE(act >= 0 && act <= 2, "rf_bias_act: act must be 0 (none), 1 (relu) or 2 (leaky relu)");
+  const int vec = dtype == 1 ? 8 : 4;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec_ok = (((uintptr_t)y & 15) == 0) && (numel % vec == 0) &&
+                      (chan_inner == 1 ? (C % vec == 0) : (chan_inner % vec == 0));
+  if (!vec_ok) {
+    long sb = (numel + 255) / 256;
+    if (sb > (long)kNumSMs * 32) sb = (long)kNumSMs * 32;
+    if (dtype == 1)
+      bias_act_scalar_kernel<__nv_bfloat16><<<(unsigned)sb, 256, 0, st>>>((__nv_bfloat16*)y, bias, numel, C, chan_inner, act, slope);
+    else
+      bias_act_scalar_kernel<float><<<(unsigned)sb, 256, 0, st>>>((float*)y, bias, numel, C, chan_inner, act, slope);
+    RF_CHECK_LAUNCH("bias_act_scalar_kernel");
+    return RF_OK;
+  }
+  const long nvec = numel / vec;
+  long blocks = (nvec + 255) / 256;
+  if (blocks > (long)kNumSMs * 16) blocks = (long)kNumSMs * 16;
+  if (dtype == 1)
+    bias_act_kernel<__nv_bfloat16, 8><<<(unsigned)blocks, 256, 0, st>>>((__nv_bfloat16*)y, bias, nvec, C, chan_inner, act, slope);
+  else
+    bias_act_kernel<float, 4><<<(unsigned)blocks, 256, 0, st>>>((float*)y, bias, nvec, C, chan_inner, act, slope);
+  RF_CHECK_LAUNCH("bias_act_kernel");
   return RF_OK;
 }

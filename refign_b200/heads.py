@@ -15,6 +15,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import ops
 from .matching_utils import unnormalise_and_convert_mapping_to_flow, warp
 from .modules import (MLP, ConvBNReLU, GlobalFeatureCorrelationLayer, LocalFeatureCorrelationLayer,
                       OpticalFlowEstimatorResidualConnection, RefinementModule, UncertaintyModule)
@@ -96,20 +97,28 @@ class DAFormerHead(BaseHead):
         n = x[-1].shape[0]
         os_size = x[0].shape[2:]
         cl = x[0].is_cuda
-        embedded = []
+        embedded, sizes = [], []
         for i in range(len(self.in_channels)):
             hi, wi = x[i].shape[2:]
-            c = self.embed_layers[str(i)](x[i])                 # [n, hi*wi, E] tokens
-            c = c.view(n, hi, wi, -1).permute(0, 3, 1, 2)       # NCHW view, channels-last memory
-            if (hi, wi) != tuple(os_size):
-                # autocast would promote the upsampling to fp32 (a 4-byte [n,256,H/4,W/4] tensor per stage and an
-                # fp32 ASPP input); the kernel accumulates in fp32 either way, keep the activations bf16
-                with torch.autocast('cuda', enabled=False):
-                    c = F.interpolate(c, size=os_size, mode='bilinear', align_corners=False)
-            embedded.append(c)
-        y = torch.cat(embedded, dim=1)
-        if cl:
-            y = y.contiguous(memory_format=torch.channels_last)
+            embedded.append(self.embed_layers[str(i)](x[i]))    # [n, hi*wi, E] tokens
+            sizes.append((hi, wi))
+        if (cl and len(embedded) <= 4 and all(c.dtype == torch.bfloat16 and c.shape[-1] % 8 == 0 for c in embedded)
+                and all(hi <= os_size[0] and wi <= os_size[1] for hi, wi in sizes)):
+            # one kernel writes the concatenated channels-last tensor (resize + cat of reference :203-221)
+            y = ops.upsample_concat(embedded, sizes, os_size)
+        else:
+            maps = []
+            for c, (hi, wi) in zip(embedded, sizes):
+                c = c.view(n, hi, wi, -1).permute(0, 3, 1, 2)       # NCHW view, channels-last memory
+                if (hi, wi) != tuple(os_size):
+                    # autocast would promote the upsampling to fp32 (a 4-byte [n,256,H/4,W/4] tensor per stage and
+                    # an fp32 ASPP input); the kernel accumulates in fp32 either way, keep the activations bf16
+                    with torch.autocast('cuda', enabled=False):
+                        c = F.interpolate(c, size=os_size, mode='bilinear', align_corners=False)
+                maps.append(c)
+            y = torch.cat(maps, dim=1)
+            if cl:
+                y = y.contiguous(memory_format=torch.channels_last)
         y = self.fuse_layer(y)
         if self.dropout is not None:
             y = self.dropout(y)

@@ -84,6 +84,10 @@ class ConvBNReLU(nn.Module):
                     and self.bn.track_running_stats and not torch.is_grad_enabled())
         if foldable:
             w, b = self._fold()
+            act = self.activation if self.use_activation else None
+            if x.is_cuda and (act is None or isinstance(act, (nn.ReLU, nn.LeakyReLU))):
+                # frozen block: library conv + ONE fused bias / activation sweep
+                return ops.conv_bias_act(x, w.to(x.dtype), b, conv.stride, conv.padding, conv.dilation, conv.groups, act)
             x = F.conv2d(x, w.to(x.dtype), b.to(x.dtype), conv.stride, conv.padding, conv.dilation, conv.groups)
         else:
             if self._is_depthwise3x3():

@@ -654,6 +654,101 @@ def refresh_derived(flat_shadow=None):
             wp.view(src.shape[0], src.shape[2], src.shape[3], src.shape[1]).copy_(src.permute(0, 2, 3, 1))
 
 
+def conv_bias_act(x, weight, bias, stride, padding, dilation, groups, act=None):
+    """``act(conv2d(x, weight) + bias)`` for the frozen (no-grad) conv stacks: library convolution without
+    bias + one in-place 16-byte-vector bias/activation kernel (the library path runs a broadcast add and a
+    separate activation pass over the full-resolution tensors).  ``act``: None, nn.ReLU or nn.LeakyReLU."""
+    y = F.conv2d(x, weight, None, stride, padding, dilation, groups)
+    code, slope = 0, 0.0
+    if isinstance(act, torch.nn.ReLU):
+        code = 1
+    elif isinstance(act, torch.nn.LeakyReLU):
+        code, slope = 2, float(act.negative_slope)
+    elif act is not None:
+        raise RuntimeError("conv_bias_act: unsupported activation %r" % (act,))
+    N, C, H, W = y.shape
+    if y.is_contiguous():
+        inner = H * W
+    elif y.is_contiguous(memory_format=torch.channels_last):
+        inner = 1
+    else:
+        inner = 0
+    if inner == 0 or bias is None or y.dtype not in (torch.float32, torch.bfloat16):
+        if bias is not None:
+            y = y + bias.to(y.dtype).view(1, -1, 1, 1)
+        return act(y) if act is not None else y
+    b = _f32c(bias)
+    with torch.cuda.device(y.device):
+        _run("rf_bias_act", ptr(y), ptr(b), y.numel(), C, inner, code, slope, _dt_code(y), _stream(),
+             work=(2 * y.numel() * y.element_size(), 2 * y.numel()))
+    return y
+
+
+class _UpsampleConcat(torch.autograd.Function):
+    """Bilinear resize (align_corners=False) of up to four token maps to (H, W) + channel concat, written
+    once as a channels-last [B, sum E, H, W] tensor; the backward gathers each source's gradient."""
+
+    @staticmethod
+    def forward(ctx, H, W, sizes, *feats):
+        n = len(feats)
+        B = feats[0].shape[0]
+        fs = [f.contiguous() for f in feats]
+        Es = [f.shape[-1] for f in fs]
+        y = torch.empty(B, H, W, sum(Es), device=fs[0].device, dtype=torch.bfloat16)
+        hs, ws = [s[0] for s in sizes], [s[1] for s in sizes]
+        ctx.meta = (B, H, W, hs, ws, Es)
+        IntArr, PtrArr = ctypes.c_int * n, ctypes.c_void_p * n
+        with torch.cuda.device(y.device):
+            _run("rf_upsample_concat_fwd", PtrArr(*[f.data_ptr() for f in fs]), IntArr(*hs), IntArr(*ws), IntArr(*Es),
+                 n, ptr(y), B, H, W, _stream(), work=(2 * y.numel() + 2 * sum(f.numel() for f in fs), 8 * y.numel()),
+                 tag="upsample_concat_fwd")
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        B, H, W, hs, ws, Es = ctx.meta
+        n = len(Es)
+        g = gy.permute(0, 2, 3, 1)
+        if g.dtype != torch.bfloat16:
+            g = g.to(torch.bfloat16)
+        g = g.contiguous()
+        grads = [torch.empty(B, hs[i] * ws[i], Es[i], device=g.device, dtype=torch.bfloat16)
+                 if ctx.needs_input_grad[3 + i] else None for i in range(n)]
+        IntArr, PtrArr = ctypes.c_int * n, ctypes.c_void_p * n
+        with torch.cuda.device(g.device):
+            _run("rf_upsample_concat_bwd", ptr(g), PtrArr(*[ptr(t) for t in grads]), IntArr(*hs), IntArr(*ws),
+                 IntArr(*Es), n, B, H, W, _stream(), work=(2 * g.numel() + 2 * sum(t.numel() for t in grads if t is not None),
+                                                          8 * g.numel()), tag="upsample_concat_bwd")
+        return (None, None, None) + tuple(grads)
+
+
+def upsample_concat(feats, sizes, out_size):
+    """DAFormer head fusion: ``cat([interpolate(f_i as NCHW, out_size, 'bilinear', align_corners=False)], 1)``
+    for bf16 token maps ``feats[i]`` [B, h_i*w_i, E_i] with ``sizes[i] = (h_i, w_i)``; returns a logical NCHW
+    tensor [B, sum E_i, H, W] with channels-last memory."""
+    require_cuda(*feats)
+    return _UpsampleConcat.apply(int(out_size[0]), int(out_size[1]), tuple((int(h), int(w)) for h, w in sizes), *feats)
+
+
+def space_to_depth(x, H, W, s, inverse=False):
+    """[B, H*W, C] tokens -> [B*(H/s)*(W/s), s*s*C] packed patches (or back with ``inverse``): one
+    16-byte-vector copy kernel instead of a generic strided permute copy."""
+    if inverse:
+        BM, K = x.shape
+        C = K // (s * s)
+        B = BM // ((H // s) * (W // s))
+        out = torch.empty(B, H * W, C, device=x.device, dtype=x.dtype)
+    else:
+        B, N, C = x.shape
+        out = torch.empty(B * (H // s) * (W // s), s * s * C, device=x.device, dtype=x.dtype)
+    x = x.contiguous()
+    with torch.cuda.device(x.device):
+        _run("rf_space_to_depth", ptr(x), ptr(out), B, H, W, C * x.element_size(), s, int(inverse), _stream(),
+             work=(2 * x.numel() * x.element_size(), 0))
+    return out
+
+
 class _SrConvGemm(torch.autograd.Function):
     """``Conv2d(C, Co, kernel_size=s, stride=s)`` on a token grid as space-to-depth + one tensor-core GEMM
     (reference mix_transformer.py:133-134,147-149 run it as a cuDNN convolution between two layout
@@ -668,10 +763,10 @@ class _SrConvGemm(torch.autograd.Function):
         Hs, Ws = H // s, W // s
         with torch.autocast('cuda', enabled=False):
             xb = x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
-            xs = xb.view(B, Hs, s, Ws, s, C).permute(0, 1, 3, 2, 4, 5).reshape(B * Hs * Ws, s * s * C)
+            xs = space_to_depth(xb, H, W, s)
             y = F.linear(xs, wperm, bias_b)
         ctx.save_for_backward(xs, wperm)
-        ctx.meta = (B, Hs, Ws, s, C, x.dtype, weight.shape)
+        ctx.meta = (B, H, W, s, C, x.dtype, weight.shape)
         ctx.targets = (gw_t, gb_t)
         return y.view(B, Hs * Ws, -1)
 
@@ -679,7 +774,7 @@ class _SrConvGemm(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, go):
         xs, wperm = ctx.saved_tensors
-        B, Hs, Ws, s, C, xdtype, wshape = ctx.meta
+        B, H, W, s, C, xdtype, wshape = ctx.meta
         gw_t, gb_t = ctx.targets
         Co = wshape[0]
         dx = dw = db = None
@@ -690,8 +785,7 @@ class _SrConvGemm(torch.autograd.Function):
             if not go2.is_contiguous():
                 go2 = go2.contiguous()
             if ctx.needs_input_grad[0]:
-                dxs = go2 @ wperm                                            # [B*M, s*s*C]
-                dx = dxs.view(B, Hs, Ws, s, s, C).permute(0, 1, 3, 2, 4, 5).reshape(B, Hs * s * Ws * s, C)
+                dx = space_to_depth(go2 @ wperm, H, W, s, inverse=True)      # [B*M, s*s*C] -> [B, N, C]
                 if dx.dtype != xdtype:
                     dx = dx.to(xdtype)
             if ctx.needs_input_grad[1]:
@@ -719,7 +813,7 @@ def sr_conv(x, H, W, conv):
     bb = getattr(conv.bias, '_rf_bf16', None) if conv.bias is not None else None
     ok = (x.is_cuda and _bf16_autocast() and wb is not None and conv.bias is not None and bb is not None
           and conv.kernel_size == conv.stride and conv.kernel_size[0] == conv.kernel_size[1]
-          and conv.padding == (0, 0) and conv.groups == 1 and H % s == 0 and W % s == 0)
+          and conv.padding == (0, 0) and conv.groups == 1 and H % s == 0 and W % s == 0 and x.shape[-1] % 8 == 0)
     if not ok:
         B, N, C = x.shape
         y = conv(x.view(B, H, W, C).permute(0, 3, 1, 2))

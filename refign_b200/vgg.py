@@ -6,6 +6,8 @@ returned as ordinary NCHW-shaped tensors (channels-last strides on CUDA)."""
 import torch
 import torch.nn as nn
 
+from . import ops
+
 _CFGS = {
     'A': [64, 'M', 128, 'M', 256, 256, 'M', 512, 512, 'M', 512, 512, 'M'],
     'B': [64, 64, 'M', 128, 128, 'M', 256, 256, 'M', 512, 512, 'M', 512, 512, 'M'],
@@ -66,8 +68,35 @@ class VGG(nn.Module):
         if x.is_cuda:
             x = x.contiguous(memory_format=torch.channels_last)
         outs, prev = [], 0
+        fused = x.is_cuda and not torch.is_grad_enabled()
         for c in cuts:
-            x = self.features[prev:c](x)
+            if fused:
+                x = self._run_fused(x, prev, c)
+            else:
+                x = self.features[prev:c](x)
             outs.append(x)
             prev = c
         return outs
+
+    def _run_fused(self, x, lo, hi):
+        """features[lo:hi] with conv + bias + ReLU as library conv + one fused in-place sweep (no-grad only)."""
+        i = lo
+        while i < hi:
+            m = self.features[i]
+            nxt = self.features[i + 1] if i + 1 < hi else None
+            if isinstance(m, nn.Conv2d) and isinstance(nxt, nn.ReLU) and m.bias is not None \
+                    and m.padding_mode == 'zeros':
+                w = m.weight
+                if torch.is_autocast_enabled() and torch.get_autocast_dtype('cuda') == torch.bfloat16:
+                    # frozen weights: one cached bf16 channels-last copy instead of an autocast cast per call
+                    x = x.to(torch.bfloat16)
+                    w = getattr(m, '_rf_w_bf16', None)
+                    if w is None or m._rf_w_version != m.weight._version:
+                        w = m.weight.detach().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+                        m._rf_w_bf16, m._rf_w_version = w, m.weight._version
+                x = ops.conv_bias_act(x, w, m.bias, m.stride, m.padding, m.dilation, m.groups, nxt)
+                i += 2
+            else:
+                x = m(x)
+                i += 1
+        return x

@@ -400,3 +400,59 @@ def test_sr_conv_patch_gemm_matches_conv(spec):
         out2 = ops.sr_conv(x, H, W, conv)
     ref2 = F.conv2d(xr.detach(), conv.weight._rf_bf16.float(), br.detach(), stride=s)
     _close(out2, ref2.permute(0, 2, 3, 1).reshape(gy.shape), 2 * 2 ** -8, 2 * 2 ** -8 * float(ref2.abs().max()), "refreshed")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("spec", [(2, 64, 24, 40, True, "relu"), (3, 32, 7, 7, False, "leaky"), (1, 19, 16, 16, True, None),
+                                  (2, 128, 8, 8, False, "relu")])
+def test_conv_bias_act_matches_library(spec, dtype):
+    """Library conv + fused in-place bias/activation sweep (vector and scalar paths, both memory formats)
+    vs conv2d + bias + activation."""
+    import torch.nn as nn
+    B, C, H, W, channels_last, actname = spec
+    torch.manual_seed(sum(spec[:4]))
+    act = {"relu": nn.ReLU(), "leaky": nn.LeakyReLU(0.1), None: None}[actname]
+    x = torch.randn(B, 16, H, W, device=DEV).to(dtype)
+    if channels_last:
+        x = x.contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(C, 16, 3, 3, device=DEV) * 0.2).to(dtype)
+    b = torch.randn(C, device=DEV)
+    ref = F.conv2d(x.float(), w.float(), b, padding=1)
+    if act is not None:
+        ref = act(ref)
+    with torch.no_grad():
+        got = ops.conv_bias_act(x, w, b, 1, 1, 1, 1, act)
+    assert got.dtype == dtype
+    tol = 1e-3 if dtype == torch.float32 else 2 * 2 ** -8
+    _close(got, ref, tol, tol * float(ref.abs().max()), "conv_bias_act")
+
+
+@pytest.mark.parametrize("spec", [(2, 32, 32, [(32, 32, 64), (16, 16, 64), (8, 8, 64), (4, 4, 64)]),
+                                  (1, 24, 40, [(24, 40, 32), (12, 20, 16), (5, 7, 8)]),
+                                  (2, 16, 16, [(8, 8, 256), (16, 16, 8)])])
+def test_upsample_concat_fwd_bwd(spec):
+    """Fused bilinear resize + concat vs F.interpolate(align_corners=False) + cat in fp32 on the same bf16
+    inputs; gradients of every source vs autograd."""
+    B, H, W, srcs = spec
+    torch.manual_seed(H + W)
+    feats = [torch.randn(B, h * w, E, device=DEV).to(torch.bfloat16) for h, w, E in srcs]
+    sizes = [(h, w) for h, w, _ in srcs]
+    refs = [f.float().clone().requires_grad_(True) for f in feats]
+    maps = []
+    for r, (h, w, E) in zip(refs, srcs):
+        m = r.view(B, h, w, E).permute(0, 3, 1, 2)
+        if (h, w) != (H, W):
+            m = F.interpolate(m, size=(H, W), mode="bilinear", align_corners=False)
+        maps.append(m)
+    ref = torch.cat(maps, 1)
+    gy = torch.randn_like(ref).to(torch.bfloat16)
+    ref.backward(gy.float())
+    ins = [f.clone().requires_grad_(True) for f in feats]
+    out = ops.upsample_concat(ins, sizes, (H, W))
+    assert out.shape == ref.shape and out.dtype == torch.bfloat16
+    assert out.is_contiguous(memory_format=torch.channels_last)
+    out.backward(gy)
+    tol = 2 * 2 ** -8
+    _close(out, ref, tol, tol * float(ref.abs().max()), "forward")
+    for i, (a, r) in enumerate(zip(ins, refs)):
+        _close(a.grad, r.grad, tol, tol * float(r.grad.abs().max()), "grad_src%d" % i)

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "step_profile.json"))
     ap.add_argument("--top", type=int, default=60)
     ap.add_argument("--ops", action="store_true", help="also list the top aten ops by device time with shapes + source line")
+    ap.add_argument("--find", default="", help="comma-separated kernel-name substrings: print which ops (with parents) launch them")
     args = ap.parse_args()
     import torch
     from torch.profiler import ProfilerActivity, profile
@@ -39,7 +40,7 @@ def main():
     t_host = time.perf_counter() - t0
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t0
-    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=args.ops,
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=args.ops or bool(args.find),
                  with_stack=args.ops) as prof:
         model.training_step(batch, 4)
         torch.cuda.synchronize()
@@ -64,6 +65,22 @@ def main():
         print("%8.3f ms %5.1f%% x%-5d %s" % (r["ms"], 100 * r["share"], r["calls"], r["kernel"][:110]))
 
 
+    if args.find:
+        pats = [p for p in args.find.split(",") if p]
+        agg = {}
+        for e in prof.events():
+            for k in getattr(e, "kernels", []) or []:
+                if all(p in k.name for p in pats):
+                    chain, q = [], e
+                    while q is not None and len(chain) < 5:
+                        chain.append(q.name[:40])
+                        q = getattr(q, "cpu_parent", None)
+                    key = (" <- ".join(chain), str(getattr(e, "input_shapes", ""))[:80])
+                    a = agg.setdefault(key, [0, 0.0])
+                    a[0] += 1
+                    a[1] += k.duration / 1e3
+        for key, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:25]:
+            print("FIND %8.3f ms x%-4d %s | %s" % (ms, n, key[0], key[1]))
     if args.ops:
         ev = [e for e in prof.key_averages(group_by_input_shape=True, group_by_stack_n=6)
               if getattr(e, "self_device_time_total", 0) > 0 and e.device_type.name != "CUDA"]
