@@ -77,7 +77,31 @@ bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float*
     }
     const long r0 = (long)blockIdx.y * strip;
     const long r1 = (r0 + strip < rows) ? r0 + strip : rows;
-    for (long r = r0 + rl; r < r1; r += BN_RL) {
+    // four rows in flight per thread (independent 16-byte loads), then the tail
+    constexpr int U = 4;
+    long r = r0 + rl;
+    for (; r + (U - 1) * BN_RL < r1; r += U * BN_RL) {
+      float v[U][8], g[U][8];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        bn_load8<T>(x + (r + u * BN_RL) * C + cg * 8, v[u]);
+        if (MODE == 1) bn_load8<T>(dy + (r + u * BN_RL) * C + cg * 8, g[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (MODE == 0) {
+            a0[k] += v[u][k];
+            a1[k] = fmaf(v[u][k], v[u][k], a1[k]);
+          } else {
+            const float gg = (relu && fmaf(v[u][k], sc[k], sh[k]) <= 0.f) ? 0.f : g[u][k];
+            a0[k] += gg;
+            a1[k] = fmaf(gg, (v[u][k] - mu[k]) * rs[k], a1[k]);
+          }
+        }
+    }
+    for (; r < r1; r += BN_RL) {
       float v[8];
       bn_load8<T>(x + r * C + cg * 8, v);
       if (MODE == 0) {
