@@ -4,7 +4,7 @@ Layout:
   csrc/                  CUDA kernels + the C-ABI (include/refign_b200.h) -> librefign_b200.so
   _lib.py, ops.py        ctypes binding and the operator layer (autograd wrappers)
   modules.py, mix_transformer.py, vgg.py, heads.py, matching_utils.py, dacs_transforms.py,
-  segmentation_model.py, alignment_model.py
+  segmentation_model.py, alignment_model.py, losses.py
                          host-side mirror of the reference's module interface (same class names,
                          constructor arguments, forward signatures and state_dict keys)
   runtime.py             flat-buffer optimiser / EMA / gradient all-reduce around training_step
@@ -13,6 +13,7 @@ There is no CPU implementation and no fallback: the operators raise if the CUDA 
 """
 from .alignment_model import AlignmentModel  # noqa: F401
 from .heads import BaseHead, DAFormerHead, UAWarpCHead  # noqa: F401
+from .losses import HuberLoss, MultiScaleFlowLoss, WBipathLoss  # noqa: F401
 from .mix_transformer import MixVisionTransformer  # noqa: F401
 from .segmentation_model import DomainAdaptationSegmentationModel, PixelWeightedCrossEntropyLoss  # noqa: F401
 from .vgg import VGG  # noqa: F401

@@ -131,6 +131,8 @@ class DomainAdaptationSegmentationModel(_Base):
         self._fused_pseudo = None             # (probs tensor, label, maxprob) handed from refine to get_dacs_mix
         self._graphs = None                   # CUDA-graph state installed by enable_cuda_graphs()
         self.fuse_source_backward = True      # one backward for loss_src + feature distance (see _step_part_a)
+        self.concurrent_branches = True       # teacher / alignment branches on side streams (see _fork_target_branches)
+        self._side_streams = None
         self.load_weights(pretrained)
 
     # ---- what Lightning would provide ---------------------------------------------------------------
@@ -231,6 +233,10 @@ class DomainAdaptationSegmentationModel(_Base):
         target + reference, align, warp, refine.  Returns what the DACS mix needs."""
         opt.zero_grad()
         self.update_momentum_encoder()
+        side = None
+        if (self.concurrent_branches and batch['image_src'].is_cuda and self.use_refign and self.use_align
+                and not self.adapt_to_ref and self.alignment_head is not None):
+            side = self._fork_target_branches(batch)
 
         # ---- source ----------------------------------------------------------------------------
         images_src, gt_src = batch['image_src'], batch['semantic_src']
@@ -246,8 +252,12 @@ class DomainAdaptationSegmentationModel(_Base):
             # distance: segmentation_model.py:172-192), i.e. it walks the backbone graph twice and sums the
             # two gradients in .grad.  The gradient of a sum is the sum of the gradients, so one backward
             # of (loss_src + loss_fd) leaves the same .grad -- and walks the 52 MiT blocks once.
+            feat_imnet = None
+            if side is not None and 'feat_imnet' in side:
+                torch.cuda.current_stream().wait_stream(self._side_streams[2])
+                feat_imnet = side['feat_imnet']
             with self._autocast():
-                loss_fd = self.calc_feat_dist(images_src, gt_src, feats_src)
+                loss_fd = self.calc_feat_dist(images_src, gt_src, feats_src, feat_imnet)
             self.log("train_loss_featdist_src", loss_fd)
             self.manual_backward(loss_src + loss_fd.to(loss_src.dtype))
             del loss_fd, loss_src, logits_src
@@ -255,8 +265,12 @@ class DomainAdaptationSegmentationModel(_Base):
             self.manual_backward(loss_src, retain_graph=self.enable_fdist)
             del loss_src, logits_src
             if self.enable_fdist:
+                feat_imnet = None
+                if side is not None and 'feat_imnet' in side:
+                    torch.cuda.current_stream().wait_stream(self._side_streams[2])
+                    feat_imnet = side['feat_imnet']
                 with self._autocast():
-                    loss_fd = self.calc_feat_dist(images_src, gt_src, feats_src)
+                    loss_fd = self.calc_feat_dist(images_src, gt_src, feats_src, feat_imnet)
                 self.log("train_loss_featdist_src", loss_fd)
                 self.manual_backward(loss_fd)
                 del loss_fd
@@ -264,6 +278,10 @@ class DomainAdaptationSegmentationModel(_Base):
 
         # ---- target (no grad) ------------------------------------------------------------------
         self._fused_pseudo = None
+        if side is not None:
+            m_probs_trg, images_trg, keep = self._join_target_branches(side, batch)
+            fused, self._fused_pseudo = self._fused_pseudo, None
+            return {'images_trg': images_trg, 'probs': m_probs_trg, 'fused': fused, 'keep': keep}
         with torch.no_grad(), self._autocast():
             if self.adapt_to_ref and random.random() < 0.5:
                 adapt_to_ref, images_trg = True, batch['image_ref']
@@ -290,6 +308,50 @@ class DomainAdaptationSegmentationModel(_Base):
                 m_probs_trg = F.softmax(m_logits_trg, dim=1)
         fused, self._fused_pseudo = self._fused_pseudo, None
         return {'images_trg': images_trg, 'probs': m_probs_trg, 'fused': fused}
+
+    # ---- concurrent branches of part A (B200: fill the SMs that one branch's small kernels leave idle) ----
+    def _fork_target_branches(self, batch):
+        """The EMA-teacher forward on (target, reference) and the alignment network (VGG + UAWarpC) depend
+        only on the input images and on weights that are final once the EMA update has been issued, so they
+        run on two side streams while the main stream does the student's source forward / backward; the
+        main stream joins them before warp + refine.  The dependency structure is captured as-is by the
+        CUDA graph of part A (fork / join through events)."""
+        images_trg, images_ref = batch['image_trg'], batch['image_ref']
+        main = torch.cuda.current_stream()
+        if self._side_streams is None:
+            self._side_streams = tuple(torch.cuda.Stream(device=images_trg.device) for _ in range(3))
+        s_teacher, s_align, s_imnet = self._side_streams
+        out = {}
+        s_teacher.wait_stream(main)
+        s_align.wait_stream(main)
+        with torch.no_grad(), self._autocast():
+            if self.enable_fdist:   # frozen ImageNet copy of the backbone on the source images (feature distance)
+                s_imnet.wait_stream(main)   # (a forked stream must get work and be joined: graph capture)
+                with torch.cuda.stream(s_imnet):
+                    out['feat_imnet'] = self.imnet_backbone(batch['image_src'])
+            with torch.cuda.stream(s_align):
+                out['flow'], out['logvar'] = _alignment_flow(self.alignment_backbone, self.alignment_head, images_trg,
+                                                             images_ref)
+            with torch.cuda.stream(s_teacher):
+                m_input = torch.cat((images_trg, images_ref))
+                m_logits = self.m_head(self.m_backbone(m_input))
+                out['m_logits'] = F.interpolate(m_logits.float(), size=m_input.shape[-2:], mode='bilinear',
+                                                align_corners=False)
+        return out
+
+    def _join_target_branches(self, side, batch):
+        main = torch.cuda.current_stream()
+        for s in self._side_streams[:2]:
+            main.wait_stream(s)
+        images_trg = batch['image_trg']
+        b = images_trg.shape[0]
+        with torch.no_grad(), self._autocast():
+            m_logits_trg, m_logits_ref = side['m_logits'][:b], side['m_logits'][b:]
+            warped_ref, warp_mask = warp(m_logits_ref, side['flow'], return_mask=True)
+            m_probs_trg = self.refine(m_logits_trg, warped_ref, warp_mask, None, logvar=side['logvar'])
+        # the cross-stream tensors stay referenced until the step's outputs are dropped, so the caching
+        # allocator cannot hand their blocks to a later side-stream allocation while the main stream reads them
+        return m_probs_trg, images_trg, side
 
     def _step_part_b(self, mixed, opt):
         """Student forward/backward on the class-mixed images (the third backward pass)."""
@@ -477,10 +539,11 @@ class DomainAdaptationSegmentationModel(_Base):
         return torch.cat(mixed_img), torch.cat(mixed_lbl).squeeze(1), pseudo_weight
 
     # ---- ImageNet feature distance (reference :584-668) --------------------------------------------
-    def calc_feat_dist(self, img, gt, feat=None):
+    def calc_feat_dist(self, img, gt, feat=None, feat_imnet=None):
         assert self.enable_fdist
         with torch.no_grad():
-            feat_imnet = self.imnet_backbone(img)
+            if feat_imnet is None:
+                feat_imnet = self.imnet_backbone(img)
             feat_imnet = [f.detach() for f in feat_imnet] if isinstance(feat_imnet, Sequence) else [feat_imnet.detach()]
         if not isinstance(feat, Sequence):
             feat = [feat]

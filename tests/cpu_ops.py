@@ -80,6 +80,36 @@ def _patch_embed_ln(x, conv_w, conv_b, ln_w, ln_b, eps):
     return F.layer_norm(y.flatten(2).transpose(1, 2), (y.shape[1],), ln_w, ln_b, eps), H, W
 
 
+def _warp(x, flo, padding_mode="zeros", return_mask=False):
+    """Oracle warp; when a gradient is needed (alignment training) the same sampling through torch's
+    differentiable grid_sample (align_corners=True, zeros padding: what helpers/matching_utils.py:11-49 calls)."""
+    if not (torch.is_grad_enabled() and (x.requires_grad or flo.requires_grad)):
+        return oracle.warp(x, flo, return_mask=return_mask)
+    B, C, H, W = x.shape
+    xs = torch.arange(W, dtype=torch.float32).view(1, 1, W).expand(B, H, W)
+    ys = torch.arange(H, dtype=torch.float32).view(1, H, 1).expand(B, H, W)
+    gx = 2.0 * (xs + flo[:, 0].float()) / max(W - 1, 1) - 1.0
+    gy = 2.0 * (ys + flo[:, 1].float()) / max(H - 1, 1) - 1.0
+    grid = torch.stack((gx, gy), -1)
+    out = F.grid_sample(x.float(), grid, mode="bilinear", padding_mode="zeros", align_corners=True)
+    if return_mask:
+        mask = (gx > -1) & (gy > -1) & (gx < 1) & (gy < 1)
+        return out, mask
+    return out
+
+
+def _local_corr(s, t, P=9):
+    """Oracle local correlation layer; differentiable shift-and-sum formulation when a gradient is needed."""
+    if not (torch.is_grad_enabled() and (s.requires_grad or t.requires_grad)):
+        return oracle.local_corr_layer(s, t, P)
+    r = (P - 1) // 2
+    B, C, H, W = s.shape
+    sp = F.pad(s.float(), (r, r, r, r))
+    planes = [(t.float() * sp[:, :, dy:dy + H, dx:dx + W]).sum(1) for dy in range(P) for dx in range(P)]
+    corr = torch.stack(planes, 1)
+    return F.normalize(F.relu(corr), p=2, dim=1)
+
+
 _PATCH = {
     "patch_embed_ln": _patch_embed_ln,
     "ema_update_dev_": _ema_dev,
@@ -88,10 +118,10 @@ _PATCH = {
     "add_layer_norm": _add_layer_norm,
     "dwconv3x3_gelu": _dwconv_gelu,
     "dwconv3x3_nhwc": _dwconv_nhwc,
-    "local_correlation_relu_l2norm": lambda s, t, P=9: oracle.local_corr_layer(s, t, P),
+    "local_correlation_relu_l2norm": _local_corr,
     "global_correlation": lambda s, t, cyclic_consistency=True, normalise=True, use_tensor_cores=-1:
         oracle.global_corr(s, t),
-    "warp": lambda x, flo, padding_mode="zeros", return_mask=False: oracle.warp(x, flo, return_mask=return_mask),
+    "warp": _warp,
     "estimate_probability_of_confidence_interval_of_mixture_density": lambda u, R=1.0: oracle.cert(u),
     "refine_fused": _refine,
     "ema_update_": _ema,

@@ -236,10 +236,15 @@ def test_graphed_train_step_matches_eager():
 
     batch = bench.synth_batch(128, 2, 5, torch.device(DEV))
     runs = []
+    # reference trajectory: eager, one stream, the reference's two source backward passes; then the graphed
+    # step with the concurrent branches and the single source backward (the defaults)
     for graphed in (False, True):
         m = build()
         if graphed:
             m.enable_cuda_graphs(warmup=2)
+        else:
+            m.concurrent_branches = False
+            m.fuse_source_backward = False
         torch.manual_seed(123)
         for i in range(6):
             m.training_step(batch, i)
