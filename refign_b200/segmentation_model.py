@@ -322,7 +322,8 @@ class DomainAdaptationSegmentationModel(_Base):
             self._side_streams = tuple(torch.cuda.Stream(device=images_trg.device) for _ in range(3))
         s_teacher, s_align, s_imnet = self._side_streams
         out = {}
-        s_teacher.wait_stream(main)
+        if not self._teacher_has_collectives():
+            s_teacher.wait_stream(main)
         s_align.wait_stream(main)
         with torch.no_grad(), self._autocast():
             if self.enable_fdist:   # frozen ImageNet copy of the backbone on the source images (feature distance)
@@ -332,19 +333,33 @@ class DomainAdaptationSegmentationModel(_Base):
             with torch.cuda.stream(s_align):
                 out['flow'], out['logvar'] = _alignment_flow(self.alignment_backbone, self.alignment_head, images_trg,
                                                              images_ref)
-            with torch.cuda.stream(s_teacher):
-                m_input = torch.cat((images_trg, images_ref))
-                m_logits = self.m_head(self.m_backbone(m_input))
-                out['m_logits'] = F.interpolate(m_logits.float(), size=m_input.shape[-2:], mode='bilinear',
-                                                align_corners=False)
+            if not self._teacher_has_collectives():
+                with torch.cuda.stream(s_teacher):
+                    out['m_logits'] = self._teacher_logits(images_trg, images_ref)
         return out
+
+    def _teacher_has_collectives(self):
+        """With world_size > 1 the teacher head's SyncBatchNorm issues NCCL all-reduces; collectives of one
+        communicator must be enqueued in the same order on every rank, which parallel graph branches do not
+        guarantee -- the teacher then stays on the main stream (the collective-free alignment / ImageNet
+        branches still run concurrently)."""
+        return self._rt is not None and self._rt.get('world_size', 1) > 1
+
+    def _teacher_logits(self, images_trg, images_ref):
+        m_input = torch.cat((images_trg, images_ref))
+        m_logits = self.m_head(self.m_backbone(m_input))
+        return F.interpolate(m_logits.float(), size=m_input.shape[-2:], mode='bilinear', align_corners=False)
 
     def _join_target_branches(self, side, batch):
         main = torch.cuda.current_stream()
-        for s in self._side_streams[:2]:
-            main.wait_stream(s)
         images_trg = batch['image_trg']
         b = images_trg.shape[0]
+        if 'm_logits' in side:
+            main.wait_stream(self._side_streams[0])
+        else:
+            with torch.no_grad(), self._autocast():
+                side['m_logits'] = self._teacher_logits(images_trg, batch['image_ref'])
+        main.wait_stream(self._side_streams[1])
         with torch.no_grad(), self._autocast():
             m_logits_trg, m_logits_ref = side['m_logits'][:b], side['m_logits'][b:]
             warped_ref, warp_mask = warp(m_logits_ref, side['flow'], return_mask=True)
