@@ -19,6 +19,8 @@
 #include <type_traits>
 
 #include "rf_common.cuh"
+#include <stdlib.h>
+
 #include "rf_sm100.cuh"
 
 namespace rf {
@@ -110,7 +112,6 @@ sr_attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
       }
     }
     lse2 = __ldg(lse + ((long)b * heads + head) * N + row) * 1.44269504088896341f;
-    dvec[((long)b * heads + head) * N + row] = Drow;
   }
 
   constexpr uint32_t IDESC_KK = make_idesc(FMT_BF16, 128, 64, 0, 0);  // both operands K-major
@@ -390,6 +391,57 @@ sr_attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
   if (warp == 0) tmem_dealloc<256>(tmem);
 }
 
+// D[b,h,n] = sum_d dO[b,n,h*64+d] * O[b,n,h*64+d] (same operation order as the dQ kernel's prologue), written
+// before the two backward kernels are forked onto separate streams (the dK/dV kernel reads it).
+__global__ void __launch_bounds__(256)
+sr_attention_dvec_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
+                         float* __restrict__ dvec, int N, int heads, long total) {
+  const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;   // (b, head, row)
+  if (idx >= total) return;
+  const int row = (int)(idx % N);
+  const long bh = idx / N;
+  const int head = (int)(bh % heads);
+  const long b = bh / heads;
+  const int C = heads * AB_D;
+  const uint4* po = reinterpret_cast<const uint4*>(o + (b * N + row) * C + head * AB_D);
+  const uint4* pg = reinterpret_cast<const uint4*>(dout + (b * N + row) * C + head * AB_D);
+  float d = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint4 a = __ldg(po + i), g = __ldg(pg + i);
+    const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* hg = reinterpret_cast<const __nv_bfloat162*>(&g);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 fa = __bfloat1622float2(ha[k]), fg = __bfloat1622float2(hg[k]);
+      d = fmaf(fa.x, fg.x, d);
+      d = fmaf(fa.y, fg.y, d);
+    }
+  }
+  dvec[idx] = d;
+}
+
+// Side stream + fork / join events per device: the dQ kernel (320 CTAs on 296 resident slots at the dominant
+// stage-3 shape = two rounds, the second nearly empty) and the dK/dV kernel (one wave by construction) are
+// independent once D is known, so they run concurrently and fill each other's tail.  cudaStreamWaitEvent
+// fork / join is legal inside a stream capture, so the CUDA-graph replay keeps the two branches parallel.
+struct BwdFork {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static BwdFork* bwd_fork() {
+  static BwdFork forks[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  BwdFork& f = forks[dev];
+  if (f.side == nullptr) {
+    if (cudaStreamCreateWithFlags(&f.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&f.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  }
+  return &f;
+}
+
 }  // namespace rf
 
 using namespace rf;
@@ -429,6 +481,21 @@ extern "C" int rf_sr_attention_bwd(const void* q, const void* kv, const void* ou
   }
   const float scale_log2 = scale * 1.44269504088896341f;
   {
+    const long total = (long)B * heads * N;
+    sr_attention_dvec_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        (const __nv_bfloat16*)out, (const __nv_bfloat16*)grad_out, dvec, N, heads, total);
+    RF_CHECK_LAUNCH("sr_attention_dvec_kernel");
+  }
+  RF_CUDA(cudaMemsetAsync(grad_kv_f32, 0, sizeof(float) * (size_t)B * M * 2 * C, st));
+  static const bool serial = [] { const char* e = getenv("RF_ATTN_BWD_SERIAL"); return e && e[0] == '1'; }();
+  BwdFork* fk = serial ? nullptr : bwd_fork();
+  cudaStream_t st_kv = st;
+  if (fk != nullptr) {   // fork: the dK/dV kernel goes to the side stream
+    RF_CUDA(cudaEventRecord(fk->fork, st));
+    RF_CUDA(cudaStreamWaitEvent(fk->side, fk->fork, 0));
+    st_kv = fk->side;
+  }
+  {
     dim3 grid((unsigned)((N + 127) / 128), (unsigned)heads, (unsigned)B);
     sr_attention_bwd_dq_kernel<<<grid, 128, AB_SMEM, st>>>(tq128, tdo128, tkv64, (const __nv_bfloat16*)out,
                                                             (const __nv_bfloat16*)grad_out, lse, dvec,
@@ -436,7 +503,6 @@ extern "C" int rf_sr_attention_bwd(const void* q, const void* kv, const void* ou
     RF_CHECK_LAUNCH("sr_attention_bwd_dq_kernel");
   }
   {
-    RF_CUDA(cudaMemsetAsync(grad_kv_f32, 0, sizeof(float) * (size_t)B * M * 2 * C, st));
     const int kvchunks = (M + 127) / 128;
     const int ntiles = (N + 63) / 64;
     // query splits so that ONE wave of CTAs (2 per SM) covers the work -- rounding up would leave a few
@@ -448,9 +514,13 @@ extern "C" int rf_sr_attention_bwd(const void* q, const void* kv, const void* ou
     const int tps = (ntiles + splits - 1) / splits;
     splits = (ntiles + tps - 1) / tps;
     dim3 grid((unsigned)splits, (unsigned)kvchunks, (unsigned)(B * heads));
-    sr_attention_bwd_dkv_kernel<<<grid, 128, AB_SMEM, st>>>(tq64, tdo64, tkv128, lse, dvec, grad_kv_f32, N, M, heads,
-                                                             tps, scale, scale_log2);
+    sr_attention_bwd_dkv_kernel<<<grid, 128, AB_SMEM, st_kv>>>(tq64, tdo64, tkv128, lse, dvec, grad_kv_f32, N, M, heads,
+                                                                tps, scale, scale_log2);
     RF_CHECK_LAUNCH("sr_attention_bwd_dkv_kernel");
+  }
+  if (fk != nullptr) {   // join
+    RF_CUDA(cudaEventRecord(fk->join, fk->side));
+    RF_CUDA(cudaStreamWaitEvent(st, fk->join, 0));
   }
   return RF_OK;
 }

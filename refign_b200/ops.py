@@ -54,7 +54,7 @@ def set_timer(timer):
 
 
 # kernels launched per C-ABI call (memsets not counted), for bench.py's gpu_launches figure
-KERNELS_PER_CALL = {"rf_refine_fwd": 3, "rf_sr_attention_bwd": 2, "rf_global_corr_fwd": 3}
+KERNELS_PER_CALL = {"rf_refine_fwd": 3, "rf_sr_attention_bwd": 3, "rf_global_corr_fwd": 3}
 _TLS = threading.local()
 
 
