@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--cpu-size", type=int, default=512, help="crop size of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-corr-sweep", action="store_true", help="skip the correlation-volume GB/s sweep (N=1 only)")
     ap.add_argument("--no-graphs", action="store_true", help="run the step eagerly instead of replaying CUDA graphs")
     return ap.parse_args()
 
@@ -135,6 +136,52 @@ def peaks():
         d = json.load(open(path))
         return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
     return 6650.0, 1590.0, "fallback"
+
+
+def corr_volume_sweep(dev, hbm):
+    """The second half of BASELINE.json's metric ("corr-vol GB/s"): the correlation-volume sweep of SURVEY 8d
+    on this GPU -- unit-norm features [B,128,H,H], local 9x9 volume (+ fused ReLU / L2-norm) and the global
+    N x N volume (+ mutual matching, ReLU, L2-norm).  CUDA events, L2 flushed between launches, median of 10;
+    GB/s = ALGORITHMIC bytes (inputs read once + volume written once) / time."""
+    import torch
+    from refign_b200 import ops
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def med(fn, iters=10):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    unit = lambda x: torch.nn.functional.normalize(x, p=2, dim=1)
+    g = torch.Generator(device=dev).manual_seed(7)
+    out = []
+    for (B, H) in [(2, 64), (2, 128), (2, 256)]:
+        a = unit(torch.randn(B, 128, H, H, device=dev, generator=g))
+        b = unit(torch.randn(B, 128, H, H, device=dev, generator=g))
+        sec = med(lambda: ops.local_correlation_relu_l2norm(b, a, 9))
+        nbytes = 4 * B * H * H * (2 * 128 + 81)
+        out.append({"op": "local_9x9+relu+l2norm", "shape": [B, 128, H, H], "us": round(sec * 1e6, 1),
+                    "GBps": round(nbytes / sec / 1e9, 1), "frac_hbm": round(nbytes / sec / 1e9 / hbm, 4)})
+    for (B, H) in [(1, 64), (1, 128)]:
+        a = unit(torch.randn(B, 128, H, H, device=dev, generator=g))
+        b = unit(torch.randn(B, 128, H, H, device=dev, generator=g))
+        n = H * H
+        sec = med(lambda: ops.global_correlation(a, b), iters=5)
+        nbytes = 4 * B * (128 * 2 * n + n * n)
+        out.append({"op": "global+mutual_matching+relu+l2norm", "shape": [B, 128, H, H], "volume_GB": round(4 * B * n * n / 1e9, 3),
+                    "us": round(sec * 1e6, 1), "GBps": round(nbytes / sec / 1e9, 1),
+                    "frac_hbm": round(nbytes / sec / 1e9 / hbm, 4)})
+    return out
 
 
 def cpu_reference_step(size, model_type, steps, warmup):
@@ -309,6 +356,11 @@ def main():
                "GBps": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 and v["bytes"] else None,
                "TFLOPs": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 and v["flops"] else None}
            for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])}
+    corr = None
+    if world == 1 and not args.no_corr_sweep:
+        del model
+        torch.cuda.empty_cache()
+        corr = corr_volume_sweep(dev, hbm)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         sec, cores = cpu_reference_step(args.cpu_size, args.model, 1, 1)
@@ -327,7 +379,7 @@ def main():
                        "precision_note": "bf16 autocast for library GEMMs/convs; correlation, warp, refine fp32",
                        "cuda_graphs": not args.no_graphs},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
-            "own_kernels": own, "loss_src": loss}
+            "corr_volume": corr, "own_kernels": own, "loss_src": loss}
     print(json.dumps(line), flush=True)
     finish()
 

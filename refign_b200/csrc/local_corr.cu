@@ -349,6 +349,173 @@ __global__ void local_corr_bwd_kernel(const float* __restrict__ other, const flo
   }
 }
 
+// ----------------------------------------------------------------------------
+// tiled backward (kernel 1, stride 1, pad 0, dilation_patch 1, odd P <= 9, W % 4 == 0)
+// ----------------------------------------------------------------------------
+// Both gradients are the same contraction
+//     gin[n,c,y,x] = sum_{ph,pw} G[n,ph,pw,y,x] * S[n,c,y+ph-R,x+pw-R]            (S = 0 outside the image)
+// grad_in1: G = grad_out,  S = in2.
+// grad_in2: gin2[c,q] = sum_d gout[d, q-d] in1[c, q-d]; substituting d' = -d gives the same form with
+//           G'[d'][q] = gout[-d'][q + d'] (zero outside) and S = in1 -- G' is built by local_corr_flip_shift_kernel
+//           into the caller's scratch buffer (one streaming pass over the volume).
+// CTA = 16 x 32 pixel tile, 128 threads (thread = 4 consecutive pixels of one row, all LC_CK channels of the
+// current chunk in registers); the S halo tile streams through the same 3-stage cp.async pipeline as the forward;
+// the thread's G values of one displacement row are read straight from L2 (coalesced 128-byte rows) and
+// prefetched one displacement row ahead.
+constexpr int LB_TH = 16;
+
+template <int P>
+struct LbCfg {
+  static constexpr int R = (P - 1) / 2;
+  static constexpr int THREADS = LB_TH * (LC_TW / 4);   // 128
+  static constexpr int HROWS = LB_TH + P - 1;
+  static constexpr int STAGE_FLOATS = LC_CK * HROWS * LC_HW;
+  static constexpr int SMEM_BYTES = LC_STAGES * STAGE_FLOATS * 4;
+};
+
+template <int P>
+__device__ __forceinline__ void lb_issue_stage(float* stage, const float* __restrict__ src, int c0, int C, int H,
+                                               int W, int y0, int x0) {
+  using Cfg = LbCfg<P>;
+  const long plane = (long)H * W;
+  constexpr int N2 = LC_CK * Cfg::HROWS * (LC_HW / 4);
+  for (int i = threadIdx.x; i < N2; i += Cfg::THREADS) {
+    const int q = i % (LC_HW / 4);
+    const int r = (i / (LC_HW / 4)) % Cfg::HROWS;
+    const int c = i / (LC_HW / 4 * Cfg::HROWS);
+    const int y = y0 - Cfg::R + r, x = x0 - LC_R4 + 4 * q, cc = c0 + c;
+    const bool ok = (cc < C) && (y >= 0) && (y < H) && (x >= 0) && (x < W);
+    const float* g = ok ? src + (long)cc * plane + (long)y * W + x : src;
+    cp_async16(stage + (c * Cfg::HROWS + r) * LC_HW + 4 * q, g, ok ? 16 : 0);
+  }
+}
+
+template <int P>
+__global__ void __launch_bounds__(LbCfg<P>::THREADS, 3)
+local_corr_bwd_tiled_kernel(const float* __restrict__ G, const float* __restrict__ S, float* __restrict__ gin, int C,
+                            int H, int W) {
+  using Cfg = LbCfg<P>;
+  extern __shared__ __align__(16) float smem[];
+  const int n = blockIdx.z;
+  const int y0 = blockIdx.y * LB_TH, x0 = blockIdx.x * LC_TW;
+  const long plane = (long)H * W;
+  S += (long)n * C * plane;
+  gin += (long)n * C * plane;
+  G += (long)n * P * P * plane;
+  const int sx = threadIdx.x & 7, r = threadIdx.x >> 3;
+  const int y = y0 + r, x = x0 + 4 * sx;
+  const bool live = y < H && x < W;
+  const float4* gp = reinterpret_cast<const float4*>(G + (long)(live ? y : 0) * W + (live ? x : 0));
+  const long gstride = plane / 4;   // float4 stride between displacement planes (W % 4 == 0)
+  constexpr int OFF = LC_R4 - Cfg::R;
+
+  const int nchunks = (C + LC_CK - 1) / LC_CK;
+#pragma unroll
+  for (int s = 0; s < LC_STAGES - 1; ++s) {
+    if (s < nchunks) lb_issue_stage<P>(smem + s * Cfg::STAGE_FLOATS, S, s * LC_CK, C, H, W, y0, x0);
+    cp_async_commit();
+  }
+  for (int k = 0; k < nchunks; ++k) {
+    cp_async_wait<LC_STAGES - 2>();
+    __syncthreads();
+    {
+      const int kn = k + LC_STAGES - 1;
+      if (kn < nchunks) lb_issue_stage<P>(smem + (kn % LC_STAGES) * Cfg::STAGE_FLOATS, S, kn * LC_CK, C, H, W, y0, x0);
+      cp_async_commit();
+    }
+    const float* st = smem + (k % LC_STAGES) * Cfg::STAGE_FLOATS;
+    float acc[LC_CK][4];
+#pragma unroll
+    for (int c = 0; c < LC_CK; ++c)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[c][i] = 0.f;
+    float4 gcur[P], gnext[P];
+#pragma unroll
+    for (int pw = 0; pw < P; ++pw) gcur[pw] = live ? __ldg(gp + (long)pw * gstride) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+    for (int ph = 0; ph < P; ++ph) {
+      if (ph + 1 < P) {
+#pragma unroll
+        for (int pw = 0; pw < P; ++pw)
+          gnext[pw] = live ? __ldg(gp + (long)((ph + 1) * P + pw) * gstride) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int c = 0; c < LC_CK; ++c) {
+        const float4* brow = reinterpret_cast<const float4*>(st + (c * Cfg::HROWS + r + ph) * LC_HW + 4 * sx);
+        const float4 b0 = brow[0], b1 = brow[1], b2 = brow[2];
+        const float bb[12] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w};
+#pragma unroll
+        for (int pw = 0; pw < P; ++pw) {
+          acc[c][0] = fmaf(gcur[pw].x, bb[0 + pw + OFF], acc[c][0]);
+          acc[c][1] = fmaf(gcur[pw].y, bb[1 + pw + OFF], acc[c][1]);
+          acc[c][2] = fmaf(gcur[pw].z, bb[2 + pw + OFF], acc[c][2]);
+          acc[c][3] = fmaf(gcur[pw].w, bb[3 + pw + OFF], acc[c][3]);
+        }
+      }
+#pragma unroll
+      for (int pw = 0; pw < P; ++pw) gcur[pw] = gnext[pw];
+    }
+    if (live) {
+#pragma unroll
+      for (int c = 0; c < LC_CK; ++c) {
+        const int cc = k * LC_CK + c;
+        if (cc < C)
+          *reinterpret_cast<float4*>(gin + (long)cc * plane + (long)y * W + x) =
+              make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+      }
+    }
+  }
+  cp_async_wait<0>();
+}
+
+// G'[n, ph', pw', y, x] = gout[n, P-1-ph', P-1-pw', y + ph' - R, x + pw' - R]  (0 outside the image)
+__global__ void local_corr_flip_shift_kernel(const float* __restrict__ gout, float* __restrict__ gflip, int P, int H,
+                                             int W, long total) {
+  const int R = (P - 1) / 2;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % W);
+    long t = idx / W;
+    const int y = (int)(t % H);
+    t /= H;
+    const int pw = (int)(t % P);
+    t /= P;
+    const int ph = (int)(t % P);
+    const long n = t / P;
+    const int ys = y + ph - R, xs = x + pw - R;
+    float v = 0.f;
+    if (ys >= 0 && ys < H && xs >= 0 && xs < W)
+      v = __ldg(gout + ((n * P + (P - 1 - ph)) * P + (P - 1 - pw)) * (long)H * W + (long)ys * W + xs);
+    gflip[idx] = v;
+  }
+}
+
+template <int P>
+static int launch_bwd_tiled(const float* G, const float* S, float* gin, int B, int C, int H, int W, cudaStream_t st) {
+  using Cfg = LbCfg<P>;
+  dim3 grid((W + LC_TW - 1) / LC_TW, (H + LB_TH - 1) / LB_TH, B);
+  RF_CUDA(cudaFuncSetAttribute(local_corr_bwd_tiled_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  local_corr_bwd_tiled_kernel<P><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(G, S, gin, C, H, W);
+  RF_CHECK_LAUNCH("local_corr_bwd_tiled_kernel");
+  return RF_OK;
+}
+
+static int bwd_tiled_dispatch(int P, const float* G, const float* S, float* gin, int B, int C, int H, int W,
+                              cudaStream_t st) {
+  switch (P) {
+    case 3: return launch_bwd_tiled<3>(G, S, gin, B, C, H, W, st);
+    case 5: return launch_bwd_tiled<5>(G, S, gin, B, C, H, W, st);
+    case 7: return launch_bwd_tiled<7>(G, S, gin, B, C, H, W, st);
+    default: return launch_bwd_tiled<9>(G, S, gin, B, C, H, W, st);
+  }
+}
+
+static bool bwd_tiled_ok(int H, int W, int kH, int kW, int pH, int pW, int padH, int padW, int dpH, int dpW, int sH,
+                         int sW) {
+  (void)H;
+  return kH == 1 && kW == 1 && sH == 1 && sW == 1 && padH == 0 && padW == 0 && dpH == 1 && dpW == 1 && pH == pW &&
+         (pH == 3 || pH == 5 || pH == 7 || pH == 9) && W % 4 == 0;
+}
+
 // backward of y = relu(c)/max(||relu(c)||,eps):  dc = relu'(c) * (gy - y * sum_k(gy*y)) / norm
 __global__ void relu_l2norm_bwd_kernel(const float* __restrict__ y, const float* __restrict__ norm,
                                        const float* __restrict__ gy, float* __restrict__ gc, int K, long HW,
@@ -420,22 +587,38 @@ extern "C" int rf_local_corr_fwd(const float* in1, const float* in2, float* out,
   return RF_OK;
 }
 
-extern "C" int64_t rf_local_corr_bwd_scratch_bytes(int, int, int, int, int, int, int, int, int, int, int, int, int, int,
-                                                   int, int) {
-  return 0;  // the gather formulation needs no scratch
+extern "C" int64_t rf_local_corr_bwd_scratch_bytes(int B, int C, int H, int W, int kH, int kW, int pH, int pW, int padH,
+                                                   int padW, int dilH, int dilW, int dpH, int dpW, int sH, int sW) {
+  (void)C; (void)dilH; (void)dilW;
+  // tiled path: the flipped / shifted copy of grad_out used for grad_in2; the generic gather path needs none
+  if (bwd_tiled_ok(H, W, kH, kW, pH, pW, padH, padW, dpH, dpW, sH, sW))
+    return (int64_t)sizeof(float) * B * pH * pW * H * W;
+  return 0;
 }
 
 extern "C" int rf_local_corr_bwd(const float* in1, const float* in2, const float* grad_out, float* grad_in1,
                                  float* grad_in2, void* scratch, int B, int C, int H, int W, int kH, int kW, int pH,
                                  int pW, int padH, int padW, int dilH, int dilW, int dpH, int dpW, int sH, int sW,
                                  void* stream) {
-  (void)scratch;
   RF_REQUIRE(in1 && in2 && grad_out, "rf_local_corr_bwd: null pointer");
   RF_REQUIRE(grad_in1 || grad_in2, "rf_local_corr_bwd: no gradient requested");
   RF_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "rf_local_corr_bwd: empty tensor");
   LcGeom g = make_geom(B, C, H, W, kH, kW, pH, pW, padH, padW, dilH, dilW, dpH, dpW, sH, sW);
   RF_REQUIRE(g.oH > 0 && g.oW > 0, "rf_local_corr_bwd: empty output");
   cudaStream_t st = (cudaStream_t)stream;
+  const bool al = (((uintptr_t)in1 | (uintptr_t)in2 | (uintptr_t)grad_out | (uintptr_t)grad_in1 | (uintptr_t)grad_in2 |
+                    (uintptr_t)scratch) % 16) == 0;
+  if (al && bwd_tiled_ok(H, W, kH, kW, pH, pW, padH, padW, dpH, dpW, sH, sW) && (grad_in2 == nullptr || scratch != nullptr)) {
+    int rc = RF_OK;
+    if (grad_in1) rc = bwd_tiled_dispatch(pH, grad_out, in2, grad_in1, B, C, H, W, st);
+    if (rc == RF_OK && grad_in2) {
+      const long vol = (long)B * pH * pW * H * W;
+      local_corr_flip_shift_kernel<<<grid_for(vol, 256), 256, 0, st>>>(grad_out, (float*)scratch, pH, H, W, vol);
+      RF_CHECK_LAUNCH("local_corr_flip_shift_kernel");
+      rc = bwd_tiled_dispatch(pH, (const float*)scratch, in1, grad_in2, B, C, H, W, st);
+    }
+    return rc;
+  }
   const long total = (long)B * C * H * W;
   if (grad_in1) {
     local_corr_bwd_kernel<false><<<grid_for(total, 256), 256, 0, st>>>(in2, grad_out, grad_in1, g);

@@ -103,6 +103,12 @@ def _check_pair(input1, input2):
         raise RuntimeError("inputs must live on the same device")
 
 
+def _corr_bwd_scratch(geo, device):
+    """Scratch of rf_local_corr_bwd (the flipped / shifted grad_out copy of the tiled grad_in2 path), or None."""
+    n = int(_lib.lib().rf_local_corr_bwd_scratch_bytes(*geo))
+    return torch.empty(n // 4, device=device, dtype=torch.float32) if n > 0 else None
+
+
 class SpatialCorrelationSamplerFunction(torch.autograd.Function):
     """Same contract as the reference's autograd function
     (correlation_function.py:46-94): fp32 even under autocast, output
@@ -138,10 +144,11 @@ class SpatialCorrelationSamplerFunction(torch.autograd.Function):
         g = _f32c(grad_output)
         ga = torch.empty_like(a) if ctx.needs_input_grad[0] else None
         gb = torch.empty_like(b) if ctx.needs_input_grad[1] else None
+        geo = (B, C, H, W, k[0], k[1], p[0], p[1], pad[0], pad[1], dil[0], dil[1], dp[0], dp[1], s[0], s[1])
+        scratch = _corr_bwd_scratch(geo, a.device) if gb is not None else None
         with torch.cuda.device(a.device):
-            _run("rf_local_corr_bwd", ptr(a), ptr(b), ptr(g), ptr(ga), ptr(gb), None, B, C, H, W, k[0],
-                                               k[1], p[0], p[1], pad[0], pad[1], dil[0], dil[1], dp[0],
-                                               dp[1], s[0], s[1], _stream())
+            _run("rf_local_corr_bwd", ptr(a), ptr(b), ptr(g), ptr(ga), ptr(gb), ptr(scratch), *geo, _stream(),
+                 work=(4 * B * H * W * (4 * C + p[0] * p[1]), 4 * B * H * W * p[0] * p[1] * C), tag="local_corr_bwd")
         if ga is not None:
             ga = ga.to(ctx.in_dtypes[0])
         if gb is not None:
@@ -192,8 +199,10 @@ class _LocalCorrReluL2Norm(torch.autograd.Function):
             _run("rf_relu_l2norm_bwd", ptr(y), ptr(norm), ptr(gy), ptr(gc), B, P * P, H * W, _stream())
             gt = torch.empty_like(t) if ctx.needs_input_grad[1] else None
             gs = torch.empty_like(s) if ctx.needs_input_grad[0] else None
-            _run("rf_local_corr_bwd", ptr(t), ptr(s), ptr(gc), ptr(gt), ptr(gs), None, B, C, H, W, 1, 1, P, P, 0,
-                                      0, 1, 1, 1, 1, 1, 1, _stream())
+            geo = (B, C, H, W, 1, 1, P, P, 0, 0, 1, 1, 1, 1, 1, 1)
+            scratch = _corr_bwd_scratch(geo, t.device) if gs is not None else None
+            _run("rf_local_corr_bwd", ptr(t), ptr(s), ptr(gc), ptr(gt), ptr(gs), ptr(scratch), *geo, _stream(),
+                 work=(4 * B * H * W * (4 * C + P * P), 4 * B * H * W * P * P * C), tag="local_corr_bwd")
         return gs, gt, None
 
 

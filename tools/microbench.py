@@ -82,12 +82,12 @@ def main():
             flops = 2 * B * H * H * P * P * C
             report("local_corr_fwd+relu_l2norm", [B, C, H, H, P], time_op(lambda: ops.local_correlation_relu_l2norm(b, a, P), args.iters), nbytes, flops)
             report("local_corr_fwd", [B, C, H, H, P], time_op(lambda: ops.spatial_correlation_sample(a, b, patch_size=P), args.iters), nbytes, flops)
-        B, C, H, P = 2, 128, 128, 9
-        a, b = unit(torch.randn(B, C, H, H, device=dev)).requires_grad_(True), unit(torch.randn(B, C, H, H, device=dev)).requires_grad_(True)
-        out = ops.spatial_correlation_sample(a, b, patch_size=P)
-        g = torch.randn_like(out)
-        report("local_corr_bwd", [B, C, H, H, P], time_op(lambda: torch.autograd.grad(out, (a, b), g, retain_graph=True), max(5, args.iters // 3)),
-               4 * B * H * H * (4 * C + P * P), 4 * B * H * H * P * P * C)
+        for (B, C, H, P) in [(2, 128, 128, 9), (2, 128, 256, 9), (2, 256, 64, 9)]:
+            a, b = unit(torch.randn(B, C, H, H, device=dev)).requires_grad_(True), unit(torch.randn(B, C, H, H, device=dev)).requires_grad_(True)
+            out = ops.spatial_correlation_sample(a, b, patch_size=P)
+            g = torch.randn_like(out)
+            report("local_corr_bwd(both grads)", [B, C, H, H, P], time_op(lambda: torch.autograd.grad(out, (a, b), g, retain_graph=True), max(5, args.iters // 3)),
+                   4 * B * H * H * (4 * C + P * P), 4 * B * H * H * P * P * C)
     if want("global_corr"):
         for (B, C, N) in [(2, 512, 16), (1, 128, 64), (1, 128, 128)]:
             s, t = unit(torch.randn(B, C, N, N, device=dev)), unit(torch.randn(B, C, N, N, device=dev))
