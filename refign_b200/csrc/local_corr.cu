@@ -393,10 +393,12 @@ __device__ __forceinline__ void lb_issue_stage(float* stage, const float* __rest
 template <int P>
 __global__ void __launch_bounds__(LbCfg<P>::THREADS, 3)
 local_corr_bwd_tiled_kernel(const float* __restrict__ G, const float* __restrict__ S, float* __restrict__ gin, int C,
-                            int H, int W) {
+                            int H, int W, int nsplit) {
   using Cfg = LbCfg<P>;
   extern __shared__ __align__(16) float smem[];
-  const int n = blockIdx.z;
+  // blockIdx.z = image * nsplit + channel split: every output channel is independent, so small maps fill the
+  // machine by giving each CTA a range of channel chunks
+  const int n = blockIdx.z / nsplit, split = blockIdx.z % nsplit;
   const int y0 = blockIdx.y * LB_TH, x0 = blockIdx.x * LC_TW;
   const long plane = (long)H * W;
   S += (long)n * C * plane;
@@ -409,21 +411,26 @@ local_corr_bwd_tiled_kernel(const float* __restrict__ G, const float* __restrict
   const long gstride = plane / 4;   // float4 stride between displacement planes (W % 4 == 0)
   constexpr int OFF = LC_R4 - Cfg::R;
 
-  const int nchunks = (C + LC_CK - 1) / LC_CK;
+  const int allchunks = (C + LC_CK - 1) / LC_CK;
+  const int per = (allchunks + nsplit - 1) / nsplit;
+  const int kbeg = split * per;
+  const int nchunks = min(per, allchunks - kbeg);   // chunks of this CTA (may be <= 0 for the last split)
 #pragma unroll
   for (int s = 0; s < LC_STAGES - 1; ++s) {
-    if (s < nchunks) lb_issue_stage<P>(smem + s * Cfg::STAGE_FLOATS, S, s * LC_CK, C, H, W, y0, x0);
+    if (s < nchunks) lb_issue_stage<P>(smem + s * Cfg::STAGE_FLOATS, S, (kbeg + s) * LC_CK, C, H, W, y0, x0);
     cp_async_commit();
   }
-  for (int k = 0; k < nchunks; ++k) {
+  for (int kk = 0; kk < nchunks; ++kk) {
+    const int k = kbeg + kk;
     cp_async_wait<LC_STAGES - 2>();
     __syncthreads();
     {
-      const int kn = k + LC_STAGES - 1;
-      if (kn < nchunks) lb_issue_stage<P>(smem + (kn % LC_STAGES) * Cfg::STAGE_FLOATS, S, kn * LC_CK, C, H, W, y0, x0);
+      const int kn = kk + LC_STAGES - 1;
+      if (kn < nchunks)
+        lb_issue_stage<P>(smem + (kn % LC_STAGES) * Cfg::STAGE_FLOATS, S, (kbeg + kn) * LC_CK, C, H, W, y0, x0);
       cp_async_commit();
     }
-    const float* st = smem + (k % LC_STAGES) * Cfg::STAGE_FLOATS;
+    const float* st = smem + (kk % LC_STAGES) * Cfg::STAGE_FLOATS;
     float acc[LC_CK][4];
 #pragma unroll
     for (int c = 0; c < LC_CK; ++c)
@@ -492,9 +499,15 @@ __global__ void local_corr_flip_shift_kernel(const float* __restrict__ gout, flo
 template <int P>
 static int launch_bwd_tiled(const float* G, const float* S, float* gin, int B, int C, int H, int W, cudaStream_t st) {
   using Cfg = LbCfg<P>;
-  dim3 grid((W + LC_TW - 1) / LC_TW, (H + LB_TH - 1) / LB_TH, B);
+  const long tiles = (long)((W + LC_TW - 1) / LC_TW) * ((H + LB_TH - 1) / LB_TH) * B;
+  const int allchunks = (C + LC_CK - 1) / LC_CK;
+  long nsplit = ((long)kNumSMs * 2 + tiles - 1) / tiles;     // >= 2 CTAs per SM when the channel count allows
+  if (nsplit > allchunks) nsplit = allchunks;
+  if (nsplit < 1) nsplit = 1;
+  RF_REQUIRE((long)B * nsplit <= 65535, "rf_local_corr_bwd: batch too large");
+  dim3 grid((W + LC_TW - 1) / LC_TW, (H + LB_TH - 1) / LB_TH, (unsigned)(B * nsplit));
   RF_CUDA(cudaFuncSetAttribute(local_corr_bwd_tiled_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-  local_corr_bwd_tiled_kernel<P><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(G, S, gin, C, H, W);
+  local_corr_bwd_tiled_kernel<P><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(G, S, gin, C, H, W, (int)nsplit);
   RF_CHECK_LAUNCH("local_corr_bwd_tiled_kernel");
   return RF_OK;
 }
