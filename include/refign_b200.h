@@ -318,6 +318,23 @@ int rf_upsample_concat_fwd(const void* const* src, const int* h, const int* w, c
  * pixel, no atomics); grad_src[i] may be NULL to skip a source. */
 int rf_upsample_concat_bwd(const void* grad_y, void* const* grad_src, const int* h, const int* w,
                            const int* E, int n, int B, int H, int W, void* stream);
+/* ---- loss tail of the student forwards ----------------------------------------------------------- */
+/* loss_sum[0] = sum over the B*H*W label pixels of  w_i * (logsumexp_k z_ik - z_i,target_i),  z = the bilinear
+ * up-sampling (align_corners = False) of the low-resolution logits [B, K, h, w] (f32, NCHW) to (H, W); pixels
+ * whose label is ignore_index (or outside [0, K)) contribute 0; pixel_weight [B, H, W] may be NULL (= 1).
+ * Restates F.interpolate + PixelWeightedCrossEntropyLoss of the train step (models/segmentation_model.py:160-170,
+ * 228-240; models/losses.py:10-22) without materialising the [B, K, H, W] tensor; the caller divides by B*H*W
+ * (the reference's mean runs over ALL pixels).  target is int64 [B, H, W]; 2 <= K <= 32, H >= h, W >= w. */
+int rf_upsample_ce_fwd(const float* logits, const int64_t* target, const float* pixel_weight, float* loss_sum,
+                       int B, int K, int h, int w, int H, int W, int ignore_index, void* stream);
+/* grad_logits [B, K, h, w] = grad_loss[0] / (B*H*W) * d loss_sum / d logits (gather, no atomics; the
+ * full-resolution softmax is recomputed).  grad_loss is a DEVICE scalar. */
+int rf_upsample_ce_bwd(const float* logits, const int64_t* target, const float* pixel_weight,
+                       const float* grad_loss, float* grad_logits, int B, int K, int h, int w, int H, int W,
+                       int ignore_index, void* stream);
+/* out [planes, H, W] = bilinear(in [planes, h, w]), align_corners = False, f32 (the teacher logits:
+ * models/segmentation_model.py:206-208); W % 4 == 0, out 16-byte aligned. */
+int rf_upsample_bilinear_f32(const float* in, float* out, int64_t planes, int h, int w, int H, int W, void* stream);
 /* fp32 -> bf16 copy of a flat parameter buffer (the bf16 shadow weights read by the tensor-core
  * GEMMs; replaces the per-tensor autocast casts of the reference's AMP path). */
 int rf_cast_bf16(const float* src, void* dst, int64_t n, void* stream);

@@ -51,6 +51,9 @@ _SIGNATURES = {
     "rf_cast_bf16": (c_int, [c_p, c_p, c_i64, c_p]),
     "rf_upsample_concat_fwd": (c_int, [c_p, c_p, c_p, c_p, c_int, c_p, c_int, c_int, c_int, c_p]),
     "rf_upsample_concat_bwd": (c_int, [c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p]),
+    "rf_upsample_ce_fwd": (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
+    "rf_upsample_ce_bwd": (c_int, [c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
+    "rf_upsample_bilinear_f32": (c_int, [c_p, c_p, c_i64, c_int, c_int, c_int, c_int, c_p]),
     "rf_bias_act": (c_int, [c_p, c_p, c_i64, c_int, c_i64, c_int, c_f32, c_int, c_p]),
     "rf_space_to_depth": (c_int, [c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
     "rf_ema_update_dev": (c_int, [c_p, c_p, c_i64, c_p, c_p]),

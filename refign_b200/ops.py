@@ -740,6 +740,73 @@ def upsample_concat(feats, sizes, out_size):
     return _UpsampleConcat.apply(int(out_size[0]), int(out_size[1]), tuple((int(h), int(w)) for h, w in sizes), *feats)
 
 
+# --------------------------------------------------------------------------
+# loss tail: bilinear up-sampling fused with the pixel-weighted cross-entropy
+# (reference: models/segmentation_model.py:160-170,228-240 + models/losses.py:10-22)
+# --------------------------------------------------------------------------
+class _UpsampleCrossEntropy(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target, pixel_weight, ignore_index):
+        lg = _f32c(logits)
+        B, K, h, w = lg.shape
+        tg = target.contiguous()
+        if tg.dtype != torch.int64:
+            tg = tg.long()
+        H, W = tg.shape[-2:]
+        pw = None if pixel_weight is None else _f32c(pixel_weight)
+        loss = torch.empty(1, device=lg.device, dtype=torch.float32)
+        with torch.cuda.device(lg.device):
+            _run("rf_upsample_ce_fwd", ptr(lg), ptr(tg), ptr(pw), ptr(loss), B, K, h, w, H, W, int(ignore_index),
+                 _stream(), work=(4 * lg.numel() + B * H * W * (8 + (4 if pw is not None else 0)), 12 * B * H * W * K),
+                 tag="upsample_ce_fwd")
+        ctx.save_for_backward(lg, tg, pw if pw is not None else lg.new_empty(0))
+        ctx.meta = (B, K, h, w, H, W, int(ignore_index), pw is not None, logits.dtype)
+        return (loss / float(B * H * W)).reshape(())
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gl):
+        lg, tg, pw = ctx.saved_tensors
+        B, K, h, w, H, W, ignore_index, has_pw, in_dtype = ctx.meta
+        g = _f32c(gl).reshape(1)
+        grad = torch.empty_like(lg)
+        with torch.cuda.device(lg.device):
+            _run("rf_upsample_ce_bwd", ptr(lg), ptr(tg), ptr(pw) if has_pw else None, ptr(g), ptr(grad), B, K, h, w,
+                 H, W, ignore_index, _stream(),
+                 work=(8 * lg.numel() + B * H * W * (8 + (4 if has_pw else 0)), 4 * 24 * B * H * W * K),
+                 tag="upsample_ce_bwd")
+        return grad.to(in_dtype), None, None, None
+
+
+def upsample_cross_entropy(logits, target, pixel_weight=None, ignore_index=255):
+    """``PixelWeightedCrossEntropyLoss(ignore_index)(F.interpolate(logits.float(), target.shape[-2:],
+    mode='bilinear', align_corners=False), target, pixel_weight)`` -- the mean over ALL label pixels of
+    ``w * CE`` (0 at ignored pixels) -- without materialising the up-sampled [B, K, H, W] logits."""
+    require_cuda(logits, target)
+    if logits.dim() != 4 or target.dim() != 3 or target.shape[0] != logits.shape[0]:
+        raise RuntimeError("upsample_cross_entropy: logits [B,K,h,w] and target [B,H,W] expected, got %s / %s"
+                           % (tuple(logits.shape), tuple(target.shape)))
+    if pixel_weight is not None and tuple(pixel_weight.shape) != tuple(target.shape):
+        raise RuntimeError("upsample_cross_entropy: pixel_weight must have the target's shape")
+    return _UpsampleCrossEntropy.apply(logits, target, pixel_weight, ignore_index)
+
+
+def upsample_bilinear(x, size):
+    """``F.interpolate(x.float(), size, mode='bilinear', align_corners=False)`` for a no-grad fp32 NCHW tensor
+    (the teacher logits), 16-byte stores."""
+    require_cuda(x)
+    if x.requires_grad and torch.is_grad_enabled():
+        raise NotImplementedError("upsample_bilinear is the no-grad (teacher) path")
+    xf = _f32c(x)
+    B, C, h, w = xf.shape
+    H, W = int(size[0]), int(size[1])
+    out = torch.empty(B, C, H, W, device=xf.device, dtype=torch.float32)
+    with torch.cuda.device(xf.device):
+        _run("rf_upsample_bilinear_f32", ptr(xf), ptr(out), B * C, h, w, H, W, _stream(),
+             work=(4 * (xf.numel() + out.numel()), 8 * out.numel()))
+    return out
+
+
 def space_to_depth(x, H, W, s, inverse=False):
     """[B, H*W, C] tokens -> [B*(H/s)*(W/s), s*s*C] packed patches (or back with ``inverse``): one
     16-byte-vector copy kernel instead of a generic strided permute copy."""

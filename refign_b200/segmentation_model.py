@@ -132,6 +132,7 @@ class DomainAdaptationSegmentationModel(_Base):
         self._graphs = None                   # CUDA-graph state installed by enable_cuda_graphs()
         self.fuse_source_backward = True      # one backward for loss_src + feature distance (see _step_part_a)
         self.concurrent_branches = True       # teacher / alignment branches on side streams (see _fork_target_branches)
+        self.fused_loss = True                # bilinear up-sampling fused into the cross-entropy (ops.upsample_cross_entropy)
         self._side_streams = None
         self.load_weights(pretrained)
 
@@ -243,9 +244,7 @@ class DomainAdaptationSegmentationModel(_Base):
         with self._autocast():
             feats_src = self.backbone(images_src)
             logits_src = self.head(feats_src)
-            logits_src = F.interpolate(logits_src.float(), images_src.shape[-2:], mode='bilinear',
-                                       align_corners=False)
-            loss_src = self.loss(logits_src, gt_src)
+            loss_src = self._upsampled_loss(logits_src, gt_src, images_src.shape[-2:])
         self.log("train_loss_src", loss_src)
         if self.enable_fdist and self.fuse_source_backward:
             # The reference runs two backward passes here (loss_src with retain_graph, then the feature
@@ -292,8 +291,7 @@ class DomainAdaptationSegmentationModel(_Base):
                 b = images_trg.shape[0]
                 m_input = torch.cat((images_trg, images_ref))
                 m_logits = self.m_head(self.m_backbone(m_input))
-                m_logits = F.interpolate(m_logits.float(), size=m_input.shape[-2:], mode='bilinear',
-                                         align_corners=False)
+                m_logits = self._upsample_logits(m_logits, m_input.shape[-2:])
                 m_logits_trg, m_logits_ref = m_logits[:b], m_logits[b:]
                 if self.use_align:
                     warped_ref, warp_mask, logvar = self.align(m_logits_ref, images_ref, images_trg,
@@ -303,8 +301,7 @@ class DomainAdaptationSegmentationModel(_Base):
                     m_probs_trg = self.refine(m_logits_trg, m_logits_ref, None, None)
             else:
                 m_logits_trg = self.m_head(self.m_backbone(images_trg))
-                m_logits_trg = F.interpolate(m_logits_trg.float(), size=images_trg.shape[-2:], mode='bilinear',
-                                             align_corners=False)
+                m_logits_trg = self._upsample_logits(m_logits_trg, images_trg.shape[-2:])
                 m_probs_trg = F.softmax(m_logits_trg, dim=1)
         fused, self._fused_pseudo = self._fused_pseudo, None
         return {'images_trg': images_trg, 'probs': m_probs_trg, 'fused': fused}
@@ -348,7 +345,27 @@ class DomainAdaptationSegmentationModel(_Base):
     def _teacher_logits(self, images_trg, images_ref):
         m_input = torch.cat((images_trg, images_ref))
         m_logits = self.m_head(self.m_backbone(m_input))
-        return F.interpolate(m_logits.float(), size=m_input.shape[-2:], mode='bilinear', align_corners=False)
+        return self._upsample_logits(m_logits, m_input.shape[-2:])
+
+    def _upsample_logits(self, logits, size):
+        """F.interpolate(logits.float(), size, 'bilinear', align_corners=False) of no-grad (teacher) logits."""
+        if self.fused_loss and logits.is_cuda and not logits.requires_grad and size[-1] % 4 == 0 \
+                and size[0] >= logits.shape[-2] and size[1] >= logits.shape[-1]:
+            return ops.upsample_bilinear(logits, size)
+        return F.interpolate(logits.float(), size=size, mode='bilinear', align_corners=False)
+
+    def _upsampled_loss(self, logits, target, size, pixel_weight=None):
+        """loss(F.interpolate(logits.float(), size, 'bilinear', align_corners=False), target[, pixel_weight])
+        (reference segmentation_model.py:160-170, 228-240).  On the GPU, with this package's
+        PixelWeightedCrossEntropyLoss, the up-sampled [B,K,H,W] logits are never materialised."""
+        if (self.fused_loss and logits.is_cuda and type(self.loss) is PixelWeightedCrossEntropyLoss
+                and target.dim() == 3 and tuple(target.shape[-2:]) == tuple(size) and 2 <= logits.shape[1] <= 32
+                and size[0] >= logits.shape[-2] and size[1] >= logits.shape[-1]):
+            return ops.upsample_cross_entropy(logits, target, pixel_weight, self.loss.ignore_index)
+        logits = F.interpolate(logits.float(), size, mode='bilinear', align_corners=False)
+        if pixel_weight is None:
+            return self.loss(logits, target)
+        return self.loss(logits, target, pixel_weight=pixel_weight)
 
     def _join_target_branches(self, side, batch):
         main = torch.cuda.current_stream()
@@ -373,9 +390,7 @@ class DomainAdaptationSegmentationModel(_Base):
         mixed_img, mixed_lbl, mixed_weight = mixed
         with self._autocast():
             mixed_pred = self.head(self.backbone(mixed_img))
-            mixed_pred = F.interpolate(mixed_pred.float(), mixed_img.shape[-2:], mode='bilinear',
-                                       align_corners=False)
-            mixed_loss = self.loss(mixed_pred, mixed_lbl, pixel_weight=mixed_weight)
+            mixed_loss = self._upsampled_loss(mixed_pred, mixed_lbl, mixed_img.shape[-2:], mixed_weight)
         self.log("train_loss_uda_trg", mixed_loss)
         self.manual_backward(mixed_loss)
         del mixed_loss, mixed_pred

@@ -245,6 +245,7 @@ def test_graphed_train_step_matches_eager():
         else:
             m.concurrent_branches = False
             m.fuse_source_backward = False
+            m.fused_loss = False     # library F.interpolate + cross-entropy, as the reference runs it
         torch.manual_seed(123)
         for i in range(6):
             m.training_step(batch, i)
@@ -257,6 +258,49 @@ def test_graphed_train_step_matches_eager():
         assert abs(l0[k] - l1[k]) <= 2e-2 * max(1.0, abs(l0[k])), (k, l0[k], l1[k])
     _close(p1, p0, 2e-3, 2e-3, "parameters")
     _close(e1, e0, 2e-3, 2e-3, "ema parameters")
+
+
+@pytest.mark.parametrize("shape", [(2, 19, 64, 64, 256, 256), (1, 19, 24, 20, 100, 84), (2, 7, 16, 16, 16, 16),
+                                   (1, 19, 8, 8, 31, 33), (1, 32, 5, 3, 40, 12)])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_upsample_cross_entropy_fwd_bwd(shape, weighted):
+    """Fused bilinear up-sampling + pixel-weighted cross-entropy (ignore_index 255, mean over ALL pixels) vs
+    the reference formulation F.interpolate(align_corners=False) + PixelWeightedCrossEntropyLoss
+    (models/losses.py:10-22) evaluated by torch on the CPU in fp32.  Loss 1e-5 relative; gradient 1e-4 relative
+    + 1e-5 of its largest entry (fp32 on both sides, different summation order)."""
+    import refign_b200 as P
+    B, K, h, w, H, W = shape
+    torch.manual_seed(sum(shape) + int(weighted))
+    low = (3.0 * torch.randn(B, K, h, w)).requires_grad_(True)
+    tgt = torch.randint(0, K, (B, H, W))
+    tgt[torch.rand(B, H, W) < 0.1] = 255
+    pw = torch.rand(B, H, W) if weighted else None
+    up = F.interpolate(low.float(), (H, W), mode='bilinear', align_corners=False)
+    want = P.PixelWeightedCrossEntropyLoss()(up, tgt, pixel_weight=pw)
+    (want * 1.7).backward()
+    g_want = low.grad.clone()
+    lg = low.detach().to(DEV).requires_grad_(True)
+    got = ops.upsample_cross_entropy(lg, tgt.to(DEV), None if pw is None else pw.to(DEV), 255)
+    assert got.shape == () and abs(float(got) - float(want)) <= 1e-5 * max(1.0, abs(float(want))), (float(got), float(want))
+    (got * 1.7).backward()
+    _close(lg.grad.cpu(), g_want, 1e-4, 1e-5 * float(g_want.abs().max()), "grad_logits")
+    # all pixels ignored: loss 0 and a zero gradient
+    lg2 = low.detach().to(DEV).requires_grad_(True)
+    z = ops.upsample_cross_entropy(lg2, torch.full((B, H, W), 255, device=DEV), None, 255)
+    z.backward()
+    assert float(z) == 0.0 and float(lg2.grad.abs().max()) == 0.0
+    with pytest.raises(RuntimeError):
+        ops.upsample_cross_entropy(lg, tgt.to(DEV)[0], None, 255)   # 2-D target
+
+
+@pytest.mark.parametrize("shape", [(4, 19, 64, 64, 256, 256), (1, 3, 24, 20, 100, 84), (2, 1, 16, 16, 16, 16)])
+def test_upsample_bilinear_f32(shape):
+    """Teacher-logit up-sampling vs F.interpolate(mode='bilinear', align_corners=False), fp32: 1e-5."""
+    B, C, h, w, H, W = shape
+    torch.manual_seed(sum(shape))
+    x = torch.randn(B, C, h, w, device=DEV)
+    _close(ops.upsample_bilinear(x, (H, W)), F.interpolate(x, (H, W), mode='bilinear', align_corners=False), 1e-5, 1e-5,
+           "upsampled")
 
 
 @pytest.mark.parametrize("spec", [(2, 64, 64, 64), (1, 64, 100, 76), (2, 32, 40, 56), (1, 64, 7, 9)])
