@@ -13,6 +13,8 @@
 //           accumulate the squared norm over s, then rescale in place.
 // Both operands are read in their native [B,C,N] layout (N contiguous), i.e.
 // no transposed copies.
+#include <stdlib.h>
+
 #include "rf_common.cuh"
 
 namespace rf {
@@ -139,6 +141,10 @@ global_corr_finish_kernel(float* __restrict__ out, const float* __restrict__ row
 int global_corr_umma(const float* src, const float* trg, float* out, float* rowmax, float* colmax, float* normsq,
                      int B, int C, long Ns, long Nt, int mode, cudaStream_t st);  // global_corr_umma.cu
 bool global_corr_umma_supported(int C, long Ns, long Nt, const void* a, const void* b, const void* c);
+// global_corr_persist.cu
+int global_corr_persist(const float* src, const float* trg, float* out, float* rowmax, float* colmax, float* normsq,
+                        int B, int C, long Ns, long Nt, int mode, cudaStream_t st);
+bool global_corr_persist_supported(int C, long Ns, long Nt, const void* a, const void* b, const void* c);
 
 }  // namespace rf
 
@@ -162,10 +168,22 @@ extern "C" int rf_global_corr_fwd(const float* src, const float* trg, float* out
     RF_CHECK_LAUNCH("fill_kernel");
   }
   const bool can_tc = global_corr_umma_supported(C, Ns, Nt, src, trg, out);
+  const bool can_pp = global_corr_persist_supported(C, Ns, Nt, src, trg, out);
   RF_REQUIRE(use_tensor_cores != 1 || can_tc,
              "rf_global_corr_fwd: tcgen05 path needs C%%32==0, Ns%%4==0, Nt%%4==0 and 16B-aligned pointers");
-  // automatic choice: the tensor-core path pays off once the volume no longer fits a handful of CTAs
-  if (use_tensor_cores == 1 || (use_tensor_cores < 0 && can_tc && Ns * Nt >= (1l << 20))) {
+  RF_REQUIRE(use_tensor_cores != 2 || can_pp,
+             "rf_global_corr_fwd: persistent tcgen05 path needs C%%32==0, C<=128, Ns%%4==0, Nt%%4==0 and 16B-aligned pointers");
+  RF_REQUIRE(use_tensor_cores <= 2, "rf_global_corr_fwd: use_tensor_cores must be -1 (auto), 0, 1 or 2");
+  // automatic choice: the tensor-core paths pay off once the volume no longer fits a handful of CTAs; the
+  // persistent kernel (source tile resident, C <= 128) is the sweep-size path
+  static const bool persist_off = [] { const char* e = getenv("RF_GCORR_PERSIST"); return e && e[0] == '0'; }();
+  const bool big = Ns * Nt >= (1l << 20);
+  if (use_tensor_cores == 2 || (use_tensor_cores < 0 && can_pp && big && !persist_off)) {
+    RF_REQUIRE(workspace != nullptr, "rf_global_corr_fwd: the tcgen05 path needs the workspace");
+    float* ws = (float*)workspace;
+    return global_corr_persist(src, trg, out, ws, ws + (long)B * Ns, ws + (long)B * (Ns + Nt), B, C, Ns, Nt, mode, st);
+  }
+  if (use_tensor_cores == 1 || (use_tensor_cores < 0 && can_tc && big)) {
     RF_REQUIRE(workspace != nullptr, "rf_global_corr_fwd: the tcgen05 path needs the workspace");
     float* ws = (float*)workspace;
     return global_corr_umma(src, trg, out, ws, ws + (long)B * Ns, ws + (long)B * (Ns + Nt), B, C, Ns, Nt, mode, st);

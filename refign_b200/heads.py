@@ -126,6 +126,68 @@ class DAFormerHead(BaseHead):
 
 
 # ------------------------------------------------------------------------------------------------
+# SegFormer (the HRDA scale-attention head: configs/*/refign_hrda_star.yaml `hrda_scale_attention`)
+# ------------------------------------------------------------------------------------------------
+def _embed_resize_concat(x, embed, order, os_size):
+    """``cat([resize(embed_i(x_i)) for i in order], 1)``: the per-stage linear embedding (tokens), bilinear
+    resize to the stride-4 map and channel concat shared by the DAFormer and SegFormer heads.  On the GPU with
+    bf16 tokens this is ONE kernel writing the channels-last concatenation (ops.upsample_concat)."""
+    n = x[0].shape[0]
+    embedded, sizes = [], []
+    for i in order:
+        hi, wi = x[i].shape[2:]
+        embedded.append(embed(i)(x[i]))    # [n, hi*wi, E] tokens
+        sizes.append((hi, wi))
+    cl = x[0].is_cuda
+    if (cl and len(embedded) <= 4 and all(c.dtype == torch.bfloat16 and c.shape[-1] % 8 == 0 for c in embedded)
+            and all(hi <= os_size[0] and wi <= os_size[1] for hi, wi in sizes)):
+        return ops.upsample_concat(embedded, sizes, os_size)
+    maps = []
+    for c, (hi, wi) in zip(embedded, sizes):
+        c = c.view(n, hi, wi, -1).permute(0, 3, 1, 2)       # NCHW view, channels-last memory
+        if (hi, wi) != tuple(os_size):
+            with torch.autocast('cuda', enabled=False):
+                c = F.interpolate(c, size=os_size, mode='bilinear', align_corners=False)
+        maps.append(c)
+    y = torch.cat(maps, dim=1)
+    return y.contiguous(memory_format=torch.channels_last) if cl else y
+
+
+class SegFormerHead(BaseHead):
+    """All-MLP decoder (reference models/heads/segformer.py:15-111; same ``state_dict`` keys:
+    ``linear_c{1..4}.proj``, ``linear_fuse.{conv,bn}``, ``linear_pred``): per-stage linear embedding, resize to
+    stride 4, concat in the order c4, c3, c2, c1, 1x1 conv + BN + ReLU, 1x1 classifier."""
+
+    os = 4
+
+    def __init__(self, in_channels, in_index, num_classes, input_transform=None, channels=256, dropout_ratio=0.1):
+        super().__init__(num_classes, in_index, input_transform)
+        self.in_channels = in_channels
+        c1, c2, c3, c4 = in_channels
+        self.linear_c4 = MLP(input_dim=c4, embed_dim=channels)
+        self.linear_c3 = MLP(input_dim=c3, embed_dim=channels)
+        self.linear_c2 = MLP(input_dim=c2, embed_dim=channels)
+        self.linear_c1 = MLP(input_dim=c1, embed_dim=channels)
+        self.linear_fuse = ConvBNReLU(channels * 4, channels, 1, norm_layer=nn.BatchNorm2d)
+        self.linear_pred = nn.Conv2d(channels, num_classes, kernel_size=1)
+        self.dropout = nn.Dropout2d(dropout_ratio) if dropout_ratio > 0 else None
+        nn.init.normal_(self.linear_pred.weight, mean=0, std=0.01)
+        nn.init.zeros_(self.linear_pred.bias)
+        nn.init.kaiming_normal_(self.linear_fuse.conv.weight, a=0, mode='fan_out', nonlinearity='relu')
+        nn.init.ones_(self.linear_fuse.bn.weight)
+        nn.init.zeros_(self.linear_fuse.bn.bias)
+
+    def forward(self, inputs):
+        c = list(inputs)   # the reference unpacks the four stage maps directly (segformer.py:79)
+        embeds = (self.linear_c1, self.linear_c2, self.linear_c3, self.linear_c4)
+        y = _embed_resize_concat(c, lambda i: embeds[i], (3, 2, 1, 0), c[0].shape[2:])
+        y = self.linear_fuse(y)
+        if self.dropout is not None:
+            y = self.dropout(y)
+        return self.linear_pred(y)
+
+
+# ------------------------------------------------------------------------------------------------
 # UAWarpC
 # ------------------------------------------------------------------------------------------------
 def _l2n(t):

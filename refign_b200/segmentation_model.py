@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops, runtime
+from . import hrda, ops, runtime
 from .dacs_transforms import get_class_masks, strong_transform
 from .matching_utils import estimate_probability_of_confidence_interval_of_mixture_density, warp
 from .modules import DropPath
@@ -73,12 +73,12 @@ class DomainAdaptationSegmentationModel(_Base):
                  inference_batched_slide=True, inference_crop_size=[1080, 1080], inference_stride=[420, 420],
                  pretrained=None, precision='fp32'):
         super().__init__()
-        if use_hrda:
-            raise NotImplementedError("HRDA multi-resolution wrappers (BASELINE config 4) are not built yet")
+        if use_hrda and hrda_scale_attention is None:
+            raise ValueError("use_hrda=True needs the hrda_scale_attention head (configs/*/refign_hrda_star.yaml)")
         # ---- model -------------------------------------------------------------------------------
         self.backbone = backbone
         self.head = head
-        self.hrda_scale_attention = None
+        self.hrda_scale_attention = hrda_scale_attention if use_hrda else None
         self.alignment_backbone = alignment_backbone
         self.alignment_head = alignment_head
         for m in filter(None, [self.alignment_backbone, self.alignment_head]):
@@ -86,7 +86,7 @@ class DomainAdaptationSegmentationModel(_Base):
                 p.requires_grad = False
         self.m_backbone = copy.deepcopy(self.backbone)
         self.m_head = copy.deepcopy(self.head)
-        self.m_hrda_scale_attention = None
+        self.m_hrda_scale_attention = copy.deepcopy(self.hrda_scale_attention)
         for p in self.ema_parameters():
             p.requires_grad = False
         self.enable_fdist = enable_fdist
@@ -118,6 +118,7 @@ class DomainAdaptationSegmentationModel(_Base):
         self.color_jitter_p = color_jitter_p
         self.blur = blur
         self.use_hrda = use_hrda
+        self.hrda_output_stride = hrda_output_stride
         self.hr_loss_weight = hr_loss_weight
         self.use_slide_inference = use_slide_inference
         self.inference_batched_slide = inference_batched_slide
@@ -242,9 +243,8 @@ class DomainAdaptationSegmentationModel(_Base):
         # ---- source ----------------------------------------------------------------------------
         images_src, gt_src = batch['image_src'], batch['semantic_src']
         with self._autocast():
-            feats_src = self.backbone(images_src)
-            logits_src = self.head(feats_src)
-            loss_src = self._upsampled_loss(logits_src, gt_src, images_src.shape[-2:])
+            feats_src, logits_src = self._student_forward(images_src)
+            loss_src = self._student_loss(logits_src, gt_src, images_src.shape[-2:])
         self.log("train_loss_src", loss_src)
         if self.enable_fdist and self.fuse_source_backward:
             # The reference runs two backward passes here (loss_src with retain_graph, then the feature
@@ -290,8 +290,7 @@ class DomainAdaptationSegmentationModel(_Base):
                 images_ref = batch['image_ref']
                 b = images_trg.shape[0]
                 m_input = torch.cat((images_trg, images_ref))
-                m_logits = self.m_head(self.m_backbone(m_input))
-                m_logits = self._upsample_logits(m_logits, m_input.shape[-2:])
+                m_logits = self._upsample_logits(self._teacher_forward(m_input), m_input.shape[-2:])
                 m_logits_trg, m_logits_ref = m_logits[:b], m_logits[b:]
                 if self.use_align:
                     warped_ref, warp_mask, logvar = self.align(m_logits_ref, images_ref, images_trg,
@@ -300,8 +299,7 @@ class DomainAdaptationSegmentationModel(_Base):
                 else:
                     m_probs_trg = self.refine(m_logits_trg, m_logits_ref, None, None)
             else:
-                m_logits_trg = self.m_head(self.m_backbone(images_trg))
-                m_logits_trg = self._upsample_logits(m_logits_trg, images_trg.shape[-2:])
+                m_logits_trg = self._upsample_logits(self._teacher_forward(images_trg), images_trg.shape[-2:])
                 m_probs_trg = F.softmax(m_logits_trg, dim=1)
         fused, self._fused_pseudo = self._fused_pseudo, None
         return {'images_trg': images_trg, 'probs': m_probs_trg, 'fused': fused}
@@ -326,7 +324,7 @@ class DomainAdaptationSegmentationModel(_Base):
             if self.enable_fdist:   # frozen ImageNet copy of the backbone on the source images (feature distance)
                 s_imnet.wait_stream(main)   # (a forked stream must get work and be joined: graph capture)
                 with torch.cuda.stream(s_imnet):
-                    out['feat_imnet'] = self.imnet_backbone(batch['image_src'])
+                    out['feat_imnet'] = self.imnet_backbone(self._imnet_input(batch['image_src']))
             with torch.cuda.stream(s_align):
                 out['flow'], out['logvar'] = _alignment_flow(self.alignment_backbone, self.alignment_head, images_trg,
                                                              images_ref)
@@ -344,8 +342,37 @@ class DomainAdaptationSegmentationModel(_Base):
 
     def _teacher_logits(self, images_trg, images_ref):
         m_input = torch.cat((images_trg, images_ref))
-        m_logits = self.m_head(self.m_backbone(m_input))
-        return self._upsample_logits(m_logits, m_input.shape[-2:])
+        return self._upsample_logits(self._teacher_forward(m_input), m_input.shape[-2:])
+
+    # ---- single-resolution / HRDA dispatch (reference :124-135: forward decorators of models/hrda.py) ----
+    def _student_forward(self, x):
+        """(features for the feature distance, head output).  With HRDA the features are those of the
+        half-resolution view and the head output is ``(logits, hr_logits, crop_box)`` in training mode."""
+        if not self.use_hrda:
+            feats = self.backbone(x)
+            return feats, self.head(feats)
+        mf = hrda.multires_features(self.backbone, x, self.hrda_output_stride, random_crop=self.backbone.training)
+        return mf[0], hrda.fuse_scales(self.head, self.hrda_scale_attention, mf, self.hrda_output_stride,
+                                       random_crop=self.head.training)
+
+    def _teacher_forward(self, x):
+        if not self.use_hrda:
+            return self.m_head(self.m_backbone(x))
+        mf = hrda.multires_features(self.m_backbone, x, self.hrda_output_stride, random_crop=False)
+        return hrda.fuse_scales(self.m_head, self.m_hrda_scale_attention, mf, self.hrda_output_stride,
+                                random_crop=False)
+
+    def _student_loss(self, out, target, size, pixel_weight=None):
+        """Segmentation loss of a student forward; with HRDA (reference :159-170, 228-240) the weighted sum
+        of the fused-prediction loss and the detail-crop loss on the cropped labels / weights."""
+        if not (self.use_hrda and isinstance(out, tuple)):
+            return self._upsampled_loss(out, target, size, pixel_weight)
+        logits, hr_logits, box = out
+        y1, y2, x1, x2 = box
+        hr_weight = None if pixel_weight is None else hrda.crop(pixel_weight, box).contiguous()
+        return ((1 - self.hr_loss_weight) * self._upsampled_loss(logits, target, size, pixel_weight)
+                + self.hr_loss_weight * self._upsampled_loss(hr_logits, hrda.crop(target, box).contiguous(),
+                                                             (y2 - y1, x2 - x1), hr_weight))
 
     def _upsample_logits(self, logits, size):
         """F.interpolate(logits.float(), size, 'bilinear', align_corners=False) of no-grad (teacher) logits."""
@@ -389,8 +416,8 @@ class DomainAdaptationSegmentationModel(_Base):
         """Student forward/backward on the class-mixed images (the third backward pass)."""
         mixed_img, mixed_lbl, mixed_weight = mixed
         with self._autocast():
-            mixed_pred = self.head(self.backbone(mixed_img))
-            mixed_loss = self._upsampled_loss(mixed_pred, mixed_lbl, mixed_img.shape[-2:], mixed_weight)
+            _, mixed_pred = self._student_forward(mixed_img)
+            mixed_loss = self._student_loss(mixed_pred, mixed_lbl, mixed_img.shape[-2:], mixed_weight)
         self.log("train_loss_uda_trg", mixed_loss)
         self.manual_backward(mixed_loss)
         del mixed_loss, mixed_pred
@@ -455,17 +482,30 @@ class DomainAdaptationSegmentationModel(_Base):
 
     # ---- inference ---------------------------------------------------------------------------------
     def forward(self, x, out_size=None):
-        if self.use_slide_inference:
-            raise NotImplementedError("slide inference is eval-only and out of the hot-path scope")
-        logits = self.whole_inference(x)
+        logits = self.slide_inference(x) if self.use_slide_inference else self.whole_inference(x)
         if out_size is not None:
             logits = F.interpolate(logits, size=out_size, mode='bilinear', align_corners=False)
         return logits
 
     def whole_inference(self, x):
         with self._autocast():
-            logits = self.head(self.backbone(x))
+            _, logits = self._student_forward(x)
+        assert not isinstance(logits, tuple), "whole_inference is an eval-mode path (call .eval() first)"
         return F.interpolate(logits.float(), x.shape[-2:], mode='bilinear', align_corners=False)
+
+    def slide_inference(self, img):
+        """Sliding-window inference with overlap averaging (reference :320-382).  The windows are always
+        run as one batch (the reference's ``inference_batched_slide=False`` loop computes the same values one
+        window at a time)."""
+        bs, _, H, W = img.shape
+        ch, cw = self.inference_crop_size
+        boxes = hrda.sliding_boxes(H, W, ch, cw, *self.inference_stride)
+        crops = torch.cat([hrda.crop(img, b) for b in boxes], dim=0)
+        if self.inference_batched_slide:
+            logits = self.whole_inference(crops)
+        else:
+            logits = torch.cat([self.whole_inference(crops[i * bs:(i + 1) * bs]) for i in range(len(boxes))])
+        return hrda.average_windows(logits, boxes, bs)
 
     # ---- optimisation plumbing (reference :384-419) ------------------------------------------------
     def configure_optimizers(self):
@@ -573,7 +613,7 @@ class DomainAdaptationSegmentationModel(_Base):
         assert self.enable_fdist
         with torch.no_grad():
             if feat_imnet is None:
-                feat_imnet = self.imnet_backbone(img)
+                feat_imnet = self.imnet_backbone(self._imnet_input(img))
             feat_imnet = [f.detach() for f in feat_imnet] if isinstance(feat_imnet, Sequence) else [feat_imnet.detach()]
         if not isinstance(feat, Sequence):
             feat = [feat]
@@ -588,6 +628,13 @@ class DomainAdaptationSegmentationModel(_Base):
                                                   self.head.num_classes, 255).long().detach()
             mask = torch.any(gt_small[..., None] == fdclasses, -1)
         return self.fdist_lambda * self.masked_feat_dist(feat[lay], feat_imnet[lay], mask)
+
+    def _imnet_input(self, img):
+        """The ImageNet copy sees what produced the student's feature-distance features: the half-resolution
+        view under HRDA (reference :595-597)."""
+        if self.use_hrda:
+            return F.interpolate(img, scale_factor=0.5, mode='bilinear', align_corners=False)
+        return img
 
     @staticmethod
     def masked_feat_dist(f1, f2, mask=None):

@@ -191,6 +191,36 @@ def test_global_corr_tcgen05_vs_oracle(shape, mm):
     assert bool(((n - 1).abs() < 1e-4).logical_or(n == 0).all())
 
 
+@pytest.mark.parametrize("shape", [(1, 128, 64, 64, 64, 64), (2, 64, 32, 32, 32, 32), (1, 128, 36, 28, 20, 52),
+                                   (1, 32, 16, 12, 128, 128), (3, 96, 40, 40, 24, 24), (2, 128, 50, 44, 36, 60),
+                                   (1, 128, 80, 80, 80, 80)])
+@pytest.mark.parametrize("mm", [True, False])
+def test_global_corr_persistent_vs_oracle(shape, mm):
+    """Persistent warp-specialised tcgen05 kind::tf32 path (use_tensor_cores=2; the automatic choice for
+    volumes >= 2^20 entries with C <= 128): same tolerances as the single-tile tcgen05 path above.  The shapes
+    cover one tile per CTA, many tiles per CTA (TMEM accumulator / operand ring wrap-around, source tile
+    replaced inside a CTA's range), ragged last tiles in both dimensions, B > 1 and 1..4 K blocks."""
+    B, C, Hs, Ws, Ht, Wt = shape
+    torch.manual_seed(sum(shape) + 2)
+    s, t = unit(torch.randn(B, C, Hs, Ws)), unit(torch.randn(B, C, Ht, Wt))
+    raw = ops.global_correlation(s.to(DEV), t.to(DEV), cyclic_consistency=False, normalise=False, use_tensor_cores=2)
+    close(raw, oracle.global_corr(s, t, mutual=False, normalise=False), atol=1e-3, rtol=0)
+    want = oracle.global_corr(s, t, mutual=mm)
+    got = ops.global_correlation(s.to(DEV), t.to(DEV), cyclic_consistency=mm, use_tensor_cores=2)
+    close(got, want, atol=3e-3 * float(want.abs().max()), rtol=2e-2)
+    n = got.norm(dim=1)
+    assert bool(((n - 1).abs() < 1e-4).logical_or(n == 0).all())
+    # the two tensor-core kernels run the same TF32 products: they agree far below the oracle tolerance
+    old = ops.global_correlation(s.to(DEV), t.to(DEV), cyclic_consistency=mm, use_tensor_cores=1)
+    close(got, old, atol=1e-5 * float(old.abs().max()), rtol=1e-4)
+
+
+def test_global_corr_persistent_rejects_wide_channels():
+    s = unit(torch.randn(1, 256, 8, 8)).to(DEV)
+    with pytest.raises(RuntimeError):
+        ops.global_correlation(s, s, use_tensor_cores=2)   # C > 128: the source tile does not stay resident
+
+
 # ----------------------------------------------------------------------------- warp
 def test_warp_golden_and_oracle(golden):
     g = golden("ops_warp")

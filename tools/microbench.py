@@ -100,6 +100,29 @@ def main():
             nn_ = N * N
             report("global_corr(tcgen05 tf32)+mm+relu_l2norm", [B, C, N, N], time_op(lambda: ops.global_correlation(s, t, use_tensor_cores=1), args.iters),
                    4 * B * (C * 2 * nn_ + nn_ * nn_), 3 * 2 * B * nn_ * nn_ * C)
+    if want("global_pp"):
+        for (B, C, N) in [(1, 128, 64), (1, 128, 128), (2, 128, 128), (1, 128, 192), (1, 64, 128)]:
+            s, t = unit(torch.randn(B, C, N, N, device=dev)), unit(torch.randn(B, C, N, N, device=dev))
+            nn_ = N * N
+            report("global_corr(persistent tcgen05 tf32)+mm+relu_l2norm", [B, C, N, N], time_op(lambda: ops.global_correlation(s, t, use_tensor_cores=2), args.iters),
+                   4 * B * (C * 2 * nn_ + nn_ * nn_), 3 * 2 * B * nn_ * nn_ * C)
+            report("global_corr(persistent tcgen05 tf32) raw volume", [B, C, N, N], time_op(lambda: ops.global_correlation(s, t, cyclic_consistency=False, normalise=False, use_tensor_cores=2), args.iters),
+                   4 * B * (C * 2 * nn_ + nn_ * nn_), 2 * B * nn_ * nn_ * C)
+    if want("upsample_ce"):
+        for (B, H) in [(2, 1024), (2, 512)]:
+            lg = (3 * torch.randn(B, 19, H // 4, H // 4, device=dev)).requires_grad_(True)
+            tg = torch.randint(0, 19, (B, H, H), device=dev)
+            pw = torch.rand(B, H, H, device=dev)
+            report("upsample_ce_fwd", [B, 19, H, H], time_op(lambda: ops.upsample_cross_entropy(lg.detach(), tg, pw), args.iters),
+                   4 * lg.numel() + 12 * B * H * H, 12 * B * H * H * 19)
+            loss = ops.upsample_cross_entropy(lg, tg, pw)
+            report("upsample_ce_bwd", [B, 19, H, H], time_op(lambda: torch.autograd.grad(loss, lg, retain_graph=True), args.iters),
+                   8 * lg.numel() + 12 * B * H * H, 4 * 24 * B * H * H * 19)
+            x4 = torch.randn(2 * B, 19, H // 4, H // 4, device=dev)
+            report("upsample_bilinear_f32", [2 * B, 19, H, H], time_op(lambda: ops.upsample_bilinear(x4, (H, H)), args.iters),
+                   4 * x4.numel() * 17, 8 * x4.numel() * 16)
+            up = lambda: torch.nn.functional.cross_entropy(torch.nn.functional.interpolate(lg.detach(), (H, H), mode="bilinear", align_corners=False), tg)
+            report("library interpolate+cross_entropy fwd (for comparison)", [B, 19, H, H], time_op(up, args.iters), 4 * lg.numel() + 12 * B * H * H, 0)
     if want("warp"):
         for (B, C, H) in [(2, 19, 512), (2, 19, 1024), (2, 128, 256), (2, 256, 128)]:
             x, f = torch.randn(B, C, H, H, device=dev), torch.randn(B, 2, H, H, device=dev) * 4
