@@ -56,6 +56,40 @@ __device__ __forceinline__ float ul_logits(const float* __restrict__ low, int KK
   return mx + logf(s);
 }
 
+// softmax of the interpolated logits of full-resolution pixel (y, x) (backward: one exponential per class)
+template <int K>
+__device__ __forceinline__ void ul_softmax(const float* __restrict__ low, int KK, int h, int w, float sy, float sx,
+                                           int y, int x, float (&p)[K > 0 ? K : UL_MAXK]) {
+  int y0, y1, x0, x1;
+  float ly, lx;
+  ul_coord(y, h, sy, y0, y1, ly);
+  ul_coord(x, w, sx, x0, x1, lx);
+  const long plane = (long)h * w;
+  const float* p00 = low + (long)y0 * w + x0;
+  const float* p01 = low + (long)y0 * w + x1;
+  const float* p10 = low + (long)y1 * w + x0;
+  const float* p11 = low + (long)y1 * w + x1;
+  float mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < (K > 0 ? K : UL_MAXK); ++k)
+    if (K > 0 || k < KK) {
+      p[k] = (1.f - ly) * ((1.f - lx) * __ldg(p00 + k * plane) + lx * __ldg(p01 + k * plane)) +
+             ly * ((1.f - lx) * __ldg(p10 + k * plane) + lx * __ldg(p11 + k * plane));
+      mx = fmaxf(mx, p[k]);
+    }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < (K > 0 ? K : UL_MAXK); ++k)
+    if (K > 0 || k < KK) {
+      p[k] = __expf(p[k] - mx);
+      s += p[k];
+    }
+  const float inv = 1.f / s;
+#pragma unroll
+  for (int k = 0; k < (K > 0 ? K : UL_MAXK); ++k)
+    if (K > 0 || k < KK) p[k] *= inv;
+}
+
 template <int K>
 __global__ void __launch_bounds__(256)
 upsample_ce_fwd_kernel(const float* __restrict__ low, const long long* __restrict__ target,
@@ -148,12 +182,12 @@ upsample_ce_bwd_kernel(const float* __restrict__ low, const long long* __restric
         const long fi = ((long)b * H + y) * W + x;
         const long long t = target[fi];
         if (t == ignore_index || t < 0 || t >= KK) continue;
-        float z[KR];
-        const float lse = ul_logits<K>(lowb, KK, h, w, sy, sx, y, x, z);
+        float pr[KR];
+        ul_softmax<K>(lowb, KK, h, w, sy, sx, y, x, pr);
         const float c = wy * wx * (weight ? __ldg(weight + fi) : 1.f);
 #pragma unroll
         for (int k = 0; k < KR; ++k)
-          if (K > 0 || k < KK) acc[k] = fmaf(c, __expf(z[k] - lse) - (k == (int)t ? 1.f : 0.f), acc[k]);
+          if (K > 0 || k < KK) acc[k] = fmaf(c, pr[k] - (k == (int)t ? 1.f : 0.f), acc[k]);
       }
     }
   }

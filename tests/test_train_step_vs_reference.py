@@ -28,18 +28,25 @@ def _fixed_masks(labels):
     return [((lab % 2) == 0).long().unsqueeze(0) for lab in labels]
 
 
-def _build(ns_backbones, ns_heads, Model, loss):
+def _build(ns_backbones, ns_heads, Model, loss, use_hrda=False):
     torch.manual_seed(7)
     bb = ns_backbones.MixVisionTransformer('mit_b0', drop_path_rate=0.0)
     hd = ns_heads.DAFormerHead([32, 64, 160, 256], [0, 1, 2, 3], 19, 'multiple_select', dropout_ratio=0.0)
     vg = ns_backbones.VGG('vgg16', out_indices=[2, 3, 4])
     ah = ns_heads.UAWarpCHead(in_index=[0, 1], input_transform='multiple_select', estimate_uncertainty=True)
+    sa = None
+    if use_hrda:   # configs/cityscapes_acdc/refign_hrda_star.yaml: SegFormerHead scale attention
+        sa = ns_heads.SegFormerHead([32, 64, 160, 256], [0, 1, 2, 3], 19, 'multiple_select', dropout_ratio=0.0)
     return Model(optimizer_init=OPT, lr_scheduler_init=SCH, backbone=bb, head=hd, loss=loss,
                  alignment_backbone=vg, alignment_head=ah, backbone_lr_factor=0.1, use_refign=True,
-                 adapt_to_ref=False, enable_fdist=True, color_jitter_p=1.1, blur=False)
+                 adapt_to_ref=False, enable_fdist=True, color_jitter_p=1.1, blur=False, use_hrda=use_hrda,
+                 hrda_scale_attention=sa)
 
 
-def test_two_train_steps_match_reference(monkeypatch):
+@pytest.mark.parametrize("use_hrda", [False, True])
+def test_two_train_steps_match_reference(monkeypatch, use_hrda):
+    """``use_hrda=True`` is BASELINE config 4's model (HRDA multi-resolution student / sliding-window teacher,
+    SegFormerHead scale attention, hr_loss_weight 0.1): the seeded ``random`` module pins the detail crops."""
     refshim.install()
     import models.backbones as rb
     import models.heads as rh
@@ -49,10 +56,11 @@ def test_two_train_steps_match_reference(monkeypatch):
     import refign_b200 as P
     from refign_b200 import segmentation_model as ps
 
-    ref = _build(rb, rh, rs.DomainAdaptationSegmentationModel, RLoss())
+    ref = _build(rb, rh, rs.DomainAdaptationSegmentationModel, RLoss(), use_hrda)
     mine = _build(types.SimpleNamespace(MixVisionTransformer=P.MixVisionTransformer, VGG=P.VGG),
-                  types.SimpleNamespace(DAFormerHead=P.DAFormerHead, UAWarpCHead=P.UAWarpCHead),
-                  P.DomainAdaptationSegmentationModel, P.PixelWeightedCrossEntropyLoss())
+                  types.SimpleNamespace(DAFormerHead=P.DAFormerHead, UAWarpCHead=P.UAWarpCHead,
+                                        SegFormerHead=P.SegFormerHead),
+                  P.DomainAdaptationSegmentationModel, P.PixelWeightedCrossEntropyLoss(), use_hrda)
     # the ImageNet copy must differ from the student, otherwise the feature-distance gradient is
     # d||x||/dx at x ~ fp32 noise (a random unit vector) and nothing downstream is comparable
     with torch.no_grad():
@@ -62,6 +70,19 @@ def test_two_train_steps_match_reference(monkeypatch):
     mine.load_state_dict(copy.deepcopy(ref.state_dict()), strict=True)
     monkeypatch.setattr(rs, 'get_class_masks', _fixed_masks)
     monkeypatch.setattr(ps, 'get_class_masks', _fixed_masks)
+    if use_hrda:
+        # the reference calls random.randrange(0, (margin + 1) // 8.0) (hrda.py:24-27): a float stop, accepted
+        # by the Python 3.8 it was written for and a TypeError since 3.12 -- same draw with the stop made integral
+        import models.hrda as rhrda
+
+        class _IntRandom:
+            def __getattr__(self, name):
+                return getattr(random, name)
+
+            @staticmethod
+            def randrange(start, stop=None, *a):
+                return random.randrange(int(start), None if stop is None else int(stop), *a)
+        monkeypatch.setattr(rhrda, 'random', _IntRandom())
 
     # --- Lightning shims for the reference ---
     opt = torch.optim.AdamW(ref.optimizer_parameters(), lr=OPT['init_args']['lr'],
@@ -80,13 +101,15 @@ def test_two_train_steps_match_reference(monkeypatch):
     mine.setup_runtime()
 
     g = torch.Generator().manual_seed(11)
+    S = 128 if use_hrda else 64    # HRDA halves the context view: keep a 2x2 stride-32 map for the feature distance
+    h = S // 2
     for step in range(2):
-        batch = {'image_src': torch.randn(1, 3, 64, 64, generator=g),
-                 'semantic_src': torch.randint(0, 19, (1, 64, 64), generator=g),
-                 'image_trg': torch.randn(1, 3, 64, 64, generator=g)}
-        batch['image_ref'] = batch['image_trg'].roll((2, -3), (2, 3)) + 0.05 * torch.randn(1, 3, 64, 64, generator=g)
-        batch['semantic_src'][0, :32, :32] = 6     # a 'thing' block so the feature-distance mask is not empty
-        batch['semantic_src'][0, :32, 32:] = 12
+        batch = {'image_src': torch.randn(1, 3, S, S, generator=g),
+                 'semantic_src': torch.randint(0, 19, (1, S, S), generator=g),
+                 'image_trg': torch.randn(1, 3, S, S, generator=g)}
+        batch['image_ref'] = batch['image_trg'].roll((2, -3), (2, 3)) + 0.05 * torch.randn(1, 3, S, S, generator=g)
+        batch['semantic_src'][0, :h, :h] = 6     # a 'thing' block so the feature-distance mask is not empty
+        batch['semantic_src'][0, :h, h:] = 12
         batch['semantic_src'][0, :4, :4] = 255
         with cpu_ops():
             random.seed(5 + step)

@@ -105,7 +105,7 @@ def main():
             s, t = unit(torch.randn(B, C, N, N, device=dev)), unit(torch.randn(B, C, N, N, device=dev))
             nn_ = N * N
             report("global_corr(persistent tcgen05 tf32)+mm+relu_l2norm", [B, C, N, N], time_op(lambda: ops.global_correlation(s, t, use_tensor_cores=2), args.iters),
-                   4 * B * (C * 2 * nn_ + nn_ * nn_), 3 * 2 * B * nn_ * nn_ * C)
+                   4 * B * (C * 2 * nn_ + nn_ * nn_), 4 * 2 * B * nn_ * nn_ * C)   # 4 tile passes: 2 x row max, row norm, write
             report("global_corr(persistent tcgen05 tf32) raw volume", [B, C, N, N], time_op(lambda: ops.global_correlation(s, t, cyclic_consistency=False, normalise=False, use_tensor_cores=2), args.iters),
                    4 * B * (C * 2 * nn_ + nn_ * nn_), 2 * B * nn_ * nn_ * C)
     if want("upsample_ce"):
