@@ -217,12 +217,12 @@ global_corr_persist_kernel(const __grid_constant__ CUtensorMap tm_a, const __gri
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = sh->tmem_base;
+  const uint32_t tmem = uniform_u32(sh->tmem_base);   // provably warp-uniform: the MMA operands stay in uniform registers
 
   if (warp == 9) {
     // ------------------------------------------------------------------ TMA producer (whole warp: the boxes of
     // one stage are issued by different lanes of one instruction)
-    if (lane == 0) {
+    if (elect_one()) {
       tma_prefetch_desc(&tm_a);
       tma_prefetch_desc(&tm_b);
     }
@@ -232,61 +232,70 @@ global_corr_persist_kernel(const __grid_constant__ CUtensorMap tm_a, const __gri
     for (int j = 0; j < ntiles; ++j) {
       if (new_row) {
         if (a_loads > 0) mbar_wait(&sh->a_empty, (a_loads - 1) & 1);   // every MMA reading the old tile is done
-        if (lane == 0) mbar_expect_tx(&sh->a_full, (uint32_t)nkb * GP_KB_BYTES);
-        __syncwarp();
-        if (lane < nkb * 4)
-          tma_load_3d(sA + lane * GP_BOX_BYTES, &tm_a, &sh->a_full, t.r_tile * 128 + (lane & 3) * 32,
-                      (lane >> 2) * GP_BK, t.b);
+        if (elect_one()) {
+          mbar_expect_tx(&sh->a_full, (uint32_t)nkb * GP_KB_BYTES);
+          for (int kb = 0; kb < nkb; ++kb)
+#pragma unroll
+            for (int blk = 0; blk < 4; ++blk)
+              tma_load_3d(sA + kb * GP_KB_BYTES + blk * GP_BOX_BYTES, &tm_a, &sh->a_full, t.r_tile * 128 + blk * 32,
+                          kb * GP_BK, t.b);
+        }
         ++a_loads;
       }
       for (int kb = 0; kb < nkb; ++kb) {
         if (fills >= GP_STAGES) mbar_wait(&sh->b_empty[st], ((fills / GP_STAGES) - 1) & 1);
-        if (lane == 0) mbar_expect_tx(&sh->b_full[st], GP_BKB_BYTES);
-        __syncwarp();
-        if (lane < GP_TN / 32)
-          tma_load_3d(ring + st * GP_BKB_BYTES + lane * GP_BOX_BYTES, &tm_b, &sh->b_full[st],
-                      t.c_tile * GP_TN + lane * 32, kb * GP_BK, t.b);
+        if (elect_one()) {
+          uint8_t* dst = ring + st * GP_BKB_BYTES;
+          mbar_expect_tx(&sh->b_full[st], GP_BKB_BYTES);
+#pragma unroll
+          for (int blk = 0; blk < GP_TN / 32; ++blk)
+            tma_load_3d(dst + blk * GP_BOX_BYTES, &tm_b, &sh->b_full[st], t.c_tile * GP_TN + blk * 32, kb * GP_BK, t.b);
+        }
         ++fills;
         st = (st + 1 == GP_STAGES) ? 0 : st + 1;
       }
       new_row = gp_next(t, nRT, nCT);
     }
   } else if (warp == 8) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t IDESC = make_idesc(FMT_TF32, 128, GP_TN, 1, 1);
-      const uint64_t da0 = make_sdesc_sw128_base32(smem_u32(sA), GP_BOX_BYTES, 512);
-      const uint64_t db0 = make_sdesc_sw128_base32(smem_u32(ring), GP_BOX_BYTES, 512);
-      GpTile t = gp_decode(start, nRT, nCT);
-      bool new_row = true;
-      uint32_t a_cnt = 0, st = 0, ph = 0;
-      for (int j = 0; j < ntiles; ++j) {
-        if (new_row) {
-          mbar_wait(&sh->a_full, a_cnt & 1);
-          ++a_cnt;
-        }
-        const uint32_t buf = (uint32_t)j & (GP_ACC - 1);
-        if (j >= GP_ACC) mbar_wait(&sh->acc_empty[buf], ((j / GP_ACC) - 1) & 1);   // epilogue drained this accumulator
+    // ------------------------------------------------------------------ MMA issuer (whole warp, elected issue)
+    constexpr uint32_t IDESC = make_idesc(FMT_TF32, 128, GP_TN, 1, 1);
+    const uint64_t da0 = make_sdesc_sw128_base32(smem_u32(sA), GP_BOX_BYTES, 512);
+    const uint64_t db0 = make_sdesc_sw128_base32(smem_u32(ring), GP_BOX_BYTES, 512);
+    GpTile t = gp_decode(start, nRT, nCT);
+    bool new_row = true;
+    uint32_t a_cnt = 0, st = 0, ph = 0;
+    for (int j = 0; j < ntiles; ++j) {
+      if (new_row) {
+        mbar_wait(&sh->a_full, a_cnt & 1);
+        ++a_cnt;
+      }
+      const uint32_t buf = (uint32_t)j & (GP_ACC - 1);
+      if (j >= GP_ACC) mbar_wait(&sh->acc_empty[buf], ((j / GP_ACC) - 1) & 1);   // epilogue drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem + buf * GP_TN;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&sh->b_full[st], ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem + buf * GP_TN;
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&sh->b_full[st], ph);
-          tc_fence_after();
-          const uint64_t da = da0 + (uint64_t)(kb * (GP_KB_BYTES >> 4));
-          const uint64_t db = db0 + (uint64_t)(st * (GP_BKB_BYTES >> 4));
+        const uint64_t da = da0 + (uint64_t)(kb * (GP_KB_BYTES >> 4));
+        const uint64_t db = db0 + (uint64_t)(st * (GP_BKB_BYTES >> 4));
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < GP_BK / 8; ++k)
             mma_tf32_ss(d_tmem, da + (uint64_t)(k * 64), db + (uint64_t)(k * 64), IDESC, (kb > 0 || k > 0) ? 1u : 0u);
           tc_commit(&sh->b_empty[st]);
-          if (++st == GP_STAGES) {
-            st = 0;
-            ph ^= 1;
-          }
         }
+        __syncwarp();
+        if (++st == GP_STAGES) {
+          st = 0;
+          ph ^= 1;
+        }
+      }
+      new_row = gp_next(t, nRT, nCT);
+      if (elect_one()) {
         tc_commit(&sh->acc_full[buf]);
-        new_row = gp_next(t, nRT, nCT);
         if (new_row && j + 1 < ntiles) tc_commit(&sh->a_empty);   // the resident tile may be replaced
       }
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps: thread = accumulator row

@@ -20,6 +20,21 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// ---------------------------------------------------------------- warp-uniform issue
+// One lane of a converged warp (elect.sync).  The warps that issue tcgen05.mma / cp.async.bulk.tensor run their
+// loops with ALL lanes on warp-uniform values and gate only the issue itself with elect_one(): inside an
+// `if (lane == 0)` region every operand lives in per-thread registers and ptxas wraps each issue in an
+// ELECT + 5 x R2UR + BRA.U.ANY loop (~17 SASS instructions per MMA -- more issue cycles than a 128x128x16 bf16 MMA
+// needs to execute); with uniform control flow the descriptors stay in uniform registers and one MMA costs a
+// UIADD3.64 pair + UTCHMMA.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// A value every lane already holds, made PROVABLY warp-uniform for ptxas (redux.sync writes a uniform register)
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __reduce_max_sync(0xffffffffu, v); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

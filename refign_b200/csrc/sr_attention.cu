@@ -341,6 +341,10 @@ struct __align__(8) Attn2Bars {
   uint32_t tmem_base;
 };
 
+// UNI: the TMA / MMA warps run with all lanes on warp-uniform values and elect one lane per issue (rf_sm100.cuh
+// elect_one(): descriptors in uniform registers, one MMA = UIADD3.64 pair + UTCHMMA); UNI = false keeps the
+// `if (lane == 0)` form (~17 SASS instructions per MMA) for A/B measurement (RF_UNIFORM_ISSUE=0).
+template <bool UNI>
 __global__ void __launch_bounds__(AT2_THREADS, 1)
 sr_attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                            __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int N, int M, int heads,
@@ -374,39 +378,47 @@ sr_attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = bars->tmem_base;
+  const uint32_t tmem = UNI ? uniform_u32(bars->tmem_base) : bars->tmem_base;
 
   constexpr uint32_t IDESC_S = make_idesc(FMT_BF16, 128, 128, 0, 0);
   constexpr uint32_t IDESC_O = make_idesc(FMT_BF16, 128, 64, 0, 1);
 
   if (warp == 9) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      tma_prefetch_desc(&tm_q);
-      tma_prefetch_desc(&tm_kv);
-      mbar_expect_tx(&bars->q_full, 2 * AT_TILE_BYTES);
-      tma_load_3d(sQ, &tm_q, &bars->q_full, head * AT_D, q0, b);
-      tma_load_3d(sQ + AT_TILE_BYTES, &tm_q, &bars->q_full, head * AT_D, q0 + AT_BM, b);
+    if (UNI || lane == 0) {
+      if (!UNI || elect_one()) {
+        tma_prefetch_desc(&tm_q);
+        tma_prefetch_desc(&tm_kv);
+        mbar_expect_tx(&bars->q_full, 2 * AT_TILE_BYTES);
+        tma_load_3d(sQ, &tm_q, &bars->q_full, head * AT_D, q0, b);
+        tma_load_3d(sQ + AT_TILE_BYTES, &tm_q, &bars->q_full, head * AT_D, q0 + AT_BM, b);
+      }
       for (int j = 0; j < nchunks; ++j) {
         const int st = j % AT2_STAGES;
         if (j >= AT2_STAGES) mbar_wait(&bars->kv_free[st], ((j / AT2_STAGES) - 1) & 1);
         uint8_t* sK = ring + st * 2 * AT_TILE_BYTES;
-        mbar_expect_tx(&bars->kv_full[st], 2 * AT_TILE_BYTES);
-        tma_load_3d(sK, &tm_kv, &bars->kv_full[st], head * AT_D, j * AT_BN, b);
-        tma_load_3d(sK + AT_TILE_BYTES, &tm_kv, &bars->kv_full[st], C + head * AT_D, j * AT_BN, b);
+        if (!UNI || elect_one()) {
+          mbar_expect_tx(&bars->kv_full[st], 2 * AT_TILE_BYTES);
+          tma_load_3d(sK, &tm_kv, &bars->kv_full[st], head * AT_D, j * AT_BN, b);
+          tma_load_3d(sK + AT_TILE_BYTES, &tm_kv, &bars->kv_full[st], C + head * AT_D, j * AT_BN, b);
+        }
+        if (UNI) __syncwarp();
       }
     }
   } else if (warp == 8) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (UNI || lane == 0) {
       const uint64_t descQ[2] = {make_sdesc_sw128(smem_u32(sQ), 16, 1024),
                                  make_sdesc_sw128(smem_u32(sQ + AT_TILE_BYTES), 16, 1024)};
       auto issue_s = [&](int t, int j) {
         const uint64_t descK = make_sdesc_sw128(smem_u32(ring + (j % AT2_STAGES) * 2 * AT_TILE_BYTES), 16, 1024);
+        if (!UNI || elect_one()) {
 #pragma unroll
-        for (int k = 0; k < AT_D / 16; ++k)
-          mma_f16_ss(tmem + t * 256, descQ[t] + (uint64_t)(k * 2), descK + (uint64_t)(k * 2), IDESC_S, k > 0 ? 1u : 0u);
-        tc_commit(&bars->s_full[t]);
+          for (int k = 0; k < AT_D / 16; ++k)
+            mma_f16_ss(tmem + t * 256, descQ[t] + (uint64_t)(k * 2), descK + (uint64_t)(k * 2), IDESC_S, k > 0 ? 1u : 0u);
+          tc_commit(&bars->s_full[t]);
+        }
+        if (UNI) __syncwarp();
       };
       mbar_wait(&bars->q_full, 0);
       mbar_wait(&bars->kv_full[0], 0);
@@ -423,13 +435,17 @@ sr_attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
           mbar_wait(&bars->p_full[t], j & 1);   // warpgroup t has consumed S(j) and written P(j)
           tc_fence_after();
           if (j + 1 < nchunks) issue_s(t, j + 1);   // next scores first: the warpgroup is waiting for them
+          if (!UNI || elect_one()) {
 #pragma unroll
-          for (int k = 0; k < AT_BN / 16; ++k)
-            mma_f16_ts(tmem + t * 256 + 128, tmem + t * 256 + 192 + k * 8, descV + (uint64_t)(k * 128), IDESC_O,
-                       (j > 0 || k > 0) ? 1u : 0u);
-          tc_commit(&bars->o_full[t]);
+            for (int k = 0; k < AT_BN / 16; ++k)
+              mma_f16_ts(tmem + t * 256 + 128, tmem + t * 256 + 192 + k * 8, descV + (uint64_t)(k * 128), IDESC_O,
+                         (j > 0 || k > 0) ? 1u : 0u);
+            tc_commit(&bars->o_full[t]);
+          }
+          if (UNI) __syncwarp();
         }
-        tc_commit(&bars->kv_free[st]);   // K_j / V_j fully consumed by both tiles (S(j) was committed earlier)
+        if (!UNI || elect_one()) tc_commit(&bars->kv_free[st]);   // K_j / V_j fully consumed by both tiles (S(j) was committed earlier)
+        if (UNI) __syncwarp();
       }
     }
   } else {
@@ -527,15 +543,17 @@ extern "C" int rf_sr_attention_fwd(const void* q, const void* kv, void* out, flo
   static bool attr_set = false;
   if (!attr_set) {
     RF_CUDA(cudaFuncSetAttribute(sr_attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-    RF_CUDA(cudaFuncSetAttribute(sr_attention_fwd_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_SMEM));
+    RF_CUDA(cudaFuncSetAttribute(sr_attention_fwd_pp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_SMEM));
+    RF_CUDA(cudaFuncSetAttribute(sr_attention_fwd_pp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_SMEM));
     attr_set = true;
   }
   const float scale_log2 = scale * 1.44269504088896341f;
   static const int variant = getenv("RF_ATTN_FWD") ? atoi(getenv("RF_ATTN_FWD")) : 2;
   if (variant == 2 && N > AT_BM) {   // two query tiles per CTA, warp-specialised
     dim3 grid((unsigned)((N + 2 * AT_BM - 1) / (2 * AT_BM)), (unsigned)heads, (unsigned)B);
-    sr_attention_fwd_pp_kernel<<<grid, AT2_THREADS, AT2_SMEM, (cudaStream_t)stream>>>(tq, tkv, (__nv_bfloat16*)out, lse,
-                                                                                     N, M, heads, scale_log2);
+    static const bool uni = [] { const char* e = getenv("RF_UNIFORM_ISSUE"); return !(e && e[0] == '0'); }();
+    auto kern = uni ? sr_attention_fwd_pp_kernel<true> : sr_attention_fwd_pp_kernel<false>;
+    kern<<<grid, AT2_THREADS, AT2_SMEM, (cudaStream_t)stream>>>(tq, tkv, (__nv_bfloat16*)out, lse, N, M, heads, scale_log2);
     RF_CHECK_LAUNCH("sr_attention_fwd_pp_kernel");
     return RF_OK;
   }

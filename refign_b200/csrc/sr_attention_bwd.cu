@@ -37,12 +37,24 @@ struct __align__(8) BwdBars {
   uint32_t tmem_base;
 };
 
+// Issue discipline of the tcgen05.mma / TMA instructions (template parameter UNI of both kernels):
+//   UNI = true : warp 0 runs the issue code with ALL lanes on warp-uniform values and only the issue itself is
+//                gated by elect_one() (rf_sm100.cuh): descriptors stay in uniform registers, one MMA = UIADD3.64
+//                pair + UTCHMMA.  These kernels issue M128 N64 K16 MMAs (32 tensor-pipe cycles each): with the
+//   UNI = false: `if (tid == 0)` form (kept for A/B measurement, RF_UNIFORM_ISSUE=0) ptxas needs ~17 SASS
+//                instructions (ELECT, 5 x R2UR, BRA.U.ANY loop) per MMA, several times its execution time.
+template <bool UNI>
+__device__ __forceinline__ bool issue_warp(int tid) { return UNI ? (tid < 32) : (tid == 0); }
+template <bool UNI>
+__device__ __forceinline__ bool issue_lane() { return UNI ? elect_one() : true; }
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
 // ------------------------------------------------------------------------------------------ kernel A: dQ (+ D)
+template <bool UNI>
 __global__ void __launch_bounds__(128, 2)
 sr_attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
                            const __grid_constant__ CUtensorMap tm_kv, const __nv_bfloat16* __restrict__ o,
@@ -72,13 +84,13 @@ sr_attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = bars->tmem_base;
+  const uint32_t tmem = UNI ? uniform_u32(bars->tmem_base) : bars->tmem_base;
   const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
   // columns: S [0,64) | dP [64,128) | dS [128,160) | dQ [160,224)
   const uint32_t tS = tmem + lane_off, tdP = tmem + lane_off + 64, tdS = tmem + lane_off + 128,
                  tdQ = tmem + lane_off + 160;
 
-  if (tid == 0) {
+  if (issue_warp<UNI>(tid) && issue_lane<UNI>()) {
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_do);
     tma_prefetch_desc(&tm_kv);
@@ -123,24 +135,26 @@ sr_attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
     const int st = j % AB_STAGES;
     uint8_t* sK = ring + st * 2 * AB_T64;
     uint8_t* sV = sK + AB_T64;
-    if (tid == 0) {
+    if (issue_warp<UNI>(tid)) {
       if (j == 0) mbar_wait(&bars->fixed, 0);
       mbar_wait(&bars->ring[st], (j / AB_STAGES) & 1);
       tc_fence_after();
       const uint64_t descK = make_sdesc_sw128(smem_u32(sK), 16, 1024);
       const uint64_t descV = make_sdesc_sw128(smem_u32(sV), 16, 1024);
+      if (issue_lane<UNI>()) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) mma_f16_ss(tmem, descQ + (uint64_t)(k * 2), descK + (uint64_t)(k * 2), IDESC_KK, k > 0);
+        for (int k = 0; k < 4; ++k) mma_f16_ss(tmem, descQ + (uint64_t)(k * 2), descK + (uint64_t)(k * 2), IDESC_KK, k > 0);
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        mma_f16_ss(tmem + 64, descdO + (uint64_t)(k * 2), descV + (uint64_t)(k * 2), IDESC_KK, k > 0);
-      tc_commit(&bars->s);
+        for (int k = 0; k < 4; ++k)
+          mma_f16_ss(tmem + 64, descdO + (uint64_t)(k * 2), descV + (uint64_t)(k * 2), IDESC_KK, k > 0);
+        tc_commit(&bars->s);
+      }
     }
     __syncwarp();
     mbar_wait(&bars->s, j & 1);
     tc_fence_after();
     // S_j and dP_j are complete, hence (in-order tensor pipe) so is dQ_{j-1}: its K / V stage is free
-    if (tid == 0 && j >= 1 && j - 1 + AB_STAGES < nchunks) {
+    if (issue_warp<UNI>(tid) && j >= 1 && j - 1 + AB_STAGES < nchunks && issue_lane<UNI>()) {
       const int jn = j - 1 + AB_STAGES, s2 = (j - 1) % AB_STAGES;
       mbar_expect_tx(&bars->ring[s2], 2 * AB_T64);
       tma_load_3d(ring + s2 * 2 * AB_T64, &tm_kv, &bars->ring[s2], head * AB_D, jn * 64, b);
@@ -178,13 +192,15 @@ sr_attention_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
     tc_wait_st();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (issue_warp<UNI>(tid)) {
       tc_fence_after();
       const uint64_t descKmn = make_sdesc_sw128(smem_u32(sK), 8192, 1024);
+      if (issue_lane<UNI>()) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        mma_f16_ts(tmem + 160, tmem + 128 + k * 8, descKmn + (uint64_t)(k * 128), IDESC_MN, (j > 0 || k > 0) ? 1u : 0u);
-      if (j == nchunks - 1) tc_commit(&bars->fin);
+        for (int k = 0; k < 4; ++k)
+          mma_f16_ts(tmem + 160, tmem + 128 + k * 8, descKmn + (uint64_t)(k * 128), IDESC_MN, (j > 0 || k > 0) ? 1u : 0u);
+        if (j == nchunks - 1) tc_commit(&bars->fin);
+      }
     }
     __syncwarp();
   }
@@ -231,6 +247,7 @@ __device__ __forceinline__ void dkv_half(const uint32_t (&sv)[32], const uint32_
 }
 
 // ------------------------------------------------------------------------------------------ kernel B: dK, dV
+template <bool UNI>
 __global__ void __launch_bounds__(128, 2)
 sr_attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
                             const __grid_constant__ CUtensorMap tm_kv, const float* __restrict__ lse,
@@ -266,13 +283,13 @@ sr_attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = bars->tmem_base;
+  const uint32_t tmem = UNI ? uniform_u32(bars->tmem_base) : bars->tmem_base;
   const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
   // columns: S^T / P^T [0,64) | dP^T / dS^T [64,128) | dK [128,192) | dV [192,256)
   const uint32_t tS = tmem + lane_off, tdP = tmem + lane_off + 64, tdK = tmem + lane_off + 128,
                  tdV = tmem + lane_off + 192;
 
-  if (tid == 0) {
+  if (issue_warp<UNI>(tid) && issue_lane<UNI>()) {
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_do);
     tma_prefetch_desc(&tm_kv);
@@ -304,18 +321,20 @@ sr_attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
     const int st = i % AB_STAGES, vb = i & 1;
     uint8_t* sQ = ring + st * 2 * AB_T64;
     uint8_t* sdO = sQ + AB_T64;
-    if (tid == 0) {
+    if (issue_warp<UNI>(tid)) {
       if (i == 0) mbar_wait(&bars->fixed, 0);
       mbar_wait(&bars->ring[st], (i / AB_STAGES) & 1);
       tc_fence_after();
       const uint64_t descQ = make_sdesc_sw128(smem_u32(sQ), 16, 1024);
       const uint64_t descdO = make_sdesc_sw128(smem_u32(sdO), 16, 1024);
+      if (issue_lane<UNI>()) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) mma_f16_ss(tmem, descK + (uint64_t)(k * 2), descQ + (uint64_t)(k * 2), IDESC_KK, k > 0);
+        for (int k = 0; k < 4; ++k) mma_f16_ss(tmem, descK + (uint64_t)(k * 2), descQ + (uint64_t)(k * 2), IDESC_KK, k > 0);
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        mma_f16_ss(tmem + 64, descV + (uint64_t)(k * 2), descdO + (uint64_t)(k * 2), IDESC_KK, k > 0);
-      tc_commit(&bars->s);
+        for (int k = 0; k < 4; ++k)
+          mma_f16_ss(tmem + 64, descV + (uint64_t)(k * 2), descdO + (uint64_t)(k * 2), IDESC_KK, k > 0);
+        tc_commit(&bars->s);
+      }
     }
     __syncwarp();
     if (i + 1 < ntiles) {  // per-query vectors of the next tile (published by this iteration's __syncthreads)
@@ -325,7 +344,7 @@ sr_attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
     }
     mbar_wait(&bars->s, i & 1);
     tc_fence_after();
-    if (tid == 0 && i >= 1 && i - 1 + AB_STAGES < ntiles) {  // stage of tile i-1 is free (in-order tensor pipe)
+    if (issue_warp<UNI>(tid) && i >= 1 && i - 1 + AB_STAGES < ntiles && issue_lane<UNI>()) {  // stage of tile i-1 is free (in-order tensor pipe)
       const int tn = t_begin + i - 1 + AB_STAGES, s2 = (i - 1) % AB_STAGES;
       mbar_expect_tx(&bars->ring[s2], 2 * AB_T64);
       tma_load_3d(ring + s2 * 2 * AB_T64, &tm_q, &bars->ring[s2], head * AB_D, tn * 64, b);
@@ -353,17 +372,19 @@ sr_attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
     tc_wait_st();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (issue_warp<UNI>(tid)) {
       tc_fence_after();
       const uint64_t descdOmn = make_sdesc_sw128(smem_u32(sdO), 8192, 1024);
       const uint64_t descQmn = make_sdesc_sw128(smem_u32(sQ), 8192, 1024);
+      if (issue_lane<UNI>()) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        mma_f16_ts(tmem + 192, tmem + k * 8, descdOmn + (uint64_t)(k * 128), IDESC_MN, (i > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < 4; ++k)
+          mma_f16_ts(tmem + 192, tmem + k * 8, descdOmn + (uint64_t)(k * 128), IDESC_MN, (i > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        mma_f16_ts(tmem + 128, tmem + 64 + k * 8, descQmn + (uint64_t)(k * 128), IDESC_MN, (i > 0 || k > 0) ? 1u : 0u);
-      if (i == ntiles - 1) tc_commit(&bars->fin);
+        for (int k = 0; k < 4; ++k)
+          mma_f16_ts(tmem + 128, tmem + 64 + k * 8, descQmn + (uint64_t)(k * 128), IDESC_MN, (i > 0 || k > 0) ? 1u : 0u);
+        if (i == ntiles - 1) tc_commit(&bars->fin);
+      }
     }
     __syncwarp();
   }
@@ -475,8 +496,10 @@ extern "C" int rf_sr_attention_bwd(const void* q, const void* kv, const void* ou
 #undef RF_TM
   static bool attr_set = false;
   if (!attr_set) {
-    RF_CUDA(cudaFuncSetAttribute(sr_attention_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
-    RF_CUDA(cudaFuncSetAttribute(sr_attention_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
+    RF_CUDA(cudaFuncSetAttribute(sr_attention_bwd_dq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
+    RF_CUDA(cudaFuncSetAttribute(sr_attention_bwd_dkv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
+    RF_CUDA(cudaFuncSetAttribute(sr_attention_bwd_dq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
+    RF_CUDA(cudaFuncSetAttribute(sr_attention_bwd_dkv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
     attr_set = true;
   }
   const float scale_log2 = scale * 1.44269504088896341f;
@@ -487,6 +510,7 @@ extern "C" int rf_sr_attention_bwd(const void* q, const void* kv, const void* ou
     RF_CHECK_LAUNCH("sr_attention_dvec_kernel");
   }
   RF_CUDA(cudaMemsetAsync(grad_kv_f32, 0, sizeof(float) * (size_t)B * M * 2 * C, st));
+  static const bool uni = [] { const char* e = getenv("RF_UNIFORM_ISSUE"); return !(e && e[0] == '0'); }();
   static const bool serial = [] { const char* e = getenv("RF_ATTN_BWD_SERIAL"); return e && e[0] == '1'; }();
   BwdFork* fk = serial ? nullptr : bwd_fork();
   cudaStream_t st_kv = st;
@@ -497,9 +521,9 @@ extern "C" int rf_sr_attention_bwd(const void* q, const void* kv, const void* ou
   }
   {
     dim3 grid((unsigned)((N + 127) / 128), (unsigned)heads, (unsigned)B);
-    sr_attention_bwd_dq_kernel<<<grid, 128, AB_SMEM, st>>>(tq128, tdo128, tkv64, (const __nv_bfloat16*)out,
-                                                            (const __nv_bfloat16*)grad_out, lse, dvec,
-                                                            (__nv_bfloat16*)grad_q, N, M, heads, scale, scale_log2);
+    auto kern = uni ? sr_attention_bwd_dq_kernel<true> : sr_attention_bwd_dq_kernel<false>;
+    kern<<<grid, 128, AB_SMEM, st>>>(tq128, tdo128, tkv64, (const __nv_bfloat16*)out, (const __nv_bfloat16*)grad_out, lse,
+                                     dvec, (__nv_bfloat16*)grad_q, N, M, heads, scale, scale_log2);
     RF_CHECK_LAUNCH("sr_attention_bwd_dq_kernel");
   }
   {
@@ -514,8 +538,8 @@ extern "C" int rf_sr_attention_bwd(const void* q, const void* kv, const void* ou
     const int tps = (ntiles + splits - 1) / splits;
     splits = (ntiles + tps - 1) / tps;
     dim3 grid((unsigned)splits, (unsigned)kvchunks, (unsigned)(B * heads));
-    sr_attention_bwd_dkv_kernel<<<grid, 128, AB_SMEM, st_kv>>>(tq64, tdo64, tkv128, lse, dvec, grad_kv_f32, N, M, heads,
-                                                                tps, scale, scale_log2);
+    auto kern = uni ? sr_attention_bwd_dkv_kernel<true> : sr_attention_bwd_dkv_kernel<false>;
+    kern<<<grid, 128, AB_SMEM, st_kv>>>(tq64, tdo64, tkv128, lse, dvec, grad_kv_f32, N, M, heads, tps, scale, scale_log2);
     RF_CHECK_LAUNCH("sr_attention_bwd_dkv_kernel");
   }
   if (fk != nullptr) {   // join

@@ -430,6 +430,7 @@ class DomainAdaptationSegmentationModel(_Base):
         Requires the flat-buffer runtime, static shapes and ``adapt_to_ref=False``."""
         assert self._rt is not None, "call setup_runtime() first"
         assert not self.adapt_to_ref, "the adapt_to_ref coin changes the control flow per step"
+        assert not self.use_hrda, "HRDA draws a new detail-crop box (host-side slicing offsets) every step"
         self._rt['opt'].enable_device_hyper()
         self._graphs = {'n': 0, 'warmup': int(warmup), 'a': None, 'b': None, 'batch': None, 'mixed': None,
                         'out_a': None}
