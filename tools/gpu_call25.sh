@@ -1,0 +1,12 @@
+#!/bin/bash
+OUT=gpurun_out
+timeout 300 python -m pytest tests/test_ops_gpu.py -x -q -k "persistent" > $OUT/s25_pytest_pp.log 2>&1; PP=$?; tail -12 $OUT/s25_pytest_pp.log | cut -c1-300
+timeout 120 python tools/run_gcorr_once.py time 128 2 > $OUT/s25_modes.log 2>&1
+timeout 120 python tools/run_gcorr_once.py time 64 2 >> $OUT/s25_modes.log 2>&1
+timeout 120 python tools/run_gcorr_once.py time 192 2 >> $OUT/s25_modes.log 2>&1
+cat $OUT/s25_modes.log
+if [ $PP -eq 0 ]; then
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:global_corr_persist -s 4 -c 4 -o $OUT/s25_gcorr_persist \
+    python tools/run_gcorr_once.py once 128 2 > $OUT/s25_ncu.log 2>&1
+tail -2 $OUT/s25_ncu.log; ls -la $OUT/s25_gcorr_persist.ncu-rep
+fi
