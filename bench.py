@@ -173,13 +173,13 @@ def corr_volume_sweep(dev, hbm):
         out.append({"op": "local_9x9+relu+l2norm", "shape": [B, 128, H, H], "us": round(sec * 1e6, 1),
                     "GBps": round(nbytes / sec / 1e9, 1), "frac_hbm": round(nbytes / sec / 1e9 / hbm, 4)})
     # stress points of the sweep (max displacement d = 9, 16 -> P = 19, 33; the model only uses P = 9):
-    # these run the generic one-thread-per-output kernel, not the tiled one
+    # these run the wide-patch tiled kernel (one displacement row per CTA) + a separate ReLU / L2-norm pass
     for (B, H, P_) in [(2, 64, 19), (2, 64, 33), (2, 128, 19)]:
         a = unit(torch.randn(B, 128, H, H, device=dev, generator=g))
         b = unit(torch.randn(B, 128, H, H, device=dev, generator=g))
         sec = med(lambda: ops.local_correlation_relu_l2norm(b, a, P_), iters=3)
         nbytes = 4 * B * H * H * (2 * 128 + P_ * P_)
-        out.append({"op": "local_%dx%d+relu+l2norm(generic kernel)" % (P_, P_), "shape": [B, 128, H, H],
+        out.append({"op": "local_%dx%d+relu+l2norm(wide-patch kernel)" % (P_, P_), "shape": [B, 128, H, H],
                     "us": round(sec * 1e6, 1), "GBps": round(nbytes / sec / 1e9, 1),
                     "frac_hbm": round(nbytes / sec / 1e9 / hbm, 4)})
     for (B, H) in [(1, 64), (1, 128), (1, 256)]:

@@ -281,19 +281,126 @@ __global__ void local_corr_generic_kernel(const float* __restrict__ in1, const f
   }
 }
 
+// ----------------------------------------------------------------------------
+// wide patches (9 < P <= 33, odd; kernel 1, stride 1, pad 0, dilation_patch 1): the sweep's stress points
+// (max displacement 9 and 16).  One CTA = an 8 x 64 tile of target pixels x ONE displacement row ph; a thread owns
+// two horizontally adjacent pixels and all P displacement columns (2 P accumulators): the source values
+// s[x + pw] of pixel x and s[x + 1 + pw'] of its neighbour overlap, so one 8-byte shared-memory load feeds four
+// FMAs (3.3 FMA per load at P = 19 against 0.95 for one pixel per thread).  Per 8-channel chunk the target tile and
+// the 8 source rows (64 + 2 R columns, zero outside the image) are staged in shared memory.
+// ----------------------------------------------------------------------------
+constexpr int LW_CK = 8, LW_TH = 8, LW_TW = 64;
+
+template <int PMAX>
+__global__ void __launch_bounds__(256, 2)
+local_corr_wide_kernel(const float* __restrict__ in1, const float* __restrict__ in2, float* __restrict__ out, int C,
+                       int H, int W, int P) {
+  constexpr int RMAX = (PMAX - 1) / 2;
+  constexpr int SW = LW_TW + 2 * RMAX;     // staged source columns (even: rows stay 8-byte aligned)
+  constexpr int NB2 = (PMAX + 2) / 2;      // float2 loads covering b[0 .. PMAX]
+  __shared__ __align__(16) float s1[LW_CK][LW_TH][LW_TW];
+  __shared__ __align__(16) float s2[LW_CK][LW_TH][SW];
+  const int R = (P - 1) / 2;
+  const int n = blockIdx.z / P, ph = blockIdx.z % P;
+  const int y0 = blockIdx.y * LW_TH, x0 = blockIdx.x * LW_TW;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long plane = (long)H * W;
+  const float* a_n = in1 + (long)n * C * plane;
+  const float* b_n = in2 + (long)n * C * plane;
+  const int sw = LW_TW + 2 * R;            // source columns actually needed
+  float acc0[PMAX], acc1[PMAX];
+#pragma unroll
+  for (int i = 0; i < PMAX; ++i) acc0[i] = acc1[i] = 0.f;
+
+  for (int c0 = 0; c0 < C; c0 += LW_CK) {
+    {  // staging: warp ty owns tile row ty of every channel of the chunk (no index divisions)
+      const int yy1 = y0 + ty, yy2 = y0 + ty + ph - R;
+      const bool y1ok = yy1 < H, y2ok = yy2 >= 0 && yy2 < H;
+#pragma unroll
+      for (int c = 0; c < LW_CK; ++c) {
+        const bool cok = c0 + c < C;
+        const float* pa = a_n + (long)(c0 + c) * plane + (long)yy1 * W;
+        const float* pb = b_n + (long)(c0 + c) * plane + (long)yy2 * W;
+#pragma unroll
+        for (int x = tx; x < LW_TW; x += 32) {
+          const int xx = x0 + x;
+          s1[c][ty][x] = (cok && y1ok && xx < W) ? __ldg(pa + xx) : 0.f;
+        }
+        for (int x = tx; x < sw; x += 32) {
+          const int xx = x0 + x - R;
+          s2[c][ty][x] = (cok && y2ok && xx >= 0 && xx < W) ? __ldg(pb + xx) : 0.f;
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < LW_CK; ++c) {
+      const float2 a = *reinterpret_cast<const float2*>(&s1[c][ty][2 * tx]);
+      float b[2 * NB2];
+#pragma unroll
+      for (int k = 0; k < NB2; ++k)
+        if (2 * k <= P) {   // b[pw] for pixel 0 and b[pw + 1] for pixel 1, pw < P
+          const float2 v = *reinterpret_cast<const float2*>(&s2[c][ty][2 * tx + 2 * k]);
+          b[2 * k] = v.x;
+          b[2 * k + 1] = v.y;
+        }
+#pragma unroll
+      for (int pw = 0; pw < PMAX; ++pw)
+        if (pw < P) {
+          acc0[pw] = fmaf(a.x, b[pw], acc0[pw]);
+          acc1[pw] = fmaf(a.y, b[pw + 1], acc1[pw]);
+        }
+    }
+    __syncthreads();
+  }
+  const int y = y0 + ty, x = x0 + 2 * tx;
+  if (y < H && x < W) {
+    float* o = out + (((long)n * P + ph) * P) * plane + (long)y * W + x;
+    const bool two = x + 1 < W;
+    const bool vec = two && ((W & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0);
+#pragma unroll
+    for (int pw = 0; pw < PMAX; ++pw)
+      if (pw < P) {
+        if (vec) {
+          *reinterpret_cast<float2*>(o + (long)pw * plane) = make_float2(acc0[pw], acc1[pw]);
+        } else {
+          o[(long)pw * plane] = acc0[pw];
+          if (two) o[(long)pw * plane + 1] = acc1[pw];
+        }
+      }
+  }
+}
+
 // relu + l2norm over K channels of [B,K,HW] (generic companion of the fused epilogue)
-__global__ void relu_l2norm_kernel(float* __restrict__ x, float* __restrict__ norm_out, int K, long HW, long total) {
-  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const long b = idx / HW, p = idx % HW;
+// block = 32 pixels x 8 channel groups: with one thread per pixel a [2,361,128,128] volume had 32 k threads doing
+// ~1 000 dependent strided accesses each (latency-bound, ~0.5 ms); here the channel loop is split 8 ways and the
+// partial sums meet in shared memory
+__global__ void __launch_bounds__(256)
+relu_l2norm_kernel(float* __restrict__ x, float* __restrict__ norm_out, int K, long HW, long total) {
+  __shared__ float part[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (long base = blockIdx.x * 32l; base < total; base += (long)gridDim.x * 32) {   // block-uniform trip count
+    const long idx = base + tx;
+    const bool ok = idx < total;
+    const long b = ok ? idx / HW : 0, p = ok ? idx % HW : 0;
     float* px = x + b * K * HW + p;
     float ss = 0.f;
-    for (int k = 0; k < K; ++k) {
-      const float v = fmaxf(px[(long)k * HW], 0.f);
-      ss = fmaf(v, v, ss);
+    if (ok)
+      for (int k = ty; k < K; k += 8) {
+        const float v = fmaxf(px[(long)k * HW], 0.f);
+        ss = fmaf(v, v, ss);
+      }
+    part[ty][tx] = ss;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += part[i][tx];
+    const float nrm = fmaxf(sqrtf(tot), 1e-12f);
+    if (ok) {
+      if (norm_out && ty == 0) norm_out[idx] = nrm;
+      for (int k = ty; k < K; k += 8) px[(long)k * HW] = fmaxf(px[(long)k * HW], 0.f) / nrm;
     }
-    const float nrm = fmaxf(sqrtf(ss), 1e-12f);
-    if (norm_out) norm_out[idx] = nrm;
-    for (int k = 0; k < K; ++k) px[(long)k * HW] = fmaxf(px[(long)k * HW], 0.f) / nrm;
+    __syncthreads();
   }
 }
 
@@ -589,12 +696,21 @@ extern "C" int rf_local_corr_fwd(const float* in1, const float* in2, float* out,
       default: return launch_tiled<9>(in1, in2, out, norm_out, B, C, H, W, fuse_relu_l2norm != 0, st);
     }
   }
-  const long total = (long)B * pH * pW * g.oH * g.oW;
-  local_corr_generic_kernel<<<grid_for(total, 256), 256, 0, st>>>(in1, in2, out, g);
-  RF_CHECK_LAUNCH("local_corr_generic_kernel");
+  if (unit && pH == pW && (pH & 1) && pH > 9 && pH <= 33 && (long)B * pH <= 65535) {   // wide odd patches: tiled, one ph per CTA
+    dim3 grid((unsigned)ceil_div(W, LW_TW), (unsigned)ceil_div(H, LW_TH), (unsigned)(B * pH));
+    if (pH <= 19)
+      local_corr_wide_kernel<19><<<grid, 256, 0, st>>>(in1, in2, out, C, H, W, pH);
+    else
+      local_corr_wide_kernel<33><<<grid, 256, 0, st>>>(in1, in2, out, C, H, W, pH);
+    RF_CHECK_LAUNCH("local_corr_wide_kernel");
+  } else {
+    const long total = (long)B * pH * pW * g.oH * g.oW;
+    local_corr_generic_kernel<<<grid_for(total, 256), 256, 0, st>>>(in1, in2, out, g);
+    RF_CHECK_LAUNCH("local_corr_generic_kernel");
+  }
   if (fuse_relu_l2norm) {
     const long npix = (long)B * g.oH * g.oW;
-    relu_l2norm_kernel<<<grid_for(npix, 256), 256, 0, st>>>(out, norm_out, pH * pW, (long)g.oH * g.oW, npix);
+    relu_l2norm_kernel<<<grid_for(npix, 32), 256, 0, st>>>(out, norm_out, pH * pW, (long)g.oH * g.oW, npix);
     RF_CHECK_LAUNCH("relu_l2norm_kernel");
   }
   return RF_OK;

@@ -48,6 +48,9 @@ LC_SPECS = [  # B C H W k P stride pad dil dil_patch
     (1, 5, 9, 11, 3, 5, 2, 1, 1, 2),        # kernel 3, stride 2, pad 1, dilated patch
     (1, 3, 10, 8, 2, 3, 1, 2, 2, 1),
     (1, 1, 1, 4, 1, 9, 1, 0, 1, 1),         # single row
+    (1, 16, 20, 70, 1, 19, 1, 0, 1, 1),     # wide-patch kernel (sweep stress point d = 9), ragged 64-wide tiles
+    (2, 9, 12, 40, 1, 33, 1, 0, 1, 1),      # wide-patch kernel, d = 16, C not a multiple of the chunk
+    (1, 8, 9, 13, 1, 11, 1, 0, 1, 1),       # wide-patch kernel, odd W (scalar stores)
 ]
 
 
@@ -65,6 +68,19 @@ def test_local_corr_fwd_bwd_vs_oracle(spec):
     wa, wb = oracle.local_corr_bwd(a, b, g, k, P, s, pad, dil, dp)
     close(ad.grad, wa, atol=1e-4 * P)
     close(bd.grad, wb, atol=1e-4 * P)
+
+
+@pytest.mark.parametrize("P", [19, 33])
+def test_local_corr_wide_patch_layer_vs_oracle(P):
+    """LocalFeatureCorrelationLayer semantics (ReLU + L2-norm over the P*P displacements) at the sweep's wide
+    patches: the wide-patch kernel + the generic ReLU / L2-norm pass vs the oracle."""
+    torch.manual_seed(P)
+    s, t = unit(torch.randn(2, 32, 24, 72)), unit(torch.randn(2, 32, 24, 72))
+    want = oracle.local_corr_layer(s, t, P)
+    got = ops.local_correlation_relu_l2norm(s.to(DEV), t.to(DEV), P)
+    close(got, want, atol=2e-6)
+    n = got.norm(dim=1)
+    assert bool(((n - 1).abs() < 1e-4).logical_or(n == 0).all())
 
 
 def test_local_corr_golden(golden):
