@@ -293,6 +293,25 @@ def test_upsample_cross_entropy_fwd_bwd(shape, weighted):
         ops.upsample_cross_entropy(lg, tgt.to(DEV)[0], None, 255)   # 2-D target
 
 
+def test_upsample_cross_entropy_golden():
+    """The fused loss tail against the values and gradients the reference's own F.interpolate +
+    models.losses.PixelWeightedCrossEntropyLoss produced (tests/golden/ops_upsample_ce.npz, generated by
+    tests/golden/make_golden_loss.py in the build container).  Same tolerances as the torch comparison above."""
+    import os
+    import numpy as np
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ops_upsample_ce.npz"))
+    for i in range(int(g["ncases"])):
+        lg = torch.from_numpy(g[f"c{i}_logits"]).to(DEV).requires_grad_(True)
+        tg = torch.from_numpy(g[f"c{i}_target"]).to(DEV)
+        w = torch.from_numpy(g[f"c{i}_weight"])
+        got = ops.upsample_cross_entropy(lg, tg, w.to(DEV) if w.numel() else None, 255)
+        want = float(g[f"c{i}_loss"])
+        assert abs(float(got.detach()) - want) <= 1e-5 * max(1.0, abs(want)), (i, float(got.detach()), want)
+        got.backward()
+        g_want = torch.from_numpy(g[f"c{i}_grad"])
+        _close(lg.grad.cpu(), g_want, 1e-4, 1e-5 * float(g_want.abs().max()), "grad_logits case %d" % i)
+
+
 @pytest.mark.parametrize("shape", [(4, 19, 64, 64, 256, 256), (1, 3, 24, 20, 100, 84), (2, 1, 16, 16, 16, 16)])
 def test_upsample_bilinear_f32(shape):
     """Teacher-logit up-sampling vs F.interpolate(mode='bilinear', align_corners=False), fp32: 1e-5."""

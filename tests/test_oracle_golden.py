@@ -68,3 +68,14 @@ def test_exact_transcendentals():
     assert ((got - ref).abs()[ok] / ref[ok]).max() < 3e-7
     x = torch.linspace(0.5, 40, 100001)
     assert (oracle.exact_logf(x).double() - torch.log(x.double())).abs().max() < 5e-7
+
+
+def test_upsample_ce_loss_tail(golden):
+    """oracle.upsample_ce (float64 torch restatement of F.interpolate + PixelWeightedCrossEntropyLoss) against the
+    loss values the reference's own loss class produced (tests/golden/make_golden_loss.py)."""
+    g = golden("ops_upsample_ce")
+    for i in range(int(g["ncases"])):
+        w = T(g[f"c{i}_weight"])
+        got = oracle.upsample_ce(T(g[f"c{i}_logits"]), T(g[f"c{i}_target"]), w if w.numel() else None, 255)
+        want = float(g[f"c{i}_loss"])
+        assert abs(float(got) - want) <= 2e-6 * max(1.0, abs(want)), (i, float(got), want)
