@@ -57,7 +57,14 @@ class PixelWeightedCrossEntropyLoss(nn.Module):
 def _instantiate(args, init):
     import importlib
     module, _, name = init['class_path'].rpartition('.')
-    cls = getattr(importlib.import_module(module), name)
+    try:
+        cls = getattr(importlib.import_module(module), name)
+    except (ImportError, AttributeError):
+        # reference class paths (helpers.metrics.IoU, ...) resolve to this package's class of the same name
+        from . import metrics as _metrics
+        if not hasattr(_metrics, name):
+            raise
+        cls = getattr(_metrics, name)
     args = args if isinstance(args, tuple) else (args,)
     return cls(*args, **init.get('init_args', {}))
 
@@ -96,6 +103,10 @@ class DomainAdaptationSegmentationModel(_Base):
                 p.requires_grad = False
         self.loss = loss
         self.metrics_cfg = metrics
+        from .metrics import MetricCollection
+        mk = lambda split: MetricCollection({'%s_%s_%s' % (split, ds, el['class_path'].split('.')[-1]): _instantiate(tuple(), el)
+                                             for ds, ms in (metrics or {}).get(split, {}).items() for el in ms})
+        self.valid_metrics, self.test_metrics = mk('val'), mk('test')   # reference :92-98
         self.optimizer_init = optimizer_init
         self.lr_scheduler_init = lr_scheduler_init
         self.backbone_lr_factor = backbone_lr_factor
@@ -480,6 +491,39 @@ class DomainAdaptationSegmentationModel(_Base):
         G['n'] += 1
         if not _HAVE_PL:
             self._step += 1
+
+    # ---- evaluation (reference :255-281) -----------------------------------------------------------
+    def _eval_step(self, metrics, split, batch, dataloader_idx):
+        x, y = batch['image'], batch['semantic']
+        with torch.no_grad():
+            y_hat = self.forward(x, out_size=y.shape[-2:])
+        # under Lightning the metric keys are filtered by the dataloader's dataset name; stand-alone every
+        # metric of the split is updated
+        trainer = getattr(self, '_trainer', None) if _HAVE_PL else None
+        src_name = trainer.datamodule.idx_to_name[split][dataloader_idx] if trainer is not None else None
+        for k, m in metrics.items():
+            if src_name is None or src_name in k:
+                m(y_hat, y)
+        return y_hat
+
+    def _eval_epoch_end(self, metrics):
+        out = metrics.compute()
+        metrics.reset()
+        for k, v in out.items():
+            self.log(k, v)
+        return out
+
+    def validation_step(self, batch, batch_idx, dataloader_idx=0):
+        self._eval_step(self.valid_metrics, 'val', batch, dataloader_idx)
+
+    def validation_epoch_end(self, outs=None):
+        return self._eval_epoch_end(self.valid_metrics)
+
+    def test_step(self, batch, batch_idx, dataloader_idx=0):
+        self._eval_step(self.test_metrics, 'test', batch, dataloader_idx)
+
+    def test_epoch_end(self, outs=None):
+        return self._eval_epoch_end(self.test_metrics)
 
     # ---- inference ---------------------------------------------------------------------------------
     def forward(self, x, out_size=None):
