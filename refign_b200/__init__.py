@@ -14,7 +14,7 @@ There is no CPU implementation and no fallback: the operators raise if the CUDA 
 from .alignment_model import AlignmentModel  # noqa: F401
 from .heads import BaseHead, DAFormerHead, SegFormerHead, UAWarpCHead  # noqa: F401
 from .losses import HuberLoss, MultiScaleFlowLoss, WBipathLoss  # noqa: F401
-from .metrics import IoU, MetricCollection  # noqa: F401
+from .metrics import IoU, MetricCollection, SparseEPE  # noqa: F401
 from .mix_transformer import MixVisionTransformer  # noqa: F401
 from .segmentation_model import DomainAdaptationSegmentationModel, PixelWeightedCrossEntropyLoss  # noqa: F401
 from .vgg import VGG  # noqa: F401

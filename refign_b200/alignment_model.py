@@ -7,7 +7,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .matching_utils import estimate_probability_of_confidence_interval_of_mixture_density
-from .segmentation_model import _Base, _HAVE_PL, _alignment_flow
+from .metrics import MetricCollection
+from .segmentation_model import _Base, _HAVE_PL, _alignment_flow, _instantiate
 
 
 class AlignmentModel(_Base):
@@ -26,6 +27,9 @@ class AlignmentModel(_Base):
         self.lr_scheduler_init = lr_scheduler_init
         self.precision = precision
         self._logged = {}
+        mk = lambda split: MetricCollection({'%s_%s_%s' % (split, ds, el['class_path'].split('.')[-1]): _instantiate(tuple(), el)
+                                             for ds, ms in (metrics or {}).get(split, {}).items() for el in ms})
+        self.valid_metrics, self.test_metrics = mk('val'), mk('test')   # reference alignment_model.py:40-46
         self.load_weights(pretrained)
 
     if not _HAVE_PL:
@@ -90,6 +94,37 @@ class AlignmentModel(_Base):
         loss = w_ss * ss_loss + w_us * us_loss
         self.log("train_matching_loss", loss, batch_size=b)
         return loss
+
+    # ---- evaluation (reference alignment_model.py:148-185): sparse EPE / PCK at ground-truth correspondences ----
+    def _eval_step(self, metrics, split, batch, dataloader_idx):
+        images_ref, images_trg = batch['image_ref'], batch['image']
+        h, w = images_ref.shape[-2:]
+        with torch.no_grad():
+            flow, uncert = self.forward(images_trg, images_ref)
+        trainer = getattr(self, '_trainer', None) if _HAVE_PL else None
+        src_name = trainer.datamodule.idx_to_name[split][dataloader_idx] if trainer is not None else None
+        for k, m in metrics.items():
+            if src_name is None or src_name in k:
+                m(flow, batch['corr_pts_ref'], batch['corr_pts'], (h, w), uncert)
+
+    def _eval_epoch_end(self, metrics):
+        out = metrics.compute()
+        metrics.reset()
+        for k, v in out.items():
+            self.log(k, v)
+        return out
+
+    def validation_step(self, batch, batch_idx, dataloader_idx=0):
+        self._eval_step(self.valid_metrics, 'val', batch, dataloader_idx)
+
+    def validation_epoch_end(self, outs=None):
+        return self._eval_epoch_end(self.valid_metrics)
+
+    def test_step(self, batch, batch_idx, dataloader_idx=0):
+        self._eval_step(self.test_metrics, 'test', batch, dataloader_idx)
+
+    def test_epoch_end(self, outs=None):
+        return self._eval_epoch_end(self.test_metrics)
 
     @staticmethod
     @torch.no_grad()

@@ -89,6 +89,88 @@ def jaccard_from_confmat(confmat, average='macro', absent_score=0.0, over_presen
     return (weights * scores_sel).sum()
 
 
+class SparseEPE(nn.Module):
+    """Sparse end-point error of a dense flow at ground-truth correspondences (reference helpers/metrics.py:36-251):
+    AEPE (mean over samples of the per-sample mean EPE), PCK at 1 / 3 / 5 / 10 px (over all valid correspondences)
+    and, with ``uncertainty_estimation``, the area under the sparsification-error curve of the EPE (AUSE).
+    Correspondences whose rounded coordinates fall outside the image in either view are dropped.  The EPE / PCK part
+    runs without a device-to-host synchronisation (masked sums instead of boolean-mask gathers); the AUSE part keeps
+    the reference's quantile subsets (evaluation-only, synchronising)."""
+
+    def __init__(self, uncertainty_estimation=False, compute_on_step=False, **_unused):
+        super().__init__()
+        self.uncertainty_estimation = uncertainty_estimation
+        self.compute_on_step = compute_on_step
+        for name in ('AEPE', 'PCK_1', 'PCK_3', 'PCK_5', 'PCK_10', 'AUSE_AEPE'):
+            self.register_buffer(name, torch.zeros((), dtype=torch.double), persistent=False)
+        self.register_buffer('nbr_valid_corr', torch.zeros((), dtype=torch.long), persistent=False)
+        self.register_buffer('nbr_samples', torch.zeros((), dtype=torch.long), persistent=False)
+
+    def reset(self):
+        for b in self.buffers():
+            b.zero_()
+
+    @torch.no_grad()
+    def update(self, t_s_flow, corr_pts_s, corr_pts_t, out_size, uncertainty_est=None):
+        h, w = out_size
+        assert tuple(t_s_flow.shape[-2:]) == (h, w), "resize the flow to out_size first"
+        for bb in range(t_s_flow.shape[0]):
+            ps, pt = corr_pts_s[bb].to(t_s_flow.device), corr_pts_t[bb].to(t_s_flow.device)
+            if ps.numel() == 0:
+                continue
+            x_s, y_s, x_t, y_t = ps[:, 0], ps[:, 1], pt[:, 0], pt[:, 1]
+            rx_s, ry_s, rx_t, ry_t = torch.round(x_s), torch.round(y_s), torch.round(x_t), torch.round(y_t)
+            valid = ((rx_s >= 0) & (rx_s < w) & (ry_s >= 0) & (ry_s < h) & (rx_t >= 0) & (rx_t < w) & (ry_t >= 0)
+                     & (ry_t < h))
+            yi, xi = ry_t.long().clamp(0, h - 1), rx_t.long().clamp(0, w - 1)
+            ex = (x_s - x_t) - t_s_flow[bb, 0, yi, xi]
+            ey = (y_s - y_t) - t_s_flow[bb, 1, yi, xi]
+            epe = (ex ** 2 + ey ** 2) ** 0.5
+            vf = valid.to(epe.dtype)
+            n = valid.sum()
+            has = n > 0
+            self.AEPE += torch.where(has, (epe * vf).sum() / n.clamp(min=1), torch.zeros_like(n, dtype=epe.dtype)).double()
+            for k, name in ((1.0, 'PCK_1'), (3.0, 'PCK_3'), (5.0, 'PCK_5'), (10.0, 'PCK_10')):
+                getattr(self, name).add_(((epe <= k) & valid).sum().double())
+            self.nbr_valid_corr += n
+            self.nbr_samples += has.long()
+            if self.uncertainty_estimation and bool(has):
+                gt = torch.stack([(x_s - x_t)[valid], (y_s - y_t)[valid]], dim=1)
+                est = torch.stack([t_s_flow[bb, 0, yi, xi][valid], t_s_flow[bb, 1, yi, xi][valid]], dim=1)
+                self.AUSE_AEPE += ause_epe(gt, est, uncertainty_est[bb, 0, yi, xi][valid]).double()
+
+    def forward(self, *args, **kwargs):
+        self.update(*args, **kwargs)
+        return self.compute() if self.compute_on_step else None
+
+    def compute(self):
+        out = {'AEPE': self.AEPE / self.nbr_samples.double(),
+               'PCK_1': self.PCK_1 / self.nbr_valid_corr.double(),
+               'PCK_3': (self.PCK_3 / self.nbr_valid_corr.float()),
+               'PCK_5': self.PCK_5 / self.nbr_valid_corr.double(),
+               'PCK_10': (self.PCK_10 / self.nbr_valid_corr.float())}
+        if self.uncertainty_estimation:
+            out['AUSE_AEPE'] = self.AUSE_AEPE / self.nbr_samples.double()
+        return out
+
+
+def ause_epe(gt, pred, uncert, intervals=50):
+    """Area between the sparsification curve of the predicted uncertainty and the oracle curve (pixels removed by
+    decreasing true error), both normalised by the oracle maximum (reference helpers/metrics.py:131-196, EPE only)."""
+    err = torch.linalg.norm(gt - pred, ord=2, dim=1)
+    quants = [1.0 / intervals * t for t in range(intervals)]
+    plotx = torch.tensor([1.0 / intervals * t for t in range(intervals + 1)], device=gt.device)
+
+    def curve(score):   # keep the elements whose (negated) score is at or above the q-quantile: drops the worst first
+        neg = -score.float()
+        pts = [err[neg.ge(torch.quantile(neg, q))].mean() for q in quants]
+        return torch.stack(pts + [torch.zeros((), device=gt.device)])
+
+    sparse, oracle = curve(uncert), curve(err)
+    mmax = oracle.max() + 1e-6
+    return torch.abs(torch.trapz(sparse / mmax, x=plotx) - torch.trapz(oracle / mmax, x=plotx))
+
+
 class MetricCollection(nn.ModuleDict):
     """Minimal stand-in for the reference's ``MyMetricCollection`` (helpers/metrics.py:13-33): a dict of metrics whose
     ``compute`` flattens dict-valued results as ``<metric>_<key>``."""

@@ -83,3 +83,57 @@ def test_validation_step_accumulates_iou():
     from refign_b200.metrics import jaccard_from_confmat
     assert torch.allclose(out['val_ACDC_IoU'], jaccard_from_confmat(total)) and 'val_ACDC_IoU' in model._logged
     assert int(model.valid_metrics['val_ACDC_IoU'].confmat.sum()) == 0
+
+
+@pytest.mark.parametrize("uncertainty", [False, True])
+def test_sparse_epe_matches_reference(uncertainty):
+    """SparseEPE (AEPE, PCK, AUSE) vs the reference class: its torchmetrics states are set by hand on an instance
+    built behind the refshim stub (``add_state`` is a no-op there), its own ``update`` / ``compute`` run unchanged."""
+    refshim.install()
+    from helpers.metrics import SparseEPE as RefEPE
+    from refign_b200.metrics import SparseEPE
+    ref = RefEPE(uncertainty_estimation=uncertainty)
+    for name in ("AEPE", "PCK_1", "PCK_3", "PCK_5", "PCK_10", "AUSE_AEPE"):
+        setattr(ref, name, torch.tensor(0, dtype=torch.double))
+    ref.nbr_valid_corr, ref.nbr_samples = torch.tensor(0), torch.tensor(0)
+    ref.uncertainty_estimation = uncertainty
+    mine = SparseEPE(uncertainty_estimation=uncertainty)
+    g = torch.Generator().manual_seed(5)
+    h, w = 40, 56
+    for step in range(2):
+        flow = torch.randn(3, 2, h, w, generator=g) * 4
+        unc = torch.rand(3, 1, h, w, generator=g)
+        pts_t = [torch.rand(n, 2, generator=g) * torch.tensor([w + 6.0, h + 6.0]) - 3.0 for n in (60, 1, 35)]
+        pts_s = [p + torch.randn(p.shape, generator=g) * 3 for p in pts_t]
+        pts_t[1] = torch.tensor([[-5.0, 2.0]])          # a sample without any valid correspondence
+        pts_s[1] = torch.tensor([[3.0, 2.0]])
+        ref.update(flow, pts_s, pts_t, (h, w), unc)
+        mine(flow, pts_s, pts_t, (h, w), unc)
+    want, got = ref.compute(), mine.compute()
+    assert set(want) == set(got)
+    for k in want:
+        assert torch.allclose(got[k].double(), want[k].double(), rtol=1e-6, atol=1e-9), (k, got[k], want[k])
+    assert int(mine.nbr_samples) == 4
+
+
+def test_alignment_validation_step_runs_sparse_epe():
+    """AlignmentModel.validation_step / validation_epoch_end (reference alignment_model.py:148-165) with the reference's
+    metric config (configs/megadepth/*.yaml: helpers.metrics.SparseEPE with uncertainty estimation)."""
+    import refign_b200 as P
+    torch.manual_seed(0)
+    metrics = {'val': {'MegaDepth': [{'class_path': 'reference_helpers.metrics.SparseEPE',
+                                      'init_args': {'uncertainty_estimation': True, 'compute_on_step': False}}]}}
+    model = P.AlignmentModel(None, None, P.VGG('vgg16', out_indices=[2, 3, 4]),
+                             P.UAWarpCHead(in_index=[0, 1], input_transform='multiple_select', estimate_uncertainty=True),
+                             metrics=metrics).eval()
+    assert list(model.valid_metrics.keys()) == ['val_MegaDepth_SparseEPE']
+    g = torch.Generator().manual_seed(1)
+    trg = torch.randn(2, 3, 64, 64, generator=g)
+    pts = [torch.rand(20, 2, generator=g) * 60 + 2 for _ in range(2)]
+    batch = {'image': trg, 'image_ref': trg.roll((2, -3), (2, 3)), 'corr_pts': pts,
+             'corr_pts_ref': [p + torch.tensor([-3.0, 2.0]) for p in pts]}
+    with cpu_ops():
+        model.validation_step(batch, 0)
+        out = model.validation_epoch_end()
+    assert set(out) == {'val_MegaDepth_SparseEPE_' + k for k in ('AEPE', 'PCK_1', 'PCK_3', 'PCK_5', 'PCK_10', 'AUSE_AEPE')}
+    assert all(bool(torch.isfinite(v)) for v in out.values()) and float(out['val_MegaDepth_SparseEPE_AEPE']) > 0
