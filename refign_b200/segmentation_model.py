@@ -60,11 +60,15 @@ def _instantiate(args, init):
     try:
         cls = getattr(importlib.import_module(module), name)
     except (ImportError, AttributeError):
-        # reference class paths (helpers.metrics.IoU, ...) resolve to this package's class of the same name
-        from . import metrics as _metrics
-        if not hasattr(_metrics, name):
+        # reference class paths (helpers.metrics.IoU, helpers.lr_scheduler.LinearWarmupPolynomialLR, ...) resolve to
+        # this package's class of the same name
+        from . import lr_scheduler as _sched, metrics as _metrics
+        for mod in (_metrics, _sched):
+            if hasattr(mod, name):
+                cls = getattr(mod, name)
+                break
+        else:
             raise
-        cls = getattr(_metrics, name)
     args = args if isinstance(args, tuple) else (args,)
     return cls(*args, **init.get('init_args', {}))
 

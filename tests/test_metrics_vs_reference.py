@@ -137,3 +137,29 @@ def test_alignment_validation_step_runs_sparse_epe():
         out = model.validation_epoch_end()
     assert set(out) == {'val_MegaDepth_SparseEPE_' + k for k in ('AEPE', 'PCK_1', 'PCK_3', 'PCK_5', 'PCK_10', 'AUSE_AEPE')}
     assert all(bool(torch.isfinite(v)) for v in out.values()) and float(out['val_MegaDepth_SparseEPE_AEPE']) > 0
+
+
+def test_lr_scheduler_matches_reference():
+    """LinearWarmupPolynomialLR (helpers/lr_scheduler.py) step by step, and the class-path fallback of
+    configure_optimizers when the reference's ``helpers`` package is not importable."""
+    refshim.install()
+    from helpers.lr_scheduler import LinearWarmupPolynomialLR as RefSch
+    from refign_b200.lr_scheduler import LinearWarmupPolynomialLR
+    from refign_b200.segmentation_model import _instantiate
+    kw = dict(max_steps=40, warmup_iters=7, warmup_ratio=1e-6, power=0.9, min_lr=1e-7)
+
+    def run(cls):
+        p = [torch.nn.Parameter(torch.zeros(1)), torch.nn.Parameter(torch.zeros(1))]
+        opt = torch.optim.AdamW([{'params': p[:1], 'lr': 6e-4}, {'params': p[1:], 'lr': 6e-5}])
+        sch = cls(opt, **kw) if isinstance(cls, type) else cls(opt)
+        lrs = []
+        for _ in range(40):
+            lrs.append([g['lr'] for g in opt.param_groups])
+            opt.step()
+            sch.step()
+        return torch.tensor(lrs)
+    want = run(RefSch)
+    assert torch.allclose(run(LinearWarmupPolynomialLR), want, rtol=1e-12, atol=0)
+    via_path = lambda opt: _instantiate(opt, {'class_path': 'reference_helpers.lr_scheduler.LinearWarmupPolynomialLR',
+                                              'init_args': kw})
+    assert torch.allclose(run(via_path), want, rtol=1e-12, atol=0)
