@@ -13,6 +13,12 @@ the path explicitly.
   run follows the same crops);
 * teacher / evaluation: overlapping sliding-window detail crops (stride = half a crop) whose logits are
   averaged where they overlap.
+
+``DeviceBox`` (opt-in, ``DomainAdaptationSegmentationModel.hrda_device_crop``): the student's crop ORIGIN lives in a
+device tensor and every use of the box (image crop, attention mask, insertion of the detail logits, label / weight
+crop of the loss) is an ``index_select`` / ``index_copy`` with device index vectors instead of host-int slicing --
+same values bit for bit (tests/test_hrda_vs_reference.py), but no host integer is baked into the launch sequence, which
+is what a CUDA-graph replay of the HRDA step needs (the host draws the box and copies two integers before the replay).
 """
 import random
 
@@ -67,7 +73,36 @@ def crop(t, box):
     return t[..., y1:y2, x1:x2]
 
 
-def multires_features(backbone, x, head_os, random_crop):
+class DeviceBox:
+    """Detail-crop box with a static size (host ints) and an origin ``[y, x]`` held in an int64 device tensor."""
+
+    def __init__(self, origin, crop_h, crop_w):
+        self.origin, self.h, self.w = origin, int(crop_h), int(crop_w)
+
+    def indices(self, scale=1):
+        """Row / column index vectors of the box at 1/scale resolution (origin and size must divide)."""
+        dev = self.origin.device
+        o = self.origin if scale == 1 else torch.div(self.origin, int(scale), rounding_mode='floor')
+        return (o[0] + torch.arange(self.h // int(scale), device=dev), o[1] + torch.arange(self.w // int(scale), device=dev))
+
+    def crop(self, t, scale=1):
+        yi, xi = self.indices(scale)
+        return t.index_select(-2, yi).index_select(-1, xi)
+
+    def insert(self, full_shape, patch, scale):
+        """zeros(full_shape) with ``patch`` written at the box (1/scale resolution); differentiable w.r.t. patch."""
+        yi, xi = self.indices(scale)
+        rows = patch.new_zeros(tuple(full_shape[:-2]) + (patch.shape[-2], full_shape[-1])).index_copy(-1, xi, patch)
+        return patch.new_zeros(tuple(full_shape)).index_copy(-2, yi, rows)
+
+    def mask(self, h, w, scale, dtype):
+        yi, xi = self.indices(scale)
+        my = torch.zeros(h, device=yi.device, dtype=dtype).index_fill(0, yi, 1.0)
+        mx = torch.zeros(w, device=xi.device, dtype=dtype).index_fill(0, xi, 1.0)
+        return my.view(1, 1, h, 1) * mx.view(1, 1, 1, w)
+
+
+def multires_features(backbone, x, head_os, random_crop, box=None):
     """Context + detail features in one backbone pass (reference hrda.py:92-130).
 
     Returns ``(lr_feats, hr_feats, boxes)``: per-stage feature tuples of the half-resolution image
@@ -75,11 +110,12 @@ def multires_features(backbone, x, head_os, random_crop):
     lr_x = _half(x)
     ch, cw = lr_x.shape[-2:]
     H, W = x.shape[-2:]
-    if random_crop:
-        boxes = [random_detail_box(H, W, ch, cw, head_os * 2.0)]
+    if random_crop and box is not None:       # device-resident origin (see DeviceBox)
+        boxes = [box]
+        hr_x = box.crop(x)
     else:
-        boxes = sliding_boxes(H, W, ch, cw)
-    hr_x = torch.cat([crop(x, b) for b in boxes], dim=0)
+        boxes = [random_detail_box(H, W, ch, cw, head_os * 2.0)] if random_crop else sliding_boxes(H, W, ch, cw)
+        hr_x = torch.cat([crop(x, b) for b in boxes], dim=0)
     feats = backbone(torch.cat((lr_x, hr_x)))
     lr_bs, hr_bs = lr_x.shape[0], hr_x.shape[0]
     lr_feats, hr_feats = zip(*(torch.split(f, [lr_bs, hr_bs]) for f in feats))
@@ -118,6 +154,12 @@ def fuse_scales(head, scale_attention, feats, head_os, random_crop):
     both = head([torch.cat(pair) for pair in zip(lr_feats, hr_feats)])
     lr_seg, hr_seg = torch.split(both, [lr_bs, hr_bs])
     lr_seg, hr_seg, att = lr_seg.float(), hr_seg.float(), att.float()
+    if random_crop and isinstance(boxes[0], DeviceBox):
+        box = boxes[0]
+        att = att * box.mask(lr_seg.shape[-2], lr_seg.shape[-1], 2 * head_os, lr_seg.dtype)
+        up_lr = _double((1 - att) * lr_seg)
+        inserted = box.insert(up_lr.shape, hr_seg, head_os)
+        return _double(att) * inserted + up_lr, hr_seg, box
     if random_crop:
         box = boxes[0]
         # attention only acts where detail logits exist

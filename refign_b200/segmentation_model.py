@@ -149,6 +149,8 @@ class DomainAdaptationSegmentationModel(_Base):
         self.fuse_source_backward = True      # one backward for loss_src + feature distance (see _step_part_a)
         self.concurrent_branches = True       # teacher / alignment branches on side streams (see _fork_target_branches)
         self.fused_loss = True                # bilinear up-sampling fused into the cross-entropy (ops.upsample_cross_entropy)
+        self.hrda_device_crop = False         # HRDA detail-crop origin in a device tensor (hrda.DeviceBox): graph-capturable
+        self._hrda_origin = None
         self._side_streams = None
         self.load_weights(pretrained)
 
@@ -366,9 +368,23 @@ class DomainAdaptationSegmentationModel(_Base):
         if not self.use_hrda:
             feats = self.backbone(x)
             return feats, self.head(feats)
-        mf = hrda.multires_features(self.backbone, x, self.hrda_output_stride, random_crop=self.backbone.training)
+        mf = hrda.multires_features(self.backbone, x, self.hrda_output_stride, random_crop=self.backbone.training,
+                                    box=self._draw_device_box(x) if self.backbone.training else None)
         return mf[0], hrda.fuse_scales(self.head, self.hrda_scale_attention, mf, self.hrda_output_stride,
                                        random_crop=self.head.training)
+
+    def _draw_device_box(self, x):
+        """``hrda_device_crop``: the same host draws as ``hrda.random_detail_box``, copied into a persistent device
+        tensor (one slot per student forward of the step would be needed under CUDA graphs; eager use overwrites)."""
+        H, W = x.shape[-2:]
+        os2 = 2 * self.hrda_output_stride
+        if not self.hrda_device_crop or H % (2 * os2) or W % (2 * os2):
+            return None
+        y1, _, x1, _ = hrda.random_detail_box(H, W, H // 2, W // 2, float(os2))
+        if self._hrda_origin is None or self._hrda_origin.device != x.device:
+            self._hrda_origin = torch.zeros(2, dtype=torch.long, device=x.device)
+        self._hrda_origin.copy_(torch.tensor([y1, x1], dtype=torch.long), non_blocking=True)
+        return hrda.DeviceBox(self._hrda_origin.clone(), H // 2, W // 2)
 
     def _teacher_forward(self, x):
         if not self.use_hrda:
@@ -383,11 +399,14 @@ class DomainAdaptationSegmentationModel(_Base):
         if not (self.use_hrda and isinstance(out, tuple)):
             return self._upsampled_loss(out, target, size, pixel_weight)
         logits, hr_logits, box = out
-        y1, y2, x1, x2 = box
-        hr_weight = None if pixel_weight is None else hrda.crop(pixel_weight, box).contiguous()
+        if isinstance(box, hrda.DeviceBox):
+            crop_fn, crop_size = box.crop, (box.h, box.w)
+        else:
+            y1, y2, x1, x2 = box
+            crop_fn, crop_size = (lambda t: hrda.crop(t, box).contiguous()), (y2 - y1, x2 - x1)
+        hr_weight = None if pixel_weight is None else crop_fn(pixel_weight)
         return ((1 - self.hr_loss_weight) * self._upsampled_loss(logits, target, size, pixel_weight)
-                + self.hr_loss_weight * self._upsampled_loss(hr_logits, hrda.crop(target, box).contiguous(),
-                                                             (y2 - y1, x2 - x1), hr_weight))
+                + self.hr_loss_weight * self._upsampled_loss(hr_logits, crop_fn(target), crop_size, hr_weight))
 
     def _upsample_logits(self, logits, size):
         """F.interpolate(logits.float(), size, 'bilinear', align_corners=False) of no-grad (teacher) logits."""

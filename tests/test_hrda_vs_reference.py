@@ -196,3 +196,44 @@ def test_slide_inference_matches_reference(ref):
         close(m(x), r(x))
         m.inference_batched_slide = r.inference_batched_slide = False
         close(m(x), r(x))
+
+
+def test_device_box_path_is_bitwise_identical(ref):
+    """``hrda_device_crop``: crop origin in a device tensor, every use of the box an index_select / index_copy --
+    same crops, fused logits, losses and gradients, bit for bit, as the host-int slicing path."""
+    from refign_b200 import hrda
+    _, m = _models(ref)
+    m.train()
+    torch.manual_seed(9)
+    x = torch.randn(2, 3, 128, 128)
+    gt = torch.randint(0, 19, (2, 128, 128))
+    gt[:, :3] = 255
+    w = torch.rand(2, 128, 128)
+    outs = []
+    for flag in (False, True):
+        m.hrda_device_crop = flag
+        m.zero_grad()
+        random.seed(11)
+        feats, out = m._student_forward(x)
+        assert isinstance(out[2], hrda.DeviceBox) == flag
+        loss = m._student_loss(out, gt, (128, 128), w)
+        loss.backward()
+        box = out[2]
+        origin = tuple(int(v) for v in box.origin) if flag else (box[0], box[2])
+        outs.append((out[0].detach().clone(), out[1].detach().clone(), loss.detach().clone(), origin,
+                     [p.grad.clone() for p in m.head.parameters()] + [p.grad.clone() for p in m.backbone.parameters()]))
+    (l0, h0, s0, o0, g0), (l1, h1, s1, o1, g1) = outs
+    assert o0 == o1 and o0[0] % 8 == 0 and o0[1] % 8 == 0
+    assert torch.equal(l0, l1) and torch.equal(h0, h1) and torch.equal(s0, s1)
+    assert all(torch.equal(a, b) for a, b in zip(g0, g1))
+    # primitives against plain slicing
+    box = hrda.DeviceBox(torch.tensor([16, 40]), 64, 48)
+    t = torch.randn(2, 5, 128, 128)
+    assert torch.equal(box.crop(t), t[..., 16:80, 40:88]) and torch.equal(box.crop(t[..., ::4, ::4], 4), t[..., ::4, ::4][..., 4:20, 10:22])
+    patch = torch.randn(2, 5, 16, 12)
+    want = torch.zeros(2, 5, 32, 32)
+    want[..., 4:20, 10:22] = patch
+    assert torch.equal(box.insert((2, 5, 32, 32), patch, 4), want)
+    mk = torch.zeros(1, 1, 16, 16)
+    mk[..., 2:10, 5:11] = 1
+    assert torch.equal(box.mask(16, 16, 8, torch.float32), mk)
