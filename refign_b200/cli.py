@@ -37,11 +37,10 @@ def resolve_class(class_path):
         for mod in (metrics, lr_scheduler):
             if hasattr(mod, name):
                 return getattr(mod, name)
-    try:
-        return getattr(importlib.import_module(module), name)
-    except (ImportError, AttributeError) as e:
+    if root in ('models', 'helpers'):   # never fall through to the reference's own modules, even if importable
         raise ImportError("class_path '%s' has no counterpart in refign_b200 (outside the hot-path scope of SURVEY 8, "
-                          "e.g. the DeepLabv2 / ResNet variant) and is not importable as written" % class_path) from e
+                          "e.g. the DeepLabv2 / ResNet variant)" % class_path)
+    return getattr(importlib.import_module(module), name)
 
 
 def build(node, no_pretrained=False):
@@ -56,6 +55,23 @@ def build(node, no_pretrained=False):
     return cls(**kwargs)
 
 
+def _map_class_paths(obj):
+    """Rewrite the reference's ``helpers.metrics.*`` / ``helpers.lr_scheduler.*`` class paths inside dict-typed
+    arguments (``metrics``, ``lr_scheduler_init``) to this package's modules, so that the model's own
+    ``instantiate`` call builds these classes even when the reference happens to be importable."""
+    if isinstance(obj, dict):
+        out = {k: _map_class_paths(v) for k, v in obj.items()}
+        cp = out.get('class_path')
+        if isinstance(cp, str):
+            for old, new in (('helpers.metrics.', 'refign_b200.metrics.'), ('helpers.lr_scheduler.', 'refign_b200.lr_scheduler.')):
+                if cp.startswith(old):
+                    out['class_path'] = new + cp[len(old):]
+        return out
+    if isinstance(obj, list):
+        return [_map_class_paths(v) for v in obj]
+    return obj
+
+
 def model_from_config(cfg, no_pretrained=False, **overrides):
     """The model of a reference YAML (dict or path) with the CLI's optimizer / lr_scheduler links applied."""
     if isinstance(cfg, str):
@@ -66,7 +82,9 @@ def model_from_config(cfg, no_pretrained=False, **overrides):
     if 'optimizer' in cfg:
         node['init_args']['optimizer_init'] = cfg['optimizer']
     if 'lr_scheduler' in cfg:
-        node['init_args']['lr_scheduler_init'] = cfg['lr_scheduler']
+        node['init_args']['lr_scheduler_init'] = _map_class_paths(cfg['lr_scheduler'])
+    if 'metrics' in node['init_args']:
+        node['init_args']['metrics'] = _map_class_paths(node['init_args']['metrics'])
     node['init_args'].update(overrides)
     return build(node, no_pretrained), cfg
 

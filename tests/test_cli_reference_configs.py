@@ -40,7 +40,9 @@ def test_reference_configs_instantiate(rel, kind, params, hrda):
     assert isinstance(model.backbone, P.MixVisionTransformer) and isinstance(model.head, P.DAFormerHead)
     assert isinstance(model.alignment_head, P.UAWarpCHead) and isinstance(model.loss, P.PixelWeightedCrossEntropyLoss)
     assert (model.hrda_scale_attention is not None) == bool(hrda)
-    assert model.optimizer_init == cfg["optimizer"] and model.lr_scheduler_init == cfg["lr_scheduler"]
+    assert model.optimizer_init == cfg["optimizer"]
+    assert model.lr_scheduler_init["init_args"] == cfg["lr_scheduler"]["init_args"]
+    assert model.lr_scheduler_init["class_path"] == "refign_b200.lr_scheduler.LinearWarmupPolynomialLR"
     assert all(isinstance(m, P.IoU) and m.ignore_index == 255 for m in model.valid_metrics.values())
     assert cli.crop_size_from_config(cfg) == (1024 if hrda else 512)
 
