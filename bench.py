@@ -200,6 +200,88 @@ def corr_volume_sweep(dev, hbm):
     return out
 
 
+def corr_volume_points(dev, hbm):
+    """The two headline points of the sweep, timed on THIS rank (used at N > 1, where every rank runs its own feature
+    pairs -- the sweep has no exchange step): local 9x9 at 2x256^2 and the global 128^2 x 128^2 volume."""
+    import torch
+    from refign_b200 import ops
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def med(fn, iters=7):
+        for _ in range(2):
+            fn()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    unit = lambda x: torch.nn.functional.normalize(x, p=2, dim=1)
+    g = torch.Generator(device=dev).manual_seed(7)
+    out = []
+    a, b = (unit(torch.randn(2, 128, 256, 256, device=dev, generator=g)) for _ in range(2))
+    out.append({"op": "local_9x9+relu+l2norm", "shape": [2, 128, 256, 256], "bytes": 4 * 2 * 256 * 256 * (2 * 128 + 81),
+                "sec": med(lambda: ops.local_correlation_relu_l2norm(b, a, 9))})
+    a, b = (unit(torch.randn(1, 128, 128, 128, device=dev, generator=g)) for _ in range(2))
+    n = 128 * 128
+    out.append({"op": "global+mutual_matching+relu+l2norm", "shape": [1, 128, 128, 128], "bytes": 4 * (128 * 2 * n + n * n),
+                "sec": med(lambda: ops.global_correlation(a, b))})
+    return out
+
+
+def aggregate_corr_points(per_rank, hbm):
+    """Whole-job correlation-volume throughput from the per-rank timings of the same points: all ranks run
+    concurrently, so the aggregate is (sum of the bytes) / (slowest rank's time)."""
+    out = []
+    for i, p0 in enumerate(per_rank[0]):
+        secs = [r[i]["sec"] for r in per_rank]
+        gbps = sum(r[i]["bytes"] for r in per_rank) / max(secs) / 1e9
+        out.append({"op": p0["op"], "shape_per_gpu": p0["shape"], "n_gpus": len(per_rank), "us_max_over_ranks": round(max(secs) * 1e6, 1),
+                    "GBps_aggregate": round(gbps, 1), "frac_hbm_per_gpu": round(gbps / len(per_rank) / hbm, 4)})
+    return out
+
+
+def corr_volume_multi(dev, hbm, rank, world, barrier, timeout_s=90.0):
+    """N > 1: every rank times the headline points on its own GPU at the same time (barrier first) and leaves its
+    numbers in a file of the job's scratch directory; rank 0 collects them.  Deliberately NO collective: a rank that
+    fails here only makes the extra `corr_volume` entry incomplete, it cannot hang the job."""
+    import tempfile
+    job = "%s_%s" % (os.environ.get("MASTER_PORT", "0"), os.environ.get("TORCHELASTIC_RUN_ID", "run"))
+    path = lambda r: os.path.join(tempfile.gettempdir(), "refign_b200_corr_%s_rank%d.json" % (job, r))
+    try:
+        if os.path.exists(path(rank)):
+            os.remove(path(rank))
+        barrier()
+        mine = corr_volume_points(dev, hbm)
+        with open(path(rank) + ".tmp", "w") as f:
+            json.dump(mine, f)
+        os.replace(path(rank) + ".tmp", path(rank))
+    except Exception as e:  # noqa: BLE001 -- an optional extra of the line, never fatal
+        sys.stderr.write("corr_volume_multi: rank %d failed: %r\n" % (rank, e))
+    if rank != 0:
+        return None
+    per_rank, t0 = [], time.perf_counter()
+    for r in range(world):
+        while not os.path.exists(path(r)) and time.perf_counter() - t0 < timeout_s:
+            time.sleep(0.05)
+        if not os.path.exists(path(r)):
+            return None
+        with open(path(r)) as f:
+            per_rank.append(json.load(f))
+    for r in range(world):
+        try:
+            os.remove(path(r))
+        except OSError:
+            pass
+    return aggregate_corr_points(per_rank, hbm)
+
+
 def cpu_reference_step(size, model_type, steps, warmup):
     """The CPU oracle port of the train step on the host cores: returns (pairs/s scaled to the 1024^2
     workload by pixel count, seconds per CPU step, cores, sample description)."""
@@ -343,10 +425,13 @@ def main():
             barrier()
             os._exit(0)
 
+    hbm, tf, which = peaks()
+    corr_multi = None
+    if world > 1 and not args.no_corr_sweep:   # EVERY rank takes part (per-rank replicas; rank 0 collects the files)
+        corr_multi = corr_volume_multi(dev, hbm, rank, world, barrier)
     if rank != 0:
         finish()
         return
-    hbm, tf, which = peaks()
     # dominant own kernel by device time inside the timed region
     roof = None
     if kern:
@@ -377,6 +462,8 @@ def main():
         del model
         torch.cuda.empty_cache()
         corr = corr_volume_sweep(dev, hbm)
+    elif world > 1:
+        corr = corr_multi
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         sec, cores = cpu_reference_step(args.cpu_size, args.model, 1, 1)

@@ -39,3 +39,32 @@ def test_two_gpu_line_is_the_aggregate():
     assert d2["n_gpus"] == 2 and d2["config"]["global_batch_pairs"] == 2 * d1["config"]["global_batch_pairs"]
     assert abs(d2["value"] - d2["config"]["global_batch_pairs"] / (d2["ms_per_step"] * 1e-3)) <= 1e-6 * d2["value"]
     assert d2["value"] > 1.8 * d1["value"]     # weak scaling over NVLink: > 90 % at N = 2
+
+
+def test_multi_gpu_corr_sweep_collects_per_rank_files(monkeypatch):
+    """N > 1 correlation sweep of bench.py: per-rank replicas, numbers exchanged through files (no collective);
+    aggregate = sum of bytes / slowest rank.  A missing rank yields None instead of hanging."""
+    import bench
+    calls = {"barrier": 0}
+    fake = {0: [{"op": "local", "shape": [2, 128, 256, 256], "bytes": 100e6, "sec": 1e-4},
+                {"op": "global", "shape": [1, 128, 128, 128], "bytes": 1e9, "sec": 5e-4}],
+            1: [{"op": "local", "shape": [2, 128, 256, 256], "bytes": 100e6, "sec": 2e-4},
+                {"op": "global", "shape": [1, 128, 128, 128], "bytes": 1e9, "sec": 4e-4}]}
+    monkeypatch.setenv("MASTER_PORT", "45678")
+    monkeypatch.setenv("TORCHELASTIC_RUN_ID", "pytest")
+    barrier = lambda: calls.__setitem__("barrier", calls["barrier"] + 1)
+    for rank in (1, 0):
+        monkeypatch.setattr(bench, "corr_volume_points", lambda dev, hbm, r=rank: fake[r])
+        out = bench.corr_volume_multi("cpu", 6500.0, rank, 2, barrier, timeout_s=5.0)
+        assert (out is None) == (rank != 0)
+    assert calls["barrier"] == 2 and [o["op"] for o in out] == ["local", "global"]
+    assert out[0]["n_gpus"] == 2 and abs(out[0]["GBps_aggregate"] - 200e6 / 2e-4 / 1e9) < 0.1
+    assert abs(out[1]["GBps_aggregate"] - 2e9 / 5e-4 / 1e9) < 0.1 and out[1]["us_max_over_ranks"] == 500.0
+    # rank 1 never reports: rank 0 gives up after the timeout
+    monkeypatch.setattr(bench, "corr_volume_points", lambda dev, hbm: fake[0])
+    assert bench.corr_volume_multi("cpu", 6500.0, 0, 2, barrier, timeout_s=0.3) is None
+    # a rank whose sweep raises still returns (and would go on to the final barrier)
+    def boom(dev, hbm):
+        raise RuntimeError("kernel failed")
+    monkeypatch.setattr(bench, "corr_volume_points", boom)
+    assert bench.corr_volume_multi("cpu", 6500.0, 1, 2, barrier, timeout_s=0.3) is None
