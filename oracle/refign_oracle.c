@@ -531,3 +531,75 @@ void orc_expf_array(const float *x, float *y, long n) {
 void orc_logf_array(const float *x, float *y, long n) {
   for (long i = 0; i < n; ++i) y[i] = orc_log_pos(x[i]);
 }
+
+/* ---------------------------------------------------------------------------
+ * Loss tail of the student forwards (models/segmentation_model.py:160-170,
+ * 228-240 + models/losses.py:10-22): bilinear up-sampling of the logits
+ * [B,K,h,w] to the label size (align_corners=False: ATen's
+ * area_pixel_compute_source_index, scale = in/out in float, negative source
+ * positions clamped to 0) followed by the pixel-weighted cross-entropy with
+ * ignore_index, averaged over ALL B*H*W pixels.  Index / lambda arithmetic in
+ * float as ATen does, values accumulated in double.  Also returns the
+ * gradient with respect to the low-resolution logits (grad may be NULL;
+ * weight may be NULL = 1).
+ * ------------------------------------------------------------------------- */
+static inline void orc_up_coord(int dst, int in, float scale, int *i0, int *i1, float *l1) {
+  float src = ((float)dst + 0.5f) * scale - 0.5f;
+  if (src < 0.f) src = 0.f;
+  int a = (int)src;
+  if (a > in - 1) a = in - 1;
+  *i0 = a;
+  *i1 = a + (a < in - 1 ? 1 : 0);
+  *l1 = src - (float)a;
+}
+
+double orc_upsample_ce(const float *logits, const int64_t *target, const float *weight, int B, int K, int h, int w,
+                       int H, int W, int ignore_index, double *grad) {
+  const float sy = (float)h / (float)H, sx = (float)w / (float)W;
+  const long plane = (long)h * w;
+  const double inv_n = 1.0 / ((double)B * H * W);
+  double total = 0.0;
+  if (grad) memset(grad, 0, sizeof(double) * (size_t)B * K * plane);
+  for (int b = 0; b < B; ++b) {   /* serial: the gradient scatter is not parallelised (test sizes only) */
+    const float *lb = logits + (long)b * K * plane;
+    double *gb = grad ? grad + (long)b * K * plane : NULL;
+    double *z = (double *)malloc(sizeof(double) * K);
+    for (int y = 0; y < H; ++y) {
+      int y0, y1;
+      float ly;
+      orc_up_coord(y, h, sy, &y0, &y1, &ly);
+      for (int x = 0; x < W; ++x) {
+        const long pix = ((long)b * H + y) * W + x;
+        const int64_t t = target[pix];
+        if (t == ignore_index || t < 0 || t >= K) continue;
+        int x0, x1;
+        float lx;
+        orc_up_coord(x, w, sx, &x0, &x1, &lx);
+        const double w00 = (1.0 - ly) * (1.0 - lx), w01 = (1.0 - ly) * lx, w10 = (double)ly * (1.0 - lx), w11 = (double)ly * lx;
+        double mx = -INFINITY;
+        for (int k = 0; k < K; ++k) {
+          const float *p = lb + (long)k * plane;
+          z[k] = w00 * p[(long)y0 * w + x0] + w01 * p[(long)y0 * w + x1] + w10 * p[(long)y1 * w + x0] + w11 * p[(long)y1 * w + x1];
+          if (z[k] > mx) mx = z[k];
+        }
+        double s = 0.0;
+        for (int k = 0; k < K; ++k) s += exp(z[k] - mx);
+        const double lse = mx + log(s);
+        const double wi = weight ? (double)weight[pix] : 1.0;
+        total += wi * (lse - z[t]);
+        if (gb) {
+          for (int k = 0; k < K; ++k) {
+            const double g = wi * (exp(z[k] - lse) - (k == t ? 1.0 : 0.0)) * inv_n;
+            double *q = gb + (long)k * plane;
+            q[(long)y0 * w + x0] += w00 * g;
+            q[(long)y0 * w + x1] += w01 * g;
+            q[(long)y1 * w + x0] += w10 * g;
+            q[(long)y1 * w + x1] += w11 * g;
+          }
+        }
+      }
+    }
+    free(z);
+  }
+  return total * inv_n;
+}

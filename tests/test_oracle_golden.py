@@ -71,11 +71,14 @@ def test_exact_transcendentals():
 
 
 def test_upsample_ce_loss_tail(golden):
-    """oracle.upsample_ce (float64 torch restatement of F.interpolate + PixelWeightedCrossEntropyLoss) against the
-    loss values the reference's own loss class produced (tests/golden/make_golden_loss.py)."""
+    """oracle.upsample_ce (C restatement of F.interpolate + PixelWeightedCrossEntropyLoss, gradient included) against
+    the loss values and logit gradients the reference's own loss class produced (tests/golden/make_golden_loss.py)."""
     g = golden("ops_upsample_ce")
     for i in range(int(g["ncases"])):
         w = T(g[f"c{i}_weight"])
-        got = oracle.upsample_ce(T(g[f"c{i}_logits"]), T(g[f"c{i}_target"]), w if w.numel() else None, 255)
+        got, grad = oracle.upsample_ce(T(g[f"c{i}_logits"]), T(g[f"c{i}_target"]), w if w.numel() else None, 255,
+                                       return_grad=True)
         want = float(g[f"c{i}_loss"])
         assert abs(float(got) - want) <= 2e-6 * max(1.0, abs(want)), (i, float(got), want)
+        g_want = T(g[f"c{i}_grad"])
+        assert torch.allclose(grad, g_want, rtol=1e-4, atol=2e-6 * float(g_want.abs().max())), i
