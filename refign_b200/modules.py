@@ -59,22 +59,32 @@ class ConvBNReLU(nn.Module):
                 and c.padding_mode == 'zeros')
 
     def _fold(self):
-        """Eval-mode BatchNorm folded into the conv weights (cached until a tensor changes)."""
+        """Eval-mode BatchNorm folded into the conv weights.
+
+        The folded tensors are cached only for FROZEN blocks (no parameter requires grad: the alignment
+        network / VGG, reference segmentation_model.py:73-75,693-694).  Trainable blocks (the student's DAFormer /
+        SegFormer heads evaluated in ``validation_step``) are re-folded on every call: under the flat-buffer
+        runtime their parameters and running statistics are written through raw pointers (``rf_adamw_step``,
+        ``rf_bn_finalize``), which changes neither ``data_ptr`` nor ``_version``, so no tensor-derived key can
+        detect the update."""
         bn, conv = self.bn, self.conv
         tensors = (conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var)
+        frozen = not any(t is not None and t.requires_grad for t in tensors)
         key = tuple((t.data_ptr(), t._version) if t is not None else None for t in tensors)
-        if self._folded is None or self._folded[0] != key:
-            with torch.no_grad():
-                inv = torch.rsqrt(bn.running_var.float() + bn.eps)
-                scale = inv * bn.weight.float() if bn.weight is not None else inv
-                w = conv.weight.float() * scale.view(-1, 1, 1, 1)
-                b = -bn.running_mean.float() * scale
-                if bn.bias is not None:
-                    b = b + bn.bias.float()
-                if conv.bias is not None:
-                    b = b + conv.bias.float() * scale
-            self._folded = (key, w.contiguous(), b.contiguous())
-        return self._folded[1], self._folded[2]
+        if frozen and self._folded is not None and self._folded[0] == key:
+            return self._folded[1], self._folded[2]
+        with torch.no_grad():
+            inv = torch.rsqrt(bn.running_var.float() + bn.eps)
+            scale = inv * bn.weight.float() if bn.weight is not None else inv
+            w = conv.weight.float() * scale.view(-1, 1, 1, 1)
+            b = -bn.running_mean.float() * scale
+            if bn.bias is not None:
+                b = b + bn.bias.float()
+            if conv.bias is not None:
+                b = b + conv.bias.float() * scale
+        w, b = w.contiguous(), b.contiguous()
+        self._folded = (key, w, b) if frozen else None
+        return w, b
 
     def forward(self, x):
         if self.depthwise_separable:
