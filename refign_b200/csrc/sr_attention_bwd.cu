@@ -467,9 +467,22 @@ static BwdFork* bwd_fork() {
 
 using namespace rf;
 
+// warp-specialised single-launch backward (sr_attention_bwd_ws.cu) -- the default; RF_ATTN_BWD=old selects the two
+// single-role kernels of this file (kept for A/B measurement)
+int64_t rf_sr_attention_bwd_ws_workspace_bytes(int B, int N, int heads);
+int rf_sr_attention_bwd_ws(const void* q, const void* kv, const void* out, const void* grad_out, const float* lse,
+                           void* grad_q, float* grad_kv_f32, void* workspace, int B, int N, int M, int heads, float scale,
+                           cudaStream_t st);
+static bool use_ws_backward() {
+  static const bool ws = [] { const char* e = getenv("RF_ATTN_BWD"); return !(e && e[0] == 'o'); }();
+  return ws;
+}
+
 extern "C" int64_t rf_sr_attention_bwd_workspace_bytes(int B, int N, int M, int heads) {
   (void)M;
-  return (int64_t)sizeof(float) * (int64_t)B * heads * N;  // D[b,h,n] = rowsum(dO * O)
+  const int64_t old_bytes = (int64_t)sizeof(float) * (int64_t)B * heads * N;  // D[b,h,n] = rowsum(dO * O)
+  const int64_t ws_bytes = rf_sr_attention_bwd_ws_workspace_bytes(B, N, heads);
+  return old_bytes > ws_bytes ? old_bytes : ws_bytes;
 }
 
 extern "C" int rf_sr_attention_bwd(const void* q, const void* kv, const void* out, const void* grad_out,
@@ -480,6 +493,10 @@ extern "C" int rf_sr_attention_bwd(const void* q, const void* kv, const void* ou
              "rf_sr_attention_bwd: bad shape");
   const int C = heads * AB_D;
   cudaStream_t st = (cudaStream_t)stream;
+  RF_REQUIRE(((uintptr_t)workspace & 15) == 0 && ((uintptr_t)grad_q & 15) == 0 && ((uintptr_t)grad_kv_f32 & 15) == 0,
+             "rf_sr_attention_bwd: workspace / gradients must be 16-byte aligned");
+  if (use_ws_backward())
+    return rf_sr_attention_bwd_ws(q, kv, out, grad_out, lse, grad_q, grad_kv_f32, workspace, B, N, M, heads, scale, st);
   float* dvec = (float*)workspace;
   CUtensorMap tq128, tdo128, tkv64, tq64, tdo64, tkv128;
   int rc;

@@ -982,7 +982,7 @@ class _SrAttentionFunction(torch.autograd.Function):
         with torch.cuda.device(q.device):
             _run("rf_sr_attention_bwd", ptr(q), ptr(kv), ptr(out), ptr(go), ptr(lse), ptr(dq), ptr(dkv), ptr(ws), B, N,
                  M, heads, float(scale), _stream(),
-                 work=(2 * (4 * q.numel() + 2 * kv.numel()), 14 * B * heads * N * M * 64), tag="sr_attention_bwd")
+                 work=(2 * (4 * q.numel() + 2 * kv.numel()), 10 * B * heads * N * M * 64), tag="sr_attention_bwd")   # ALGORITHMIC: 5 GEMMs (S, dP, dV, dK, dQ); the kernels recompute S / dP once more
         return dq, dkv.to(kv.dtype), None, None
 
 

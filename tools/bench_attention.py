@@ -40,4 +40,4 @@ for size in ((1024,) if FAST else (512, 1024)):
         print(json.dumps({"kernel": "sr_attention_fwd", "size": size, "stage": stage + 1, "B": B, "N": N, "M": M, "heads": heads,
                           "us": round(ms * 1e3, 1), "TFLOPs": round(fl / ms / 1e9, 1), "frac_of_bf16_peak": round(fl / ms / 1e9 / peak, 4),
                           "library_us": round(ms_lib * 1e3, 1),
-                          "bwd_us": round(ms_bwd * 1e3, 1), "bwd_TFLOPs": round(3.5 * fl / ms_bwd / 1e9, 1), "bwd_library_us": round(ms_bwd_lib * 1e3, 1)}))
+                          "bwd_us": round(ms_bwd * 1e3, 1), "bwd_TFLOPs_algorithmic_5gemm": round(2.5 * fl / ms_bwd / 1e9, 1), "bwd_frac_of_bf16_peak": round(2.5 * fl / ms_bwd / 1e9 / peak, 4), "bwd_library_us": round(ms_bwd_lib * 1e3, 1)}))

@@ -5,3 +5,5 @@ cd "$(dirname "$0")/.."
 mkdir -p tools/_bin
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo --expt-relaxed-constexpr -ccbin /usr/bin/g++ \
   tools/ubench_sm100.cu refign_b200/csrc/tensormap.cu -o tools/_bin/ubench_sm100
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo --expt-relaxed-constexpr -ccbin /usr/bin/g++ \
+  tools/trace_attn_bwd.cu refign_b200/csrc/tensormap.cu -o tools/_bin/trace_attn_bwd

@@ -159,6 +159,100 @@ __global__ void __launch_bounds__(128, 1) mma_kernel(int rounds, int per_round, 
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
+
+// ------------------------------------------------------------------------------------------------ commit latency
+// Does the mbarrier of a tcgen05.commit fire when ITS batch completes, while the issuing warp then waits (mbarrier
+// spin) and other warps keep the SM busy?   warp 0 = MMA issuer, warp 1 = observer, warps 2..9 = load generators.
+// LOAD 0: idle   1: FMA + MUFU loop   2: tcgen05.ld loop   WAITMODE 0: issuer spins on clock64   1: issuer waits on an mbarrier
+template <int LOAD, int WAITMODE>
+__global__ void __launch_bounds__(320, 1) commit_latency_kernel(long long* out, int gap) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t barA, barB, barX;
+  __shared__ uint32_t slot;
+  __shared__ long long t_issue[2];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (16384 + 32768) / 4; i += 320) reinterpret_cast<uint32_t*>(smem)[i] = 0x3f803f00u + (i & 0x7f);
+  if (tid == 0) {
+    mbar_init(&barA, 1);
+    mbar_init(&barB, 1);
+    mbar_init(&barX, 256);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(&slot);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = uniform_u32(slot);
+  constexpr uint32_t IDESC_S = make_idesc(FMT_BF16, 128, 128, 0, 0);
+  constexpr uint32_t IDESC_A = make_idesc(FMT_BF16, 128, 64, 0, 1);
+  const uint64_t dA = make_sdesc_sw128(smem_u32(smem), 16, 1024);
+  const uint64_t dB = make_sdesc_sw128(smem_u32(smem + 16384), 16, 1024);
+  const uint64_t dBmn = make_sdesc_sw128(smem_u32(smem + 16384), 8192, 1024);
+  const long long t_start = clock64();
+  if (warp == 0) {
+    if (elect_one()) {
+      t_issue[0] = clock64() - t_start;
+      for (int k = 0; k < 4; ++k) mma_f16_ss(tmem, dA + (uint64_t)(k * 2), dB + (uint64_t)(k * 2), IDESC_S, k > 0);
+      for (int k = 0; k < 4; ++k) mma_f16_ss(tmem + 128, dA + (uint64_t)(k * 2), dB + (uint64_t)(k * 2), IDESC_S, k > 0);
+      tc_commit(&barA);
+    }
+    __syncwarp();
+    if (WAITMODE == 0) {
+      while (clock64() - t_start < gap) {}
+    } else {
+      mbar_wait(&barX, 0);
+    }
+    tc_fence_after();
+    if (elect_one()) {
+      t_issue[1] = clock64() - t_start;
+      for (int k = 0; k < 8; ++k) mma_f16_ts(tmem + 448, tmem + 256 + k * 8, dBmn + (uint64_t)(k * 128), IDESC_A, k > 0);
+      for (int k = 0; k < 8; ++k) mma_f16_ts(tmem + 384, tmem + 320 + k * 8, dBmn + (uint64_t)(k * 128), IDESC_A, k > 0);
+      tc_commit(&barB);
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    mbar_wait(&barA, 0);
+    const long long ta = clock64() - t_start;
+    mbar_wait(&barB, 0);
+    const long long tb = clock64() - t_start;
+    if ((tid & 31) == 0 && blockIdx.x == 0) {
+      out[0] = ta;
+      out[1] = tb;
+    }
+  } else {
+    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    float x = 0.001f * tid, y = 0.f;
+    uint32_t v[32];
+    uint32_t acc = 0;
+    while (clock64() - t_start < gap) {
+      if (LOAD == 1) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          x = fast_exp2(x) - 1.0f;
+          y = fmaf(y, 1.0001f, x);
+        }
+      } else if (LOAD == 2) {
+        tmem_ld32(taddr, v);
+        tc_wait_ld();
+        acc ^= v[3];
+      }
+    }
+    if (x + y == 123.f || acc == 77u) out[7] = 1;
+    tc_fence_before();
+    mbar_arrive(&barX);
+  }
+  __syncthreads();
+  if (tid == 0 && blockIdx.x == 0) {
+    out[2] = t_issue[0];
+    out[3] = t_issue[1];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
 // ------------------------------------------------------------------------------------------------ TMA reduce
 __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
   asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
@@ -270,6 +364,25 @@ int main() {
         printf(" \"mma_%s_batch%d_clk_per_mma\": %.1f,\n", names[mode], per, max_cycles(cyc, 148) / ((double)rounds * per));
       }
     }
+  }
+  // ---- commit latency
+  {
+    const int smem = 16384 + 32768 + 1024;
+    long long* out;
+    CK(cudaMalloc(&out, 64));
+#define RUN_CL(L, W)                                                                                                   \
+  {                                                                                                                    \
+    CK(cudaFuncSetAttribute(commit_latency_kernel<L, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));          \
+    long long h[4];                                                                                                    \
+    for (int rep = 0; rep < 2; ++rep) {                                                                                \
+      commit_latency_kernel<L, W><<<148, 320, smem>>>(out, 4000);                                                      \
+      CK(cudaDeviceSynchronize());                                                                                     \
+    }                                                                                                                  \
+    CK(cudaMemcpy(h, out, 32, cudaMemcpyDeviceToHost));                                                                \
+    printf(" \"commit_latency_load%d_wait%d\": {\"issueA\": %lld, \"barA_seen\": %lld, \"issueB\": %lld, \"barB_seen\": %lld},\n", L, W, \
+           h[2], h[0], h[3], h[1]);                                                                                    \
+  }
+    RUN_CL(0, 0) RUN_CL(0, 1) RUN_CL(1, 0) RUN_CL(1, 1) RUN_CL(2, 0) RUN_CL(2, 1)
   }
   // ---- TMA reduce-add and red.v4
   {
