@@ -42,18 +42,15 @@ constexpr int WS_TILE = 128 * 64 * 2;                 // one [128 x 64] bf16 til
 constexpr int WS_VEC = 128 * 4;                       // 128 floats
 constexpr int WS_STAGES = 3;
 constexpr int WS_STAGE_BYTES = 2 * WS_TILE + 2 * WS_VEC;   // role KV: Q | dO | lse2 | D   (role Q uses the first 2 tiles: K | V)
-#ifdef WS_TRACE
-constexpr int WS_THREADS = 352;   // + an observer warp that timestamps barrier completions
-#else
 constexpr int WS_THREADS = 320;
-#endif
 constexpr int WS_SMEM = 2 * WS_TILE + WS_STAGES * WS_STAGE_BYTES + 1024 /*alignment*/ + 256 /*barriers*/;
 
 struct __align__(8) WsBars {
   uint64_t fixed_full;                         // role KV: K, V block; role Q: Q, dO tile
   uint64_t ring_full[WS_STAGES], ring_free[WS_STAGES];
-  uint64_t s_full, sdp_free;                   // score tiles complete / loaded into registers by all 256 softmax threads
-  uint64_t a_full[2], a_free[2];               // bf16 A operands written / consumed (role KV uses index 0 only)
+  uint64_t s_full;                             // S and dP tiles complete (tcgen05.commit)
+  uint64_t s_free;                             // ... loaded into registers by all 8 softmax warps (one elected arrive per warp)
+  uint64_t ds_full[2], ds_free[2];             // bf16 A operands (dS; role KV: + P^T) written / consumed (role Q: double-buffered; role KV: index 0)
   uint64_t fin;
   uint32_t tmem_base;
 };
@@ -73,24 +70,30 @@ struct WsParams {
 #ifdef WS_TRACE
 __device__ long long* g_ws_trace;
 __device__ int g_ws_trace_blocks[2];
-// inline (a call would spill the ~128 live score registers of the softmax threads around every probe)
+__shared__ long long ws_trace_buf[11][256];     // per traced warp: [0] = count, then (tag << 48 | clock) records
+// inline and in shared memory: a call would spill the ~128 live score registers around every probe, a global
+// counter costs a ~400-cycle round trip per probe
 __device__ __forceinline__ void ws_trace(int tag) {
   const int warp = threadIdx.x >> 5;
-  if ((threadIdx.x & 31) != 0 || (warp != 0 && warp < 8)) return;
-  const int slot = (int)blockIdx.x == g_ws_trace_blocks[0] ? 0 : ((int)blockIdx.x == g_ws_trace_blocks[1] ? 1 : -1);
-  if (slot < 0) return;
-  long long* base = g_ws_trace + (slot * 4 + (warp == 0 ? 0 : warp - 7)) * 1024;
+  if ((threadIdx.x & 31) != 0) return;
+  long long* base = ws_trace_buf[warp];
   const int n = (int)base[0];
-  if (n < 1000) {
+  if (n < 254) {
     base[1 + n] = ((long long)tag << 48) | (clock64() & 0xffffffffffffll);
     base[0] = n + 1;
   }
 }
+__device__ __forceinline__ void ws_trace_init() {
+  if (threadIdx.x < 11) ws_trace_buf[threadIdx.x][0] = 0;
+}
+__device__ __forceinline__ void ws_trace_flush() {   // after the final __syncthreads
+  const int slot = (int)blockIdx.x == g_ws_trace_blocks[0] ? 0 : ((int)blockIdx.x == g_ws_trace_blocks[1] ? 1 : -1);
+  if (slot < 0) return;
+  for (int i = threadIdx.x; i < 11 * 256; i += blockDim.x) g_ws_trace[slot * 11 * 256 + i] = ws_trace_buf[i >> 8][i & 255];
+}
 #define WS_T(tag) ws_trace(tag)
-#define WS_OBSERVER 1
 #else
 #define WS_T(tag)
-#define WS_OBSERVER 0
 #endif
 
 __device__ __forceinline__ uint32_t ws_pack_bf16(float a, float b) {
@@ -168,74 +171,80 @@ __device__ __forceinline__ void ws_role_kv(const CUtensorMap& tm_q, const CUtens
       __syncwarp();
       WS_T(30);
     }
-  } else if (WS_OBSERVER && warp == 10) {
-    for (int i = 0; i < ntiles; ++i) {
-      mbar_wait(&bars->s_full, i & 1);
-      WS_T(40);
-      mbar_wait(&bars->a_free[0], i & 1);
-      WS_T(41);
-    }
   } else if (warp == 8) {
     // ------------------------------------------------------------------ MMA issuer
+    // per tile i, in this order:  S^T(i+1) | dV(i) | dP^T(i+1) | dK(i)   -- the next S^T is queued as soon as the softmax
+    // warps hold S^T(i) in registers, so it is long finished when they come back for it
     const uint64_t descK = make_sdesc_sw128(smem_u32(sK), 16, 1024);
     const uint64_t descV = make_sdesc_sw128(smem_u32(sV), 16, 1024);
-    auto issue_scores = [&](int i) {
-      uint8_t* stage = ring + (i % WS_STAGES) * WS_STAGE_BYTES;
-      const uint64_t descQ = make_sdesc_sw128(smem_u32(stage), 16, 1024);
-      const uint64_t descdO = make_sdesc_sw128(smem_u32(stage + WS_TILE), 16, 1024);
-      WS_T(23);
+    // ring-stage descriptors: built once; stage st adds st * (stage bytes >> 4) to the 14-bit start-address field
+    constexpr uint64_t STEP = (uint64_t)(WS_STAGE_BYTES >> 4);
+    const uint32_t ring_a = smem_u32(ring);
+    const uint64_t dQk0 = make_sdesc_sw128(ring_a, 16, 1024), dOk0 = make_sdesc_sw128(ring_a + WS_TILE, 16, 1024);
+    const uint64_t dQmn0 = make_sdesc_sw128(ring_a, 8192, 1024), dOmn0 = make_sdesc_sw128(ring_a + WS_TILE, 8192, 1024);
+    auto issue_s = [&](uint64_t st) {
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          mma_f16_ss(tmem, descK + (uint64_t)(k * 2), descQ + (uint64_t)(k * 2), WS_IDESC_S, k > 0 ? 1u : 0u);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          mma_f16_ss(tmem + 128, descV + (uint64_t)(k * 2), descdO + (uint64_t)(k * 2), WS_IDESC_S, k > 0 ? 1u : 0u);
-        tc_commit(&bars->s_full);
+          mma_f16_ss(tmem, descK + (uint64_t)(k * 2), dQk0 + st * STEP + (uint64_t)(k * 2), WS_IDESC_S, k > 0 ? 1u : 0u);
       }
       __syncwarp();
-      WS_T(24);
+    };
+    auto issue_dp = [&](uint64_t st) {
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          mma_f16_ss(tmem + 128, descV + (uint64_t)(k * 2), dOk0 + st * STEP + (uint64_t)(k * 2), WS_IDESC_S, k > 0 ? 1u : 0u);
+        tc_commit(&bars->s_full);   // S and dP of this tile are complete (in-order tensor pipe)
+      }
+      __syncwarp();
     };
     mbar_wait(&bars->fixed_full, 0);
     mbar_wait(&bars->ring_full[0], 0);
     tc_fence_after();
-    issue_scores(0);
+    issue_s(0);
+    issue_dp(0);
+    int st = 0;
     for (int i = 0; i < ntiles; ++i) {
-      if (i + 1 < ntiles) {
-        mbar_wait(&bars->ring_full[(i + 1) % WS_STAGES], ((i + 1) / WS_STAGES) & 1);
-        mbar_wait(&bars->sdp_free, i & 1);      // S^T(i) / dP^T(i) are in registers
+      const int st1 = st + 1 == WS_STAGES ? 0 : st + 1;
+      const bool more = i + 1 < ntiles;
+      if (more) {
+        mbar_wait(&bars->ring_full[st1], ((i + 1) / WS_STAGES) & 1);
+        mbar_wait(&bars->s_free, i & 1);        // S^T(i) and dP^T(i) are in registers
         tc_fence_after();
-        WS_T(21);
-        issue_scores(i + 1);
+        issue_s(st1);
+        issue_dp(st1);
       }
-      mbar_wait(&bars->a_full[0], i & 1);       // P^T(i), dS^T(i) written
+      mbar_wait(&bars->ds_full[0], i & 1);      // P^T(i), dS^T(i) written
       tc_fence_after();
-      WS_T(22);
-      uint8_t* stage = ring + (i % WS_STAGES) * WS_STAGE_BYTES;
-      const uint64_t descQmn = make_sdesc_sw128(smem_u32(stage), 8192, 1024);
-      const uint64_t descdOmn = make_sdesc_sw128(smem_u32(stage + WS_TILE), 8192, 1024);
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          mma_f16_ts(tmem + 448, tmem + 256 + k * 8, descdOmn + (uint64_t)(k * 128), WS_IDESC_ACC, (i > 0 || k > 0) ? 1u : 0u);
+          mma_f16_ts(tmem + 448, tmem + 256 + k * 8, dOmn0 + st * STEP + (uint64_t)(k * 128), WS_IDESC_ACC, (i > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          mma_f16_ts(tmem + 384, tmem + 320 + k * 8, descQmn + (uint64_t)(k * 128), WS_IDESC_ACC, (i > 0 || k > 0) ? 1u : 0u);
-        tc_commit(&bars->a_free[0]);
-        tc_commit(&bars->ring_free[i % WS_STAGES]);
-        if (i == ntiles - 1) tc_commit(&bars->fin);
+          mma_f16_ts(tmem + 384, tmem + 320 + k * 8, dQmn0 + st * STEP + (uint64_t)(k * 128), WS_IDESC_ACC, (i > 0 || k > 0) ? 1u : 0u);
+        tc_commit(&bars->ds_free[0]);
+        tc_commit(&bars->ring_free[st]);
+        if (!more) tc_commit(&bars->fin);
       }
       __syncwarp();
+      WS_T(25);
+      st = st1;
     }
   } else {
     // ------------------------------------------------------------------ softmax warpgroups (lane = key)
     const int g = warp >> 2;                       // query columns [64 g, 64 g + 64)
+    const bool lane0 = (tid & 31) == 0;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t tS = tmem + lane_off + 64 * g, tdP = tmem + lane_off + 128 + 64 * g;
     const uint32_t tP = tmem + lane_off + 256 + 32 * g, tdS = tmem + lane_off + 320 + 32 * g;
+    const float2 sl = make_float2(p.scale_log2, p.scale_log2);
     for (int i = 0; i < ntiles; ++i) {
       const int st = i % WS_STAGES;
-      mbar_wait(&bars->ring_full[st], (i / WS_STAGES) & 1);   // lse2 / D vectors of this tile (already complete)
+      const uint32_t vec = smem_u32(ring + st * WS_STAGE_BYTES + 2 * WS_TILE) + 256 * g;   // -lse2 | -D of this warpgroup's 64 queries
+      // the -lse2 / -D vectors of this stage landed before the MMA warp issued S^T(i) (it waited on ring_full), and
+      // s_full is observed after that: no separate wait (every mbarrier test costs ~100 cycles of latency here)
       mbar_wait(&bars->s_full, i & 1);
       tc_fence_after();
       WS_T(10);
@@ -246,9 +255,10 @@ __device__ __forceinline__ void ws_role_kv(const CUtensorMap& tm_q, const CUtens
       tmem_ld32(tdP + 32, dv[1]);
       tc_wait_ld();
       tc_fence_before();
-      mbar_arrive(&bars->sdp_free);
-      const uint32_t vec = smem_u32(ring + st * WS_STAGE_BYTES + 2 * WS_TILE) + 256 * g;   // -lse2 | -D of this warpgroup's 64 queries
-      const float2 sl = make_float2(p.scale_log2, p.scale_log2);
+      __syncwarp();
+      if (lane0) mbar_arrive(&bars->s_free);   // one arrival per warp: 256 per-thread arrivals serialise in the barrier unit (~380 cycles)
+      WS_T(11);
+      // ONE compute phase: the exponentials (MUFU) and the dS arithmetic (FMA pipe) interleave
       uint32_t pp[32], pd[32];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -264,14 +274,15 @@ __device__ __forceinline__ void ws_role_kv(const CUtensorMap& tm_q, const CUtens
         }
       }
       if (i >= 1) {   // dV / dK MMAs of tile i-1 have consumed P^T / dS^T
-        mbar_wait(&bars->a_free[0], (i - 1) & 1);
+        mbar_wait(&bars->ds_free[0], (i - 1) & 1);
         tc_fence_after();
       }
       tmem_st32(tP, pp);
       tmem_st32(tdS, pd);
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive(&bars->a_full[0]);
+      __syncwarp();
+      if (lane0) mbar_arrive(&bars->ds_full[0]);
       WS_T(14);
     }
     // epilogue: warpgroup 0 -> dK (scaled), warpgroup 1 -> dV
@@ -339,65 +350,67 @@ __device__ __forceinline__ void ws_role_q(const CUtensorMap& tm_q, const CUtenso
       }
       __syncwarp();
     }
-  } else if (WS_OBSERVER && warp == 10) {
-    for (int j = 0; j < nchunks; ++j) {
-      mbar_wait(&bars->s_full, j & 1);
-      WS_T(40);
-      mbar_wait(&bars->a_free[j & 1], (j >> 1) & 1);
-      WS_T(41);
-    }
   } else if (warp == 8) {
     // ------------------------------------------------------------------ MMA issuer
+    // per chunk j, in this order:  S(j+1) | dP(j+1) | dQ(j)
     const uint64_t descQ = make_sdesc_sw128(smem_u32(sQ), 16, 1024);
     const uint64_t descdO = make_sdesc_sw128(smem_u32(sdO), 16, 1024);
-    auto issue_scores = [&](int j) {
-      uint8_t* stage = ring + (j % WS_STAGES) * WS_STAGE_BYTES;
-      const uint64_t descK = make_sdesc_sw128(smem_u32(stage), 16, 1024);
-      const uint64_t descV = make_sdesc_sw128(smem_u32(stage + WS_TILE), 16, 1024);
-      WS_T(23);
+    constexpr uint64_t STEP = (uint64_t)(WS_STAGE_BYTES >> 4);
+    const uint32_t ring_a = smem_u32(ring);
+    const uint64_t dKk0 = make_sdesc_sw128(ring_a, 16, 1024), dVk0 = make_sdesc_sw128(ring_a + WS_TILE, 16, 1024);
+    const uint64_t dKmn0 = make_sdesc_sw128(ring_a, 8192, 1024);
+    auto issue_s = [&](uint64_t st) {
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          mma_f16_ss(tmem, descQ + (uint64_t)(k * 2), descK + (uint64_t)(k * 2), WS_IDESC_S, k > 0 ? 1u : 0u);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          mma_f16_ss(tmem + 128, descdO + (uint64_t)(k * 2), descV + (uint64_t)(k * 2), WS_IDESC_S, k > 0 ? 1u : 0u);
-        tc_commit(&bars->s_full);
+          mma_f16_ss(tmem, descQ + (uint64_t)(k * 2), dKk0 + st * STEP + (uint64_t)(k * 2), WS_IDESC_S, k > 0 ? 1u : 0u);
       }
       __syncwarp();
-      WS_T(24);
+    };
+    auto issue_dp = [&](uint64_t st) {
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          mma_f16_ss(tmem + 128, descdO + (uint64_t)(k * 2), dVk0 + st * STEP + (uint64_t)(k * 2), WS_IDESC_S, k > 0 ? 1u : 0u);
+        tc_commit(&bars->s_full);   // S and dP of this tile are complete (in-order tensor pipe)
+      }
+      __syncwarp();
     };
     mbar_wait(&bars->fixed_full, 0);
     mbar_wait(&bars->ring_full[0], 0);
     tc_fence_after();
-    issue_scores(0);
+    issue_s(0);
+    issue_dp(0);
+    int st = 0;
     for (int j = 0; j < nchunks; ++j) {
-      if (j + 1 < nchunks) {
-        mbar_wait(&bars->ring_full[(j + 1) % WS_STAGES], ((j + 1) / WS_STAGES) & 1);
-        mbar_wait(&bars->sdp_free, j & 1);
+      const int st1 = st + 1 == WS_STAGES ? 0 : st + 1;
+      const bool more = j + 1 < nchunks;
+      if (more) {
+        mbar_wait(&bars->ring_full[st1], ((j + 1) / WS_STAGES) & 1);
+        mbar_wait(&bars->s_free, j & 1);
         tc_fence_after();
-        WS_T(21);
-        issue_scores(j + 1);
+        issue_s(st1);
+        issue_dp(st1);
       }
-      mbar_wait(&bars->a_full[j & 1], (j >> 1) & 1);   // dS(j) written
+      mbar_wait(&bars->ds_full[j & 1], (j >> 1) & 1);   // dS(j) written
       tc_fence_after();
-      WS_T(22);
-      uint8_t* stage = ring + (j % WS_STAGES) * WS_STAGE_BYTES;
-      const uint64_t descKmn = make_sdesc_sw128(smem_u32(stage), 8192, 1024);
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          mma_f16_ts(tmem + 384, tmem + 256 + (j & 1) * 64 + k * 8, descKmn + (uint64_t)(k * 128), WS_IDESC_ACC,
+          mma_f16_ts(tmem + 384, tmem + 256 + (j & 1) * 64 + k * 8, dKmn0 + st * STEP + (uint64_t)(k * 128), WS_IDESC_ACC,
                      (j > 0 || k > 0) ? 1u : 0u);
-        tc_commit(&bars->a_free[j & 1]);
-        tc_commit(&bars->ring_free[j % WS_STAGES]);
-        if (j == nchunks - 1) tc_commit(&bars->fin);
+        tc_commit(&bars->ds_free[j & 1]);
+        tc_commit(&bars->ring_free[st]);
+        if (!more) tc_commit(&bars->fin);
       }
       __syncwarp();
+      WS_T(25);
+      st = st1;
     }
   } else {
     // ------------------------------------------------------------------ softmax warpgroups (lane = query)
     const int g = warp >> 2;                       // key columns [64 g, 64 g + 64) of every chunk
+    const bool lane0 = (tid & 31) == 0;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t tS = tmem + lane_off + 64 * g, tdP = tmem + lane_off + 128 + 64 * g;
     const int row = q0 + (tid & 127);              // < Npad: the workspace rows are padded to whole tiles
@@ -415,7 +428,9 @@ __device__ __forceinline__ void ws_role_q(const CUtensorMap& tm_q, const CUtenso
       tmem_ld32(tdP + 32, dv[1]);
       tc_wait_ld();
       tc_fence_before();
-      mbar_arrive(&bars->sdp_free);
+      __syncwarp();
+      if (lane0) mbar_arrive(&bars->s_free);
+      WS_T(11);
       uint32_t pd[32];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -424,13 +439,14 @@ __device__ __forceinline__ void ws_role_q(const CUtensorMap& tm_q, const CUtenso
           pd[h * 16 + e] = ws_ds2(ws_prob2(sv[h][2 * e], sv[h][2 * e + 1], sl, nl), dv[h][2 * e], dv[h][2 * e + 1], nd);
       }
       if (j >= 2) {   // dQ MMAs of chunk j-2 have consumed this dS buffer
-        mbar_wait(&bars->a_free[j & 1], ((j >> 1) - 1) & 1);
+        mbar_wait(&bars->ds_free[j & 1], ((j >> 1) - 1) & 1);
         tc_fence_after();
       }
       tmem_st32(tmem + lane_off + 256 + (j & 1) * 64 + 32 * g, pd);
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive(&bars->a_full[j & 1]);
+      __syncwarp();
+      if (lane0) mbar_arrive(&bars->ds_full[j & 1]);
       WS_T(14);
     }
     // epilogue: warpgroup g stores dQ columns [32 g, 32 g + 32) of its row
@@ -455,6 +471,10 @@ __device__ __forceinline__ void ws_role_q(const CUtensorMap& tm_q, const CUtenso
 __global__ void __launch_bounds__(WS_THREADS, 1)
 sr_attention_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
                            const __grid_constant__ CUtensorMap tm_kv, const WsParams p) {
+#ifdef WS_TRACE
+  ws_trace_init();
+  __syncthreads();
+#endif
   WS_T(0);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -471,10 +491,10 @@ sr_attention_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
         mbar_init(&bars->ring_free[s], 1);
       }
       mbar_init(&bars->s_full, 1);
-      mbar_init(&bars->sdp_free, 256);
+      mbar_init(&bars->s_free, 8);
       for (int s = 0; s < 2; ++s) {
-        mbar_init(&bars->a_full[s], 256);
-        mbar_init(&bars->a_free[s], 1);
+        mbar_init(&bars->ds_full[s], 8);
+        mbar_init(&bars->ds_free[s], 1);
       }
       mbar_init(&bars->fin, 1);
       fence_barrier_init();
@@ -495,41 +515,54 @@ sr_attention_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
   tc_fence_before();
   __syncthreads();
   WS_T(2);
+#ifdef WS_TRACE
+  __syncthreads();
+  ws_trace_flush();
+#endif
   if (warp == 8) tmem_dealloc<512>(tmem);
 }
 
-// D[bh][n] = sum_d dO * O and LSE * log2(e), rows padded to whole 128-query tiles with zeros
+// -D[bh][n] = -sum_d dO * O and -LSE * log2(e), rows padded to whole 128-query tiles with zeros.  Eight lanes per
+// (row, head) unit: one warp instruction reads 512 contiguous bytes of O / dO (four units).
 __global__ void __launch_bounds__(256)
 sr_attention_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
                              const float* __restrict__ lse, float* __restrict__ dvec, float* __restrict__ lse2, int N,
-                             int Npad, int heads, long total) {
-  const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;   // (b, head, padded row)
-  if (idx >= total) return;
-  const int row = (int)(idx % Npad);
-  const long bh = idx / Npad;
-  float d = 0.f, l = 0.f;
-  if (row < N) {
-    const int head = (int)(bh % heads);
-    const long b = bh / heads;
-    const int C = heads * 64;
-    const uint4* po = reinterpret_cast<const uint4*>(o + (b * N + row) * C + head * 64);
-    const uint4* pg = reinterpret_cast<const uint4*>(dout + (b * N + row) * C + head * 64);
+                             int Npad, int heads, long units, long pad_entries) {
+  const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  const long u = t >> 3;                 // ((b * N + row) * heads + head): 128-byte chunks in memory order
+  const int l8 = (int)(t & 7);
+  float d = 0.f;
+  if (u < units) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(o) + u * 8 + l8);
+    const uint4 g = __ldg(reinterpret_cast<const uint4*>(dout) + u * 8 + l8);
+    const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* hg = reinterpret_cast<const __nv_bfloat162*>(&g);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const uint4 a = __ldg(po + i), g = __ldg(pg + i);
-      const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
-      const __nv_bfloat162* hg = reinterpret_cast<const __nv_bfloat162*>(&g);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 fa = __bfloat1622float2(ha[k]), fg = __bfloat1622float2(hg[k]);
-        d = fmaf(fa.x, fg.x, d);
-        d = fmaf(fa.y, fg.y, d);
-      }
+    for (int k = 0; k < 4; ++k) {
+      const float2 fa = __bfloat1622float2(ha[k]), fg = __bfloat1622float2(hg[k]);
+      d = fmaf(fa.x, fg.x, d);
+      d = fmaf(fa.y, fg.y, d);
     }
-    l = __ldg(lse + bh * N + row) * 1.44269504088896341f;
   }
-  dvec[idx] = -d;     // both vectors are stored negated: the kernels add them (FFMA2 / FADD2 operands)
-  lse2[idx] = -l;
+  d += __shfl_xor_sync(0xffffffffu, d, 1);
+  d += __shfl_xor_sync(0xffffffffu, d, 2);
+  d += __shfl_xor_sync(0xffffffffu, d, 4);
+  if (u < units && l8 == 0) {
+    const int head = (int)(u % heads);
+    const long brow = u / heads;
+    const long b = brow / N;
+    const int row = (int)(brow % N);
+    const long bh = b * heads + head;
+    dvec[bh * Npad + row] = -d;     // both vectors are stored negated: the kernels add them (FFMA2 / FADD2 operands)
+    lse2[bh * Npad + row] = -__ldg(lse + bh * N + row) * 1.44269504088896341f;
+  }
+  if (t < pad_entries) {            // zero the padding rows [N, Npad) of every (b, head)
+    const int npadrows = Npad - N;
+    const long bh = t / npadrows;
+    const int row = N + (int)(t % npadrows);
+    dvec[bh * Npad + row] = 0.f;
+    lse2[bh * Npad + row] = 0.f;
+  }
 }
 
 }  // namespace rf
@@ -565,9 +598,10 @@ int rf_sr_attention_bwd_ws(const void* q, const void* kv, const void* out, const
     attr_set = true;
   }
   {
-    const long total = (long)B * heads * npad;
-    sr_attention_bwd_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-        (const __nv_bfloat16*)out, (const __nv_bfloat16*)grad_out, lse, dvec, lse2, N, npad, heads, total);
+    const long units = (long)B * N * heads, pad_entries = (long)B * heads * (npad - N);
+    const long threads = units * 8 > pad_entries ? units * 8 : pad_entries;
+    sr_attention_bwd_prep_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
+        (const __nv_bfloat16*)out, (const __nv_bfloat16*)grad_out, lse, dvec, lse2, N, npad, heads, units, pad_entries);
     RF_CHECK_LAUNCH("sr_attention_bwd_prep_kernel");
   }
   WsParams p;

@@ -42,7 +42,7 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&kv, nkv * 2)); CK(cudaMalloc(&dkv, nkv * 4));
   CK(cudaMalloc(&lse, (long)B * heads * N * 4));
   CK(cudaMalloc(&ws, rf_sr_attention_bwd_ws_workspace_bytes(B, N, heads)));
-  CK(cudaMalloc(&trace, 8 * 1024 * 8));
+  CK(cudaMalloc(&trace, 2 * 11 * 256 * 8));
   fill_bf16<<<(nq + 255) / 256, 256>>>(q, nq, 1, 1.f);
   fill_bf16<<<(nq + 255) / 256, 256>>>(o, nq, 2, 1.f);
   fill_bf16<<<(nq + 255) / 256, 256>>>(go, nq, 3, 1.f);
@@ -51,9 +51,8 @@ int main(int argc, char** argv) {
   CK(cudaDeviceSynchronize());
   // unit counts as the launcher computes them
   const int q_tiles = (N + 127) / 128, kvb = (M + 127) / 128;
-  long bhk = (long)B * heads * kvb, tps = ((long)q_tiles * bhk + 177) / 178;
-  if (tps < 4) tps = 4; if (tps > q_tiles) tps = q_tiles;
-  const int splits = (q_tiles + tps - 1) / tps;
+  long bhk = (long)B * heads * kvb;
+  const int splits = getenv("RF_ATTN_BWD_KV_SPLITS") ? atoi(getenv("RF_ATTN_BWD_KV_SPLITS")) : 1;   // keep in step with the launcher via the env override
   const int n_kv = (int)(bhk * splits), n_q = B * heads * q_tiles;
   int blocks[2] = {argc > 5 ? atoi(argv[5]) : n_kv / 2, argc > 6 ? atoi(argv[6]) : n_kv + n_q / 2};
   CK(cudaMemcpyToSymbol(rf::g_ws_trace, &trace, sizeof(trace)));
@@ -61,7 +60,7 @@ int main(int argc, char** argv) {
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   float ms = 0;
   for (int rep = 0; rep < 3; ++rep) {
-    CK(cudaMemset(trace, 0, 8 * 1024 * 8));
+    CK(cudaMemset(trace, 0, 2 * 11 * 256 * 8));
     CK(cudaEventRecord(e0));
     if (rf_sr_attention_bwd_ws(q, kv, o, go, lse, dq, dkv, ws, B, N, M, heads, 0.125f, 0) != 0) return 1;
     CK(cudaEventRecord(e1));
@@ -70,18 +69,17 @@ int main(int argc, char** argv) {
   }
   printf("B %d N %d M %d heads %d: n_kv_units %d (splits %d, %ld tiles each) n_q_units %d; prep+memset+kernel %.1f us\n", B, N, M, heads,
          n_kv, splits, (long)((q_tiles + splits - 1) / splits), n_q, ms * 1e3);
-  std::vector<long long> h(8 * 1024);
-  CK(cudaMemcpy(h.data(), trace, 8 * 1024 * 8, cudaMemcpyDeviceToHost));
-  const char* names[4] = {"softmax", "mma", "tma", "observer"};
+  std::vector<long long> h(2 * 11 * 256);
+  CK(cudaMemcpy(h.data(), trace, 2 * 11 * 256 * 8, cudaMemcpyDeviceToHost));
   for (int slot = 0; slot < 2; ++slot) {
     long long t0 = 0;
-    for (int w = 0; w < 4; ++w) {
-      long long* base = h.data() + (slot * 4 + w) * 1024;
+    for (int w = 0; w < 11; ++w) {
+      long long* base = h.data() + (slot * 11 + w) * 256;
       if (base[0] > 0) { long long c = base[1] & 0xffffffffffffll; if (t0 == 0 || c < t0) t0 = c; }
     }
-    for (int w = 0; w < 4; ++w) {
-      long long* base = h.data() + (slot * 4 + w) * 1024;
-      printf("%s block %d %s:", slot == 0 ? "KV" : "Q", blocks[slot], names[w]);
+    for (int w = 0; w < 11; ++w) {
+      long long* base = h.data() + (slot * 11 + w) * 256;
+      printf("%s block %d warp %d:", slot == 0 ? "KV" : "Q", blocks[slot], w);
       for (int i = 0; i < (int)base[0]; ++i) printf(" %d@%lld", (int)(base[1 + i] >> 48), (base[1 + i] & 0xffffffffffffll) - t0);
       printf("\n");
     }

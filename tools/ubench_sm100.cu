@@ -253,6 +253,77 @@ __global__ void __launch_bounds__(320, 1) commit_latency_kernel(long long* out, 
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
+
+// ------------------------------------------------------------------------------------------------ LDTM under MMA load
+// 8 warps run the softmax warps' load pattern (4 x tcgen05.ld.32x32b.x32 + wait) while warp 8 keeps the tensor pipe busy.
+// MMAMODE 0: tensor pipe idle   1: SS N=128 MMAs   2: TS N=64 MMAs (A operand read from TMEM)
+template <int MMAMODE>
+__global__ void __launch_bounds__(288, 1) ldtm_under_mma_kernel(long long* out, int span) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  __shared__ int iters[8];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (16384 + 32768) / 4; i += 288) reinterpret_cast<uint32_t*>(smem)[i] = 0x3f803f00u + (i & 0x7f);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(&slot);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = uniform_u32(slot);
+  const long long t_start = clock64();
+  if (warp == 8) {
+    constexpr uint32_t IDESC_S = make_idesc(FMT_BF16, 128, 128, 0, 0);
+    constexpr uint32_t IDESC_A = make_idesc(FMT_BF16, 128, 64, 0, 1);
+    const uint64_t dA = make_sdesc_sw128(smem_u32(smem), 16, 1024);
+    const uint64_t dB = make_sdesc_sw128(smem_u32(smem + 16384), 16, 1024);
+    const uint64_t dBmn = make_sdesc_sw128(smem_u32(smem + 16384), 8192, 1024);
+    int r = 0;
+    while (MMAMODE != 0 && clock64() - t_start < span) {
+      if (elect_one()) {
+        for (int k = 0; k < 8; ++k) {
+          if (MMAMODE == 1) mma_f16_ss(tmem + 256, dA + (uint64_t)((k & 3) * 2), dB + (uint64_t)((k & 3) * 2), IDESC_S, 1u);
+          else mma_f16_ts(tmem + 448, tmem + 384 + k * 8, dBmn + (uint64_t)(k * 128), IDESC_A, 1u);
+        }
+        tc_commit(&bar);
+      }
+      __syncwarp();
+      mbar_wait(&bar, r & 1);
+      ++r;
+    }
+  } else {
+    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (warp >> 2) * 64;
+    uint32_t a[32], b[32], c[32], d[32];
+    uint32_t acc = 0;
+    int n = 0;
+    while (clock64() - t_start < span) {
+      tmem_ld32(taddr, a);
+      tmem_ld32(taddr + 32, b);
+      tmem_ld32(taddr + 128, c);
+      tmem_ld32(taddr + 160, d);
+      tc_wait_ld();
+      acc ^= a[1] ^ b[2] ^ c[3] ^ d[4];
+      ++n;
+    }
+    if ((tid & 31) == 0) iters[warp] = n;
+    if (acc == 77u) out[7] = 1;
+  }
+  __syncthreads();
+  if (tid == 0 && blockIdx.x == 0) {
+    int tot = 0;
+    for (int w = 0; w < 8; ++w) tot += iters[w];
+    out[0] = tot;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
 // ------------------------------------------------------------------------------------------------ TMA reduce
 __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
   asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
@@ -383,6 +454,24 @@ int main() {
            h[2], h[0], h[3], h[1]);                                                                                    \
   }
     RUN_CL(0, 0) RUN_CL(0, 1) RUN_CL(1, 0) RUN_CL(1, 1) RUN_CL(2, 0) RUN_CL(2, 1)
+  }
+  // ---- LDTM bandwidth while the tensor pipe runs
+  {
+    const int smem = 16384 + 32768 + 1024;
+    long long* out;
+    CK(cudaMalloc(&out, 64));
+#define RUN_LM(M)                                                                                              \
+  {                                                                                                            \
+    CK(cudaFuncSetAttribute(ldtm_under_mma_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));     \
+    long long h[1];                                                                                            \
+    for (int rep = 0; rep < 2; ++rep) {                                                                        \
+      ldtm_under_mma_kernel<M><<<148, 288, smem>>>(out, 200000);                                               \
+      CK(cudaDeviceSynchronize());                                                                             \
+    }                                                                                                          \
+    CK(cudaMemcpy(h, out, 8, cudaMemcpyDeviceToHost));                                                         \
+    printf(" \"ldtm_x32_8warps_mma_mode%d_bytes_per_clk_per_sm\": %.1f,\n", M, h[0] * 16384.0 / 200000.0);      \
+  }
+    RUN_LM(0) RUN_LM(1) RUN_LM(2)
   }
   // ---- TMA reduce-add and red.v4
   {
