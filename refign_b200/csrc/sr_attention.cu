@@ -368,7 +368,7 @@ sr_attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&bars->s_full[t], 1);
-      mbar_init(&bars->p_full[t], 128);
+      mbar_init(&bars->p_full[t], 4);
       mbar_init(&bars->o_full[t], 1);
       mbar_init(&bars->s_free[t], 128);
     }
@@ -410,8 +410,12 @@ sr_attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
     if (UNI || lane == 0) {
       const uint64_t descQ[2] = {make_sdesc_sw128(smem_u32(sQ), 16, 1024),
                                  make_sdesc_sw128(smem_u32(sQ + AT_TILE_BYTES), 16, 1024)};
+      // ring-stage descriptors built once: stage st adds st * (stage bytes >> 4) to the 14-bit start-address field
+      constexpr uint64_t STEP = (uint64_t)((2 * AT_TILE_BYTES) >> 4);
+      const uint64_t descK0 = make_sdesc_sw128(smem_u32(ring), 16, 1024);
+      const uint64_t descV0 = make_sdesc_sw128(smem_u32(ring + AT_TILE_BYTES), 8192, 1024);
       auto issue_s = [&](int t, int j) {
-        const uint64_t descK = make_sdesc_sw128(smem_u32(ring + (j % AT2_STAGES) * 2 * AT_TILE_BYTES), 16, 1024);
+        const uint64_t descK = descK0 + (uint64_t)(j % AT2_STAGES) * STEP;
         if (!UNI || elect_one()) {
 #pragma unroll
           for (int k = 0; k < AT_D / 16; ++k)
@@ -427,8 +431,7 @@ sr_attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
       issue_s(1, 0);
       for (int j = 0; j < nchunks; ++j) {
         const int st = j % AT2_STAGES;
-        const uint64_t descV =
-            make_sdesc_sw128(smem_u32(ring + st * 2 * AT_TILE_BYTES + AT_TILE_BYTES), 8192, 1024);
+        const uint64_t descV = descV0 + (uint64_t)st * STEP;
         if (j + 1 < nchunks) mbar_wait(&bars->kv_full[(j + 1) % AT2_STAGES], ((j + 1) / AT2_STAGES) & 1);
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
@@ -460,7 +463,9 @@ sr_attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
       tc_fence_after();
       const int kvalid = M - j * AT_BN;
       const bool full = kvalid >= AT_BN;               // only the last chunk of a ragged M needs masking
-      const float mx = full ? attn_row_max<false>(tS, kvalid) : attn_row_max<true>(tS, kvalid);
+      // S is read ONCE: four tcgen05.ld in flight, one wait (every ld + wait round trip costs ~100 cycles of latency)
+      AttnRow srow;
+      const float mx = full ? attn_load_max<false>(tS, kvalid, srow) : attn_load_max<true>(tS, kvalid, srow);
       // lazy rescale: move the reference maximum only when it is exceeded by more than 2^8
       const bool move = (mx - m_run) * scale_log2 > 8.f;   // true on the first chunk (m_run = -inf)
       if (j > 0) {   // PV(j-1) must have consumed P(j-1) (and landed in O) before P / O are touched again
@@ -472,25 +477,26 @@ sr_attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
         const float alpha = fast_exp2((m_run - m_new) * scale_log2);   // 0 on the first chunk, 1 for rows that stay
         m_run = m_new;
         l_run *= alpha;
-        if (j > 0) {
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t v[32];
-            tmem_ld32(tO + c * 32, v);
+        if (j > 0) {   // rare (lazy rescale): 16 columns at a time, the 128 score registers stay live
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t v[16];
+            tmem_ld16(tO + c * 16, v);
             tc_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-            tmem_st32(tO + c * 32, v);
+            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st16(tO + c * 16, v);
           }
         }
       }
       const float mneg = -m_run * scale_log2;
-      const float rs = full ? attn_exp_pack<false>(tS, tP, scale_log2, mneg, kvalid)
-                            : attn_exp_pack<true>(tS, tP, scale_log2, mneg, kvalid);
+      const float rs = full ? attn_exp_pack_regs<false>(srow, tP, scale_log2, mneg, kvalid)
+                            : attn_exp_pack_regs<true>(srow, tP, scale_log2, mneg, kvalid);
       l_run += rs;
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive(&bars->p_full[t]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->p_full[t]);   // one arrival per warp (128 per-thread arrivals serialise in the barrier unit)
     }
     mbar_wait(&bars->o_full[t], (nchunks - 1) & 1);
     tc_fence_after();
