@@ -199,6 +199,17 @@ int rf_sr_attention_bwd(const void* q, const void* kv, const void* out, const vo
                         const float* lse, void* grad_q, float* grad_kv_f32, void* workspace,
                         int B, int N, int M, int heads, float scale, void* stream);
 
+/* fp32 variants of the same two operators for the fp32 PARITY mode (precision='fp32'): exact FFMA tiles with expf /
+ * logf, same fused formulation (no [B,heads,N,M] matrix; q / kv read in place; lse saved for the backward), so the
+ * parity mode runs through the C-ABI too instead of library batched GEMMs + softmax
+ * (models/backbones/mix_transformer.py:150-160).  All tensors f32; grad_kv is [B,M,2*heads*64] (dK | dV). */
+int rf_sr_attention_f32_fwd(const float* q, const float* kv, float* out, float* lse, int B, int N, int M, int heads,
+                            int head_dim /* 64 or 32 */, float scale, void* stream);
+int64_t rf_sr_attention_f32_bwd_workspace_bytes(int B, int N, int heads);
+int rf_sr_attention_f32_bwd(const float* q, const float* kv, const float* out, const float* grad_out, const float* lse,
+                            float* grad_q, float* grad_kv, void* workspace, int B, int N, int M, int heads, int head_dim,
+                            float scale, void* stream);
+
 /* ---- stage-1 OverlapPatchEmbed: 7x7/s4 conv (3 -> 32|64 channels) + LayerNorm ---- */
 /* Replaces OverlapPatchEmbed.forward for patch_embed1 (models/backbones/mix_transformer.py:236-242,
  * LayerNorm eps 1e-5 :234): conv + NCHW->NLC transpose + LayerNorm in one pass.

