@@ -360,6 +360,23 @@ int rf_adamw_step_dev(float* param, const float* grad, float* exp_avg, float* ex
                       float beta1, float beta2, float eps, float grad_scale, const float* hyper,
                       void* stream);
 
+/* ---- DACS strong transform (class mix + colour jitter + gaussian blur) ---------------------------------- */
+/* Replaces get_dacs_mix's per-image loop over helpers/dacs_transforms.py strong_transform
+ * (models/segmentation_model.py:552-570; dacs_transforms.py:14-112; kornia 0.5.8 ColorJitter / GaussianBlur2d).
+ *   rf_dacs_count : count_u64[0] = #{prob >= threshold} over n pixels (zeroed by the call)
+ *   rf_dacs_mix   : mix_mask u8 [B,H,W] (1 = source pixel); img_* f32 [B,3,H,W]; gt_src / pseudo_label i64 [B,H,W];
+ *                   out_weight = mask ? 1 : count / (B*H*W) (0 in the first ignore_top / last ignore_bottom rows);
+ *                   params f32 [B,64] on the device: [0] jitter on, [1..4] order of (brightness, contrast, saturation,
+ *                   hue), [5] brightness shift, [6] contrast factor, [7] saturation factor, [8] hue shift (radians),
+ *                   [9] blur on, [10] / [11] tap radius along y / x (<= 16), [12..28] / [29..45] half kernels
+ *   rf_dacs_blur  : separable gaussian with reflect border on img f32 [B,3,H,W], in place (tmp = same-size scratch);
+ *                   images whose blur flag is 0 are left untouched */
+int rf_dacs_count(const float* prob, int64_t n, float threshold, void* count_u64, void* stream);
+int rf_dacs_mix(const float* img_src, const float* img_trg, const int64_t* gt_src, const int64_t* pseudo_label,
+                const void* count_u64, const uint8_t* mix_mask, const float* params, float* out_img, int64_t* out_label,
+                float* out_weight, int B, int H, int W, int ignore_top, int ignore_bottom, void* stream);
+int rf_dacs_blur(float* img, float* tmp, const float* params, int B, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -899,6 +899,40 @@ def sr_conv(x, H, W, conv):
 
 
 # --------------------------------------------------------------------------
+# DACS strong transform (reference: models/segmentation_model.py:525-582, helpers/dacs_transforms.py)
+# --------------------------------------------------------------------------
+def dacs_mix(images_src, images_trg, gt_src, pseudo_label, pseudo_prob, threshold, ignore_top, ignore_bottom, mix_mask,
+             params, blur=True):
+    """Class mix of (source, target) images / labels / weights + kornia-0.5.8 colour jitter (+ separable gaussian blur)
+    for a whole batch in one fused kernel (csrc/dacs.cu).  ``mix_mask`` u8 [B,H,W] (1 = source pixel), ``params`` the
+    DEVICE copy of dacs_transforms.draw_strong_params ([B,64] f32).  Returns (mixed image f32 [B,3,H,W], mixed label
+    i64 [B,H,W], mixed pixel weight f32 [B,H,W]); the weight of a target pixel is the fraction of pseudo-label
+    confidences >= threshold (0 in the ignored top / bottom rows), of a source pixel 1."""
+    require_cuda(images_src, images_trg, gt_src, pseudo_label, pseudo_prob, mix_mask, params)
+    B, C, H, W = images_trg.shape
+    assert C == 3 and images_src.shape == images_trg.shape and params.shape == (B, 64) and params.dtype == torch.float32
+    src, trg = _f32c(images_src), _f32c(images_trg)
+    gt, pl, pp = gt_src.contiguous(), pseudo_label.contiguous(), _f32c(pseudo_prob)
+    assert gt.dtype == torch.int64 and pl.dtype == torch.int64 and mix_mask.dtype == torch.uint8
+    mask = mix_mask.contiguous()
+    dev = trg.device
+    count = torch.empty(1, dtype=torch.int64, device=dev)
+    out_img = torch.empty_like(trg)
+    out_lbl = torch.empty(B, H, W, dtype=torch.int64, device=dev)
+    out_w = torch.empty(B, H, W, dtype=torch.float32, device=dev)
+    n = B * H * W
+    with torch.cuda.device(dev):
+        _run("rf_dacs_count", ptr(pp), pp.numel(), float(threshold), ptr(count), _stream(), work=(4 * n, n))
+        _run("rf_dacs_mix", ptr(src), ptr(trg), ptr(gt), ptr(pl), ptr(count), ptr(mask), ptr(params.contiguous()), ptr(out_img),
+             ptr(out_lbl), ptr(out_w), B, H, W, int(ignore_top), int(ignore_bottom), _stream(),
+             work=(n * (2 * 12 + 16 + 1 + 12 + 8 + 4), 40 * n))
+        if blur:
+            tmp = torch.empty_like(out_img)
+            _run("rf_dacs_blur", ptr(out_img), ptr(tmp), ptr(params), B, H, W, _stream(), work=(4 * 12 * n, 2 * 21 * 3 * n))
+    return out_img, out_lbl, out_w
+
+
+# --------------------------------------------------------------------------
 # MiT operators (reference: models/backbones/mix_transformer.py)
 # --------------------------------------------------------------------------
 FUSED_ATTENTION = True

@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import hrda, ops, runtime
+from . import dacs_transforms, hrda, ops, runtime
 from .dacs_transforms import get_class_masks, strong_transform
 from .matching_utils import estimate_probability_of_confidence_interval_of_mixture_density, warp
 from .modules import DropPath
@@ -651,14 +651,25 @@ class DomainAdaptationSegmentationModel(_Base):
         nt = images_trg.shape[0]
         if images_src.shape[0] > nt:
             images_src, gt_src = images_src[:nt], gt_src[:nt]
-        strong = {'mix': None, 'color_jitter': random.uniform(0, 1), 'color_jitter_s': self.color_jitter_s,
-                  'color_jitter_p': self.color_jitter_p, 'blur': random.uniform(0, 1) if self.blur else 0}
+        # the per-batch draws of the reference (:544-549) and, per image, kornia's jitter factors / blur sigma
+        H, W = images_trg.shape[-2:]
+        params = dacs_transforms.draw_strong_params(nt, H, W, random.uniform(0, 1), self.color_jitter_s,
+                                                    self.color_jitter_p, random.uniform(0, 1) if self.blur else 0)
         fp = fused if fused is not None else self._fused_pseudo
         if fp is not None and fp[0] is probs_trg and fp[1] is not None:
             pseudo_label, pseudo_prob = fp[1], fp[2]
         else:
             pseudo_prob, pseudo_label = torch.max(probs_trg, dim=1)
         self._fused_pseudo = None
+        mix_masks = get_class_masks(gt_src.unsqueeze(1))
+        if images_trg.is_cuda:
+            # B200 path: ONE fused kernel for the whole batch (+ the two blur passes) instead of the per-image loop
+            mask = torch.cat(mix_masks).view(nt, H, W)
+            if mask.dtype != torch.uint8:
+                mask = mask.to(torch.uint8)
+            return ops.dacs_mix(images_src, images_trg, gt_src, pseudo_label, pseudo_prob, self.pseudo_label_threshold,
+                                self.psweight_ignore_top, self.psweight_ignore_bottom, mask,
+                                self._dacs_params_to_device(params, images_trg.device), blur=bool(self.blur))
         frac = (pseudo_prob >= self.pseudo_label_threshold).sum() / pseudo_label.numel()
         pseudo_weight = frac.to(pseudo_prob.dtype).expand_as(pseudo_prob).clone()
         if self.psweight_ignore_top > 0:
@@ -666,15 +677,27 @@ class DomainAdaptationSegmentationModel(_Base):
         if self.psweight_ignore_bottom > 0:
             pseudo_weight[:, -self.psweight_ignore_bottom:, :] = 0
         gt_weight = torch.ones_like(pseudo_weight)
-        mix_masks = get_class_masks(gt_src.unsqueeze(1))
         mixed_img, mixed_lbl = [None] * nt, [None] * nt
         for i in range(nt):
-            strong['mix'] = mix_masks[i]
+            strong = {'mix': mix_masks[i], 'row': params[i]}
             mixed_img[i], mixed_lbl[i] = strong_transform(
                 strong, data=torch.stack((images_src[i], images_trg[i])),
                 target=torch.stack((gt_src[i], pseudo_label[i])))
             _, pseudo_weight[i] = strong_transform(strong, target=torch.stack((gt_weight[i], pseudo_weight[i])))
         return torch.cat(mixed_img), torch.cat(mixed_lbl).squeeze(1), pseudo_weight
+
+    def _dacs_params_to_device(self, params, device):
+        """Async H2D copy of the augmentation parameter block through a small ring of pinned buffers (the host runs
+        ahead of the device: a single staging buffer could be rewritten before its copy has executed)."""
+        ring = getattr(self, '_dacs_ring', None)
+        if ring is None or ring['host'][0].shape != params.shape or ring['dev'].device != device:
+            ring = self._dacs_ring = {'host': [torch.empty_like(params).pin_memory() for _ in range(8)], 'i': 0,
+                                      'dev': torch.empty_like(params, device=device)}
+        h = ring['host'][ring['i'] % 8]
+        ring['i'] += 1
+        h.copy_(params)
+        ring['dev'].copy_(h, non_blocking=True)
+        return ring['dev']
 
     # ---- ImageNet feature distance (reference :584-668) --------------------------------------------
     def calc_feat_dist(self, img, gt, feat=None, feat_imnet=None):
