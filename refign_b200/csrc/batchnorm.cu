@@ -140,6 +140,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, const float* 
                                    const float* __restrict__ beta, float* __restrict__ mean, float* __restrict__ rstd,
                                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ run_mean,
                                    float* __restrict__ run_var, int C, float count, float eps, float momentum) {
+  if (count <= 0.f) count = sums[2 * C];   // SyncBN with per-rank sample counts: the all-reduced count travels behind the sums
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float m = sums[c] / count;
@@ -166,6 +167,7 @@ __global__ void __launch_bounds__(256)
 bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ mean,
                 const float* __restrict__ rstd, const float* __restrict__ scale, const float* __restrict__ shift,
                 const float* __restrict__ sums, T* __restrict__ out, long rows, int C, float inv_count, int relu) {
+  if (MODE == 1 && inv_count <= 0.f) inv_count = 1.f / __ldg(sums + 2 * C);   // all-reduced sample count behind the sums (SyncBN)
   const int CG = C / 8;
   const long tid = blockIdx.x * (long)blockDim.x + threadIdx.x;
   const long nthr = (long)gridDim.x * blockDim.x;       // multiple of CG
@@ -261,7 +263,7 @@ extern "C" int rf_bn_stats(const void* x, float* sums, int64_t rows, int C, int 
 extern "C" int rf_bn_finalize(const float* sums, const float* gamma, const float* beta, float* mean, float* rstd,
                               float* scale, float* shift, float* running_mean, float* running_var, int C,
                               double count, float eps, float momentum, void* stream) {
-  RF_REQUIRE(sums && mean && rstd && scale && shift && C > 0 && count >= 1.0, "rf_bn_finalize: bad argument");
+  RF_REQUIRE(sums && mean && rstd && scale && shift && C > 0 && (count >= 1.0 || count == 0.0), "rf_bn_finalize: bad argument");
   RF_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "rf_bn_finalize: running statistics go together");
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, gamma, beta, mean, rstd, scale, shift,
                                                                          running_mean, running_var, C, (float)count, eps,
@@ -305,10 +307,10 @@ extern "C" int rf_bn_bwd_apply(const void* x, const void* grad_y, const float* m
                                int C, double count, int relu, int dtype, void* stream) {
   int rc = bn_check(x, rows, C, dtype, "rf_bn_bwd_apply");
   if (rc != RF_OK) return rc;
-  RF_REQUIRE(grad_y && mean && rstd && scale && shift && sums && grad_x && count >= 1.0, "rf_bn_bwd_apply: bad argument");
+  RF_REQUIRE(grad_y && mean && rstd && scale && shift && sums && grad_x && (count >= 1.0 || count == 0.0), "rf_bn_bwd_apply: bad argument");
   const long blocks = bn_apply_blocks(rows, C);
   cudaStream_t st = (cudaStream_t)stream;
-  const float inv = (float)(1.0 / count);
+  const float inv = count > 0.0 ? (float)(1.0 / count) : 0.f;   // 0: the kernel reads the all-reduced count from sums[2C]
   if (dtype == 1)
     bn_apply_kernel<__nv_bfloat16, 1><<<(int)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)grad_y,
                                                                    mean, rstd, scale, shift, sums, (__nv_bfloat16*)grad_x,

@@ -23,6 +23,7 @@
 
 #include "rf_common.cuh"
 #include "rf_sm100.cuh"
+#include "rf_trace.cuh"
 
 namespace rf {
 using namespace sm100;
@@ -291,33 +292,33 @@ __device__ __forceinline__ float attn_load_max(uint32_t tS, int kvalid, AttnRow&
 template <bool MASK>
 __device__ __forceinline__ float attn_exp_pack_regs(const AttnRow& row, uint32_t tP, float scale_log2, float mneg,
                                                     int kvalid) {
-  float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+  // packed fp32 pipe (FFMA2 / FADD2): 5 issue slots per PAIR of scores around its two MUFU.EX2
+  const float2 sl = make_float2(scale_log2, scale_log2), mn = make_float2(mneg, mneg);
+  float2 r01 = make_float2(0.f, 0.f), r23 = make_float2(0.f, 0.f);
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     uint32_t pk[16];
 #pragma unroll
     for (int i = 0; i < 16; i += 2) {
-      float p0 = fast_exp2(fmaf(__uint_as_float(row.v[c][2 * i + 0]), scale_log2, mneg));
-      float p1 = fast_exp2(fmaf(__uint_as_float(row.v[c][2 * i + 1]), scale_log2, mneg));
-      float p2 = fast_exp2(fmaf(__uint_as_float(row.v[c][2 * i + 2]), scale_log2, mneg));
-      float p3 = fast_exp2(fmaf(__uint_as_float(row.v[c][2 * i + 3]), scale_log2, mneg));
+      const float2 a = __ffma2_rn(make_float2(__uint_as_float(row.v[c][2 * i + 0]), __uint_as_float(row.v[c][2 * i + 1])), sl, mn);
+      const float2 b = __ffma2_rn(make_float2(__uint_as_float(row.v[c][2 * i + 2]), __uint_as_float(row.v[c][2 * i + 3])), sl, mn);
+      float2 p01 = make_float2(fast_exp2(a.x), fast_exp2(a.y));
+      float2 p23 = make_float2(fast_exp2(b.x), fast_exp2(b.y));
       if (MASK) {
-        if (c * 32 + 2 * i + 0 >= kvalid) p0 = 0.f;
-        if (c * 32 + 2 * i + 1 >= kvalid) p1 = 0.f;
-        if (c * 32 + 2 * i + 2 >= kvalid) p2 = 0.f;
-        if (c * 32 + 2 * i + 3 >= kvalid) p3 = 0.f;
+        if (c * 32 + 2 * i + 0 >= kvalid) p01.x = 0.f;
+        if (c * 32 + 2 * i + 1 >= kvalid) p01.y = 0.f;
+        if (c * 32 + 2 * i + 2 >= kvalid) p23.x = 0.f;
+        if (c * 32 + 2 * i + 3 >= kvalid) p23.y = 0.f;
       }
-      r0 += p0;
-      r1 += p1;
-      r2 += p2;
-      r3 += p3;
-      const __nv_bfloat162 h0 = __floats2bfloat162_rn(p0, p1), h1 = __floats2bfloat162_rn(p2, p3);
+      r01 = __fadd2_rn(r01, p01);
+      r23 = __fadd2_rn(r23, p23);
+      const __nv_bfloat162 h0 = __floats2bfloat162_rn(p01.x, p01.y), h1 = __floats2bfloat162_rn(p23.x, p23.y);
       pk[i] = *reinterpret_cast<const uint32_t*>(&h0);
       pk[i + 1] = *reinterpret_cast<const uint32_t*>(&h1);
     }
     tmem_st16(tP + c * 16, pk);
   }
-  return (r0 + r1) + (r2 + r3);
+  return (r01.x + r01.y) + (r23.x + r23.y);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -349,6 +350,8 @@ __global__ void __launch_bounds__(AT2_THREADS, 1)
 sr_attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                            __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int N, int M, int heads,
                            float scale_log2) {
+  WS_T_INIT();
+  WS_T(0);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;                                   // 2 tiles
@@ -370,7 +373,7 @@ sr_attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
       mbar_init(&bars->s_full[t], 1);
       mbar_init(&bars->p_full[t], 4);
       mbar_init(&bars->o_full[t], 1);
-      mbar_init(&bars->s_free[t], 128);
+      mbar_init(&bars->s_free[t], 4);
     }
     fence_barrier_init();
   }
@@ -432,12 +435,24 @@ sr_attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
       for (int j = 0; j < nchunks; ++j) {
         const int st = j % AT2_STAGES;
         const uint64_t descV = descV0 + (uint64_t)st * STEP;
-        if (j + 1 < nchunks) mbar_wait(&bars->kv_full[(j + 1) % AT2_STAGES], ((j + 1) / AT2_STAGES) & 1);
+        if (j + 1 < nchunks) {
+          mbar_wait(&bars->kv_full[(j + 1) % AT2_STAGES], ((j + 1) / AT2_STAGES) & 1);
+          // the next scores are queued as soon as warpgroup t holds S(j) in registers -- not after it has written P(j):
+          // S(j+1) is then long finished when the warpgroup comes back for it (the commit -> wake-up -> issue -> MMA
+          // round trip, ~500 cycles, leaves the per-tile critical path)
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            mbar_wait(&bars->s_free[t], j & 1);
+            tc_fence_after();
+            WS_T(20 + t);
+            issue_s(t, j + 1);
+          }
+        }
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
-          mbar_wait(&bars->p_full[t], j & 1);   // warpgroup t has consumed S(j) and written P(j)
+          mbar_wait(&bars->p_full[t], j & 1);   // warpgroup t has written P(j)
           tc_fence_after();
-          if (j + 1 < nchunks) issue_s(t, j + 1);   // next scores first: the warpgroup is waiting for them
+          WS_T(22 + t);
           if (!UNI || elect_one()) {
 #pragma unroll
             for (int k = 0; k < AT_BN / 16; ++k)
@@ -458,20 +473,31 @@ sr_attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t tS = tmem + t * 256 + lane_off, tO = tS + 128, tP = tS + 192;
     float m_run = -INFINITY, l_run = 0.f;            // m_run: the (possibly stale) maximum rows are normalised by
+    // The exponential phases of the two warpgroups ALTERNATE (named barriers 1 + t, the FlashAttention-3 "ping-pong"):
+    // measured on B200, both warpgroups otherwise run in lockstep, share the 16 ex2/clk of the SM during their
+    // simultaneous MUFU phases (2 x 1024 cycles) and leave the MUFU idle during their simultaneous load / max / wait
+    // phases (~1 200 cycles) -- alternating lets one warpgroup's non-MUFU work hide under the other's exponentials.
+    if (t == 1) asm volatile("bar.arrive 1, 256;" ::: "memory");   // warpgroup 0 goes first
     for (int j = 0; j < nchunks; ++j) {
       mbar_wait(&bars->s_full[t], j & 1);
       tc_fence_after();
+      WS_T(10);
       const int kvalid = M - j * AT_BN;
       const bool full = kvalid >= AT_BN;               // only the last chunk of a ragged M needs masking
       // S is read ONCE: four tcgen05.ld in flight, one wait (every ld + wait round trip costs ~100 cycles of latency)
       AttnRow srow;
       const float mx = full ? attn_load_max<false>(tS, kvalid, srow) : attn_load_max<true>(tS, kvalid, srow);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->s_free[t]);   // S(j) is in registers: the MMA warp may overwrite it with S(j+1)
+      WS_T(11);
       // lazy rescale: move the reference maximum only when it is exceeded by more than 2^8
       const bool move = (mx - m_run) * scale_log2 > 8.f;   // true on the first chunk (m_run = -inf)
       if (j > 0) {   // PV(j-1) must have consumed P(j-1) (and landed in O) before P / O are touched again
         mbar_wait(&bars->o_full[t], (j - 1) & 1);
         tc_fence_after();
       }
+      WS_T(12);
       if (__any_sync(0xffffffffu, move)) {
         const float m_new = move ? mx : m_run;
         const float alpha = fast_exp2((m_run - m_new) * scale_log2);   // 0 on the first chunk, 1 for rows that stay
@@ -490,13 +516,17 @@ sr_attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
         }
       }
       const float mneg = -m_run * scale_log2;
+      if (t == 0) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 2, 256;" ::: "memory");
+      WS_T(13);
       const float rs = full ? attn_exp_pack_regs<false>(srow, tP, scale_log2, mneg, kvalid)
                             : attn_exp_pack_regs<true>(srow, tP, scale_log2, mneg, kvalid);
+      if (t == 0) asm volatile("bar.arrive 2, 256;" ::: "memory"); else asm volatile("bar.arrive 1, 256;" ::: "memory");
       l_run += rs;
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->p_full[t]);   // one arrival per warp (128 per-thread arrivals serialise in the barrier unit)
+      WS_T(14);
     }
     mbar_wait(&bars->o_full[t], (nchunks - 1) & 1);
     tc_fence_after();
@@ -526,6 +556,8 @@ sr_attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
   }
   tc_fence_before();
   __syncthreads();
+  WS_T(2);
+  WS_T_FLUSH();
   if (warp == 8) tmem_dealloc<512>(tmem);
 }
 

@@ -34,6 +34,7 @@
 
 #include "rf_common.cuh"
 #include "rf_sm100.cuh"
+#include "rf_trace.cuh"
 
 namespace rf {
 using namespace sm100;
@@ -64,37 +65,6 @@ struct WsParams {
   int n_kv_units, kv_blocks, kv_splits, tiles_per_split, q_tiles;
   float scale, scale_log2;
 };
-
-// Optional per-phase timeline (tools/trace_attn_bwd.cu builds this file with -DWS_TRACE): lane 0 of softmax warp 0,
-// of the MMA warp and of the TMA warp of two chosen blocks append (tag << 48 | clock) records.
-#ifdef WS_TRACE
-__device__ long long* g_ws_trace;
-__device__ int g_ws_trace_blocks[2];
-__shared__ long long ws_trace_buf[11][256];     // per traced warp: [0] = count, then (tag << 48 | clock) records
-// inline and in shared memory: a call would spill the ~128 live score registers around every probe, a global
-// counter costs a ~400-cycle round trip per probe
-__device__ __forceinline__ void ws_trace(int tag) {
-  const int warp = threadIdx.x >> 5;
-  if ((threadIdx.x & 31) != 0) return;
-  long long* base = ws_trace_buf[warp];
-  const int n = (int)base[0];
-  if (n < 254) {
-    base[1 + n] = ((long long)tag << 48) | (clock64() & 0xffffffffffffll);
-    base[0] = n + 1;
-  }
-}
-__device__ __forceinline__ void ws_trace_init() {
-  if (threadIdx.x < 11) ws_trace_buf[threadIdx.x][0] = 0;
-}
-__device__ __forceinline__ void ws_trace_flush() {   // after the final __syncthreads
-  const int slot = (int)blockIdx.x == g_ws_trace_blocks[0] ? 0 : ((int)blockIdx.x == g_ws_trace_blocks[1] ? 1 : -1);
-  if (slot < 0) return;
-  for (int i = threadIdx.x; i < 11 * 256; i += blockDim.x) g_ws_trace[slot * 11 * 256 + i] = ws_trace_buf[i >> 8][i & 255];
-}
-#define WS_T(tag) ws_trace(tag)
-#else
-#define WS_T(tag)
-#endif
 
 __device__ __forceinline__ uint32_t ws_pack_bf16(float a, float b) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -471,10 +441,7 @@ __device__ __forceinline__ void ws_role_q(const CUtensorMap& tm_q, const CUtenso
 __global__ void __launch_bounds__(WS_THREADS, 1)
 sr_attention_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
                            const __grid_constant__ CUtensorMap tm_kv, const WsParams p) {
-#ifdef WS_TRACE
-  ws_trace_init();
-  __syncthreads();
-#endif
+  WS_T_INIT();
   WS_T(0);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -515,10 +482,7 @@ sr_attention_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
   tc_fence_before();
   __syncthreads();
   WS_T(2);
-#ifdef WS_TRACE
-  __syncthreads();
-  ws_trace_flush();
-#endif
+  WS_T_FLUSH();
   if (warp == 8) tmem_dealloc<512>(tmem);
 }
 

@@ -423,7 +423,10 @@ class _BatchNormAct(torch.autograd.Function):
         dt = _dt_code(x)
         dev = x.device
         f32 = dict(device=dev, dtype=torch.float32)
-        sums = torch.empty(2 * C, **f32)
+        sync = group is not None and world > 1
+        # SyncBN: the per-rank sample count travels behind the sums in the same all-reduce (ranks may hold different
+        # batch sizes -- torch.nn.SyncBatchNorm gathers the counts too); the kernels then read the global count there
+        sums = torch.empty(2 * C + (1 if sync else 0), **f32)
         stats = torch.empty(4, C, **f32)                     # mean, rstd, scale, shift
         y = torch.empty_like(x)
         w = None if weight is None else _f32c(weight)
@@ -432,9 +435,10 @@ class _BatchNormAct(torch.autograd.Function):
         with torch.cuda.device(dev):
             _run("rf_bn_stats", ptr(x), ptr(sums), rows, C, dt, _stream(), work=(nbytes, 3 * x.numel()), tag="bn_stats")
             count = rows
-            if group is not None and world > 1:
+            if sync:
+                sums[2 * C:].fill_(float(rows))
                 torch.distributed.all_reduce(sums, group=group)
-                count = rows * world
+                count = 0      # "read the all-reduced count from sums[2C]"
             _run("rf_bn_finalize", ptr(sums), ptr(w), ptr(b), ptr(stats[0]), ptr(stats[1]), ptr(stats[2]),
                  ptr(stats[3]), ptr(running_mean), ptr(running_var), C, float(count), float(eps), float(momentum),
                  _stream(), tag="bn_finalize")
@@ -455,7 +459,8 @@ class _BatchNormAct(torch.autograd.Function):
         gy = gy.contiguous()
         if gy.dtype != x.dtype:
             gy = gy.to(x.dtype)
-        sums = torch.empty(2 * C, device=x.device, dtype=torch.float32)
+        sync = group is not None and world > 1
+        sums = torch.empty(2 * C + (1 if sync else 0), device=x.device, dtype=torch.float32)
         gx = torch.empty_like(x)
         nbytes = x.numel() * x.element_size()
         with torch.cuda.device(x.device):
@@ -463,8 +468,9 @@ class _BatchNormAct(torch.autograd.Function):
                  ptr(sums), rows, C, int(relu), dt, _stream(), work=(2 * nbytes, 6 * x.numel()), tag="bn_bwd_reduce")
             # local sums are the parameter gradients (the runtime all-reduces all gradients at the end)
             gb = sums[:C].clone() if has_b else None
-            gw = sums[C:].clone() if has_w else None
-            if group is not None and world > 1:
+            gw = sums[C:2 * C].clone() if has_w else None
+            if sync:
+                sums[2 * C:].fill_(float(rows))
                 torch.distributed.all_reduce(sums, group=group)
             _run("rf_bn_bwd_apply", ptr(x), ptr(gy), ptr(stats[0]), ptr(stats[1]), ptr(stats[2]), ptr(stats[3]),
                  ptr(sums), ptr(gx), rows, C, float(count), int(relu), dt, _stream(),

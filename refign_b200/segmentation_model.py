@@ -155,14 +155,32 @@ class DomainAdaptationSegmentationModel(_Base):
         self.load_weights(pretrained)
 
     # ---- what Lightning would provide ---------------------------------------------------------------
-    def setup_runtime(self, process_group=None, world_size=1, betas=(0.9, 0.999), eps=1e-8, sync_batchnorm=None):
+    def setup_runtime(self, process_group=None, world_size=1, betas=(0.9, 0.999), eps=1e-8, sync_batchnorm=None,
+                      teacher_process_group=None):
         """Flat parameter/gradient/EMA buffers + fused optimiser + LR schedule (replaces
-        ``configure_optimizers`` + Lightning's DDP wrap).  Call after ``.to(device)``."""
+        ``configure_optimizers`` + Lightning's DDP wrap).  Call after ``.to(device)``.
+        ``teacher_process_group``: the communicator of the EMA teacher's SyncBatchNorm statistics.  With a communicator
+        of its own (created here when none is given and world_size > 1; every rank must call setup_runtime) the
+        teacher's collectives are ordered among themselves only, so the teacher forward can run on its side stream /
+        parallel graph branch at world_size > 1 as it does at world_size 1."""
         if sync_batchnorm is None:
             sync_batchnorm = world_size > 1
+        self._teacher_own_comm = False
         if sync_batchnorm and world_size > 1:
+            if teacher_process_group is None and torch.distributed.is_available() and torch.distributed.is_initialized():
+                ranks = (torch.distributed.get_process_group_ranks(process_group) if process_group is not None
+                         else list(range(torch.distributed.get_world_size())))
+                teacher_process_group = torch.distributed.new_group(ranks=ranks)
+            self._teacher_own_comm = teacher_process_group is not None and teacher_process_group is not process_group
+            tg = teacher_process_group if teacher_process_group is not None else process_group
+            # every BatchNorm of the model, as Lightning's sync_batchnorm=True converts it (the HRDA scale-attention
+            # heads included)
             self.head = nn.SyncBatchNorm.convert_sync_batchnorm(self.head, process_group)
-            self.m_head = nn.SyncBatchNorm.convert_sync_batchnorm(self.m_head, process_group)
+            self.m_head = nn.SyncBatchNorm.convert_sync_batchnorm(self.m_head, tg)
+            if self.hrda_scale_attention is not None:
+                self.hrda_scale_attention = nn.SyncBatchNorm.convert_sync_batchnorm(self.hrda_scale_attention, process_group)
+            if self.m_hrda_scale_attention is not None:
+                self.m_hrda_scale_attention = nn.SyncBatchNorm.convert_sync_batchnorm(self.m_hrda_scale_attention, tg)
         groups = runtime.group_parameters(self.named_parameters())
         lr = self.optimizer_init['init_args']['lr']
         wd = self.optimizer_init['init_args'].get('weight_decay', 0.01)
@@ -353,9 +371,10 @@ class DomainAdaptationSegmentationModel(_Base):
     def _teacher_has_collectives(self):
         """With world_size > 1 the teacher head's SyncBatchNorm issues NCCL all-reduces; collectives of one
         communicator must be enqueued in the same order on every rank, which parallel graph branches do not
-        guarantee -- the teacher then stays on the main stream (the collective-free alignment / ImageNet
-        branches still run concurrently)."""
-        return self._rt is not None and self._rt.get('world_size', 1) > 1
+        guarantee -- unless the teacher's SyncBatchNorm owns a communicator (setup_runtime's default), the teacher
+        then stays on the main stream (the collective-free alignment / ImageNet branches still run concurrently)."""
+        return (self._rt is not None and self._rt.get('world_size', 1) > 1
+                and not getattr(self, '_teacher_own_comm', False))
 
     def _teacher_logits(self, images_trg, images_ref):
         m_input = torch.cat((images_trg, images_ref))
