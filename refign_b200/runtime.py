@@ -140,6 +140,17 @@ class FlatAdamW:
         self.launch_step()
         self.step_count += 1
 
+    # ---- checkpoint / resume (what Lightning's checkpoint holds for torch.optim.AdamW) ----
+    def state_dict(self):
+        return {'exp_avg': self.exp_avg.detach().clone(), 'exp_avg_sq': self.exp_avg_sq.detach().clone(),
+                'step_count': int(self.step_count), 'seg_lr': list(self.seg_lr)}
+
+    def load_state_dict(self, state):
+        self.exp_avg.copy_(state['exp_avg'])
+        self.exp_avg_sq.copy_(state['exp_avg_sq'])
+        self.step_count = int(state['step_count'])
+        self.seg_lr = list(state.get('seg_lr', self.seg_lr))
+
 
 class PolyLRSchedule:
     def __init__(self, optimizer, max_steps=40000, warmup_iters=1500, warmup_ratio=1e-6, power=0.9, min_lr=0.0):
@@ -158,6 +169,13 @@ class PolyLRSchedule:
 
     def get_last_lr(self):
         return list(self.opt.seg_lr)
+
+    def state_dict(self):
+        return {'last_epoch': int(self.last_epoch)}
+
+    def load_state_dict(self, state):
+        self.last_epoch = int(state['last_epoch'])
+        self._apply()
 
 
 def ema_momentum(global_step, ema_momentum=0.999):

@@ -618,6 +618,24 @@ class DomainAdaptationSegmentationModel(_Base):
         self.load_state_dict(ckpt['state_dict'] if 'state_dict' in ckpt else ckpt, strict=True)
         self.refresh_shadows()
 
+    # ---- checkpoint / resume of the flat-buffer runtime -----------------------------------------------
+    def runtime_state_dict(self):
+        """Everything a resume needs beyond ``state_dict()`` (parameters, EMA teacher, BN statistics): the Adam moments
+        and step count, the LR-schedule position and the global step (the EMA momentum min(1 - 1/(step+1), m) restarts
+        from 0 -- i.e. overwrites the teacher with the student -- if the step is lost)."""
+        assert self._rt is not None, "call setup_runtime() first"
+        return {'optimizer': self._rt['opt'].state_dict(), 'lr_scheduler': self._rt['sch'].state_dict(),
+                'global_step': int(self.global_step)}
+
+    def load_runtime_state_dict(self, state):
+        """Restore ``runtime_state_dict()`` after ``load_state_dict`` + ``setup_runtime``."""
+        assert self._rt is not None, "call setup_runtime() first"
+        self._rt['opt'].load_state_dict(state['optimizer'])
+        self._rt['sch'].load_state_dict(state['lr_scheduler'])
+        if not _HAVE_PL:
+            self._step = int(state['global_step'])
+        self.refresh_shadows()
+
     def refresh_shadows(self):
         """Re-derive the bf16 shadow weights after the fp32 masters were changed from outside the
         runtime (checkpoint load, manual edits)."""
