@@ -360,6 +360,19 @@ int rf_adamw_step_dev(float* param, const float* grad, float* exp_avg, float* ex
                       float beta1, float beta2, float eps, float grad_scale, const float* hyper,
                       void* stream);
 
+/* ---- bf16 tensor-core GEMM with fused epilogues (Linear layers: forward, dgrad, wgrad) ---------------------- */
+/* Replaces the library GEMMs behind nn.Linear in the MiT encoder / DAFormer head
+ * (models/backbones/mix_transformer.py:96-103,137-164; models/modules.py:59-68):
+ *     out[m,n] (+)= sum_k A(m,k) * B(n,k) (+ bias[n])
+ *   a : bf16, stored [M,K] (a_mn_major = 0) or [K,M] (a_mn_major = 1);  b : bf16, stored [N,K] (0) or [K,N] (1)
+ *   out : bf16 [M,N] (out_f32 = 0) or f32 [M,N] (out_f32 = 1); accumulate = 1 (f32 only, no bias): out += product, the
+ *         contraction is split over CTAs and partial sums are added with red.global (weight gradients into the flat
+ *         gradient buffer); bias : f32 [N] or NULL.  All row pitches must be multiples of 8 elements.
+ *   forward y = x W^T + b : (a = x, b = W);   dgrad dx = dy W : (a = dy, b = W, b_mn_major = 1);
+ *   wgrad dW += dy^T x : (a = dy, a_mn_major = 1, b = x, b_mn_major = 1, out_f32 = 1, accumulate = 1). */
+int rf_gemm_bf16(const void* a, const void* b, const float* bias, void* out, int M, int N, int K, int a_mn_major,
+                 int b_mn_major, int out_f32, int accumulate, void* stream);
+
 /* ---- DACS strong transform (class mix + colour jitter + gaussian blur) ---------------------------------- */
 /* Replaces get_dacs_mix's per-image loop over helpers/dacs_transforms.py strong_transform
  * (models/segmentation_model.py:552-570; dacs_transforms.py:14-112; kornia 0.5.8 ColorJitter / GaussianBlur2d).

@@ -1,0 +1,298 @@
+// bf16 GEMM on tcgen05 with fused epilogues for the Linear layers of the MiT encoder and the DAFormer head
+// (reference: models/backbones/mix_transformer.py:96-103,137-164 q / kv / proj / fc1 / fc2 nn.Linear;
+// models/modules.py:59-68 MLP embedding) -- forward, input gradient and weight gradient through ONE kernel:
+//     out[m, n] (+)= sum_k A(m, k) * B(n, k)  (+ bias[n])
+//   forward  y  = x W^T + b : A = x  [T, K]  (K-major),  B = W [N, K] (K-major)            -> bf16 out, fp32 bias fused
+//   dgrad    dx = dy W      : A = dy [T, N]  (K-major),  B = W [N, K] read MN-major        -> bf16 out
+//   wgrad    dW += dy^T x   : A = dy [T, N] read MN-major, B = x [T, K] read MN-major      -> fp32 out, accumulated in place
+//                             (split over the token dimension, partial sums leave with red.global.add.f32 straight
+//                             into the flat gradient buffer: no scratch, no memset, no separate add)
+// Both operand layouts are consumed in place through TMA + UMMA shared-memory descriptors (128-byte swizzle; an
+// MN-major operand is a set of [64 k x 64 m] boxes, 8 KiB each): no transposed copies of weights or activations.
+//
+// Persistent, warp-specialised: warp 4 = TMA producer, warp 5 = MMA issuer, warps 0-3 = epilogue (thread = accumulator
+// row).  128 x BN output tiles (BN = 128, or 64 for narrow outputs), BK = 64, a ring of smem stages, and the 512 TMEM
+// columns as 4 (BN = 128) / 8 (BN = 64) accumulator buffers so the MMA warp runs ahead of the epilogue.  Tiles are
+// walked n-fastest so consecutive CTAs share the A rows in L2.  All barrier arrivals are one per warp / tcgen05.commit.
+#include <cuda_bf16.h>
+#include <stdlib.h>
+
+#include "rf_common.cuh"
+#include "rf_sm100.cuh"
+
+namespace rf {
+using namespace sm100;
+
+constexpr int GM_BM = 128, GM_BK = 64;
+constexpr int GM_THREADS = 192;
+constexpr int GM_A_BYTES = GM_BM * GM_BK * 2;          // 16 KiB per stage
+
+template <int BN>
+struct GmCfg {
+  static constexpr int B_BYTES = BN * GM_BK * 2;
+  static constexpr int STAGE = GM_A_BYTES + B_BYTES;
+  static constexpr int STAGES = BN == 128 ? 6 : 8;
+  static constexpr int ACC = 512 / BN;                 // accumulator buffers in TMEM
+  static constexpr int SMEM = STAGES * STAGE + 1024 + 512;
+};
+
+struct GmBars {
+  uint64_t full[8], empty[8];
+  uint64_t acc_full[8], acc_empty[8];
+  uint32_t tmem_base;
+};
+
+struct GmParams {
+  const float* bias;       // [N] or nullptr
+  void* out;               // bf16 or fp32 [M, N] row-major
+  int M, N, K;
+  int m_tiles, n_tiles, k_blocks, splits, kb_per_split;
+  int out_f32, accumulate;
+};
+
+// A / B tiles of one k-block: K-major = one box [rows x 64 k]; MN-major = rows/64 boxes [64 k x 64 rows]
+template <bool MN>
+__device__ __forceinline__ void gm_load(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int row0, int k0, int rows) {
+  if (!MN) {
+    tma_load_3d(smem_dst, tm, bar, k0, row0, 0);
+  } else {
+    for (int blk = 0; blk < rows / 64; ++blk)
+      tma_load_3d(reinterpret_cast<uint8_t*>(smem_dst) + blk * 8192, tm, bar, row0 + blk * 64, k0, 0);
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GmParams p) {
+  using Cfg = GmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  GmBars* bars = reinterpret_cast<GmBars*>(smem + Cfg::STAGES * Cfg::STAGE);
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  if (warp == 4) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tm_a);
+      tma_prefetch_desc(&tm_b);
+      for (int s = 0; s < Cfg::STAGES; ++s) {
+        mbar_init(&bars->full[s], 1);
+        mbar_init(&bars->empty[s], 1);
+      }
+      for (int s = 0; s < Cfg::ACC; ++s) {
+        mbar_init(&bars->acc_full[s], 1);
+        mbar_init(&bars->acc_empty[s], 4);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+  }
+  if (warp == 5) tmem_alloc<512>(&bars->tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = uniform_u32(bars->tmem_base);
+
+  const int tiles = p.m_tiles * p.n_tiles;
+  const long items = (long)tiles * p.splits;          // work items: (tile, k split), tile-major
+
+  if (warp == 4) {
+    // ------------------------------------------------------------------ TMA producer
+    int it = 0;
+    for (long w = blockIdx.x; w < items; w += gridDim.x) {
+      const int tile = (int)(w / p.splits), split = (int)(w % p.splits);
+      const int m0 = (tile / p.n_tiles) * GM_BM, n0 = (tile % p.n_tiles) * BN;
+      const int kb0 = split * p.kb_per_split, kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int st = it % Cfg::STAGES;
+        if (it >= Cfg::STAGES) mbar_wait(&bars->empty[st], ((it / Cfg::STAGES) - 1) & 1);
+        uint8_t* stage = smem + st * Cfg::STAGE;
+        if (elect_one()) {
+          mbar_expect_tx(&bars->full[st], Cfg::STAGE);
+          gm_load<A_MN>(stage, &tm_a, &bars->full[st], m0, kb * GM_BK, GM_BM);
+          gm_load<B_MN>(stage + GM_A_BYTES, &tm_b, &bars->full[st], n0, kb * GM_BK, BN);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t IDESC = make_idesc(FMT_BF16, GM_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    constexpr uint64_t STEP = (uint64_t)(Cfg::STAGE >> 4);
+    const uint32_t base = smem_u32(smem);
+    const uint64_t dA0 = A_MN ? make_sdesc_sw128(base, 8192, 1024) : make_sdesc_sw128(base, 16, 1024);
+    const uint64_t dB0 = B_MN ? make_sdesc_sw128(base + GM_A_BYTES, 8192, 1024) : make_sdesc_sw128(base + GM_A_BYTES, 16, 1024);
+    constexpr uint64_t KA = A_MN ? 128 : 2, KB = B_MN ? 128 : 2;   // descriptor advance per 16-element k step
+    int it = 0, local = 0;
+    for (long w = blockIdx.x; w < items; w += gridDim.x, ++local) {
+      const int split = (int)(w % p.splits);
+      const int kb0 = split * p.kb_per_split, kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
+      const int buf = local % Cfg::ACC;
+      if (local >= Cfg::ACC) mbar_wait(&bars->acc_empty[buf], ((local / Cfg::ACC) - 1) & 1);
+      tc_fence_after();
+      const uint32_t d = tmem + buf * BN;
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int st = it % Cfg::STAGES;
+        mbar_wait(&bars->full[st], (it / Cfg::STAGES) & 1);
+        tc_fence_after();
+        const uint64_t dA = dA0 + st * STEP, dB = dB0 + st * STEP;
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < GM_BK / 16; ++k)
+            mma_f16_ss(d, dA + k * KA, dB + k * KB, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+          tc_commit(&bars->empty[st]);
+          if (kb == kb1 - 1) tc_commit(&bars->acc_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (thread = accumulator row)
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    int local = 0;
+    for (long w = blockIdx.x; w < items; w += gridDim.x, ++local) {
+      const int tile = (int)(w / p.splits);
+      const int m0 = (tile / p.n_tiles) * GM_BM, n0 = (tile % p.n_tiles) * BN;
+      const int buf = local % Cfg::ACC;
+      mbar_wait(&bars->acc_full[buf], (local / Cfg::ACC) & 1);
+      tc_fence_after();
+      const int row = m0 + tid;
+      const uint32_t t = tmem + lane_off + buf * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(t + c * 32, v);
+        tc_wait_ld();
+        const int col = n0 + c * 32;
+        if (row < p.M && col < p.N) {
+          if (p.out_f32) {
+            float* o = reinterpret_cast<float*>(p.out) + (long)row * p.N + col;
+            const bool full = col + 32 <= p.N;
+            if (p.accumulate && p.splits > 1) {
+              if (full) {
+#pragma unroll
+                for (int e = 0; e < 32; e += 4)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + e), "f"(__uint_as_float(v[e])),
+                               "f"(__uint_as_float(v[e + 1])), "f"(__uint_as_float(v[e + 2])), "f"(__uint_as_float(v[e + 3]))
+                               : "memory");
+              } else {
+#pragma unroll
+                for (int e = 0; e < 32; ++e)
+                  if (col + e < p.N) atomicAdd(o + e, __uint_as_float(v[e]));
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) {
+                if (col + e < p.N) {
+                  float r = __uint_as_float(v[e]) + (p.bias ? __ldg(p.bias + col + e) : 0.f);
+                  if (p.accumulate) r += o[e];
+                  o[e] = r;
+                }
+              }
+            }
+          } else {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long)row * p.N + col;
+            if (col + 32 <= p.N) {
+              uint32_t pk[16];
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                float a = __uint_as_float(v[2 * e]), b = __uint_as_float(v[2 * e + 1]);
+                if (p.bias) {
+                  a += __ldg(p.bias + col + 2 * e);
+                  b += __ldg(p.bias + col + 2 * e + 1);
+                }
+                const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+                pk[e] = *reinterpret_cast<const uint32_t*>(&h);
+              }
+              uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) o4[e] = make_uint4(pk[4 * e], pk[4 * e + 1], pk[4 * e + 2], pk[4 * e + 3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 32; ++e)
+                if (col + e < p.N) o[e] = __float2bfloat16(__uint_as_float(v[e]) + (p.bias ? __ldg(p.bias + col + e) : 0.f));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&bars->acc_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<512>(tmem);
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, GmParams p, cudaStream_t st) {
+  using Cfg = GmCfg<BN>;
+  static bool attr = false;
+  if (!attr) {
+    RF_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr = true;
+  }
+  const long items = (long)p.m_tiles * p.n_tiles * p.splits;
+  const int grid = (int)(items < kNumSMs ? items : kNumSMs);
+  gemm_bf16_kernel<BN, A_MN, B_MN><<<grid, GM_THREADS, Cfg::SMEM, st>>>(ta, tb, p);
+  RF_CHECK_LAUNCH("gemm_bf16_kernel");
+  return RF_OK;
+}
+
+}  // namespace rf
+
+using namespace rf;
+
+extern "C" int rf_gemm_bf16(const void* a, const void* b, const float* bias, void* out, int M, int N, int K, int a_mn_major,
+                            int b_mn_major, int out_f32, int accumulate, void* stream) {
+  RF_REQUIRE(a && b && out && M > 0 && N > 0 && K > 0, "rf_gemm_bf16: bad arguments");
+  RF_REQUIRE((((uintptr_t)a | (uintptr_t)b | (uintptr_t)out) & 15) == 0, "rf_gemm_bf16: operands must be 16-byte aligned");
+  RF_REQUIRE(!(accumulate && !out_f32), "rf_gemm_bf16: accumulation needs an fp32 output");
+  RF_REQUIRE(!(accumulate && bias), "rf_gemm_bf16: bias and accumulation are exclusive");
+  // TMA: every global row pitch must be a multiple of 16 bytes
+  const long a_pitch = a_mn_major ? M : K, b_pitch = b_mn_major ? N : K;
+  RF_REQUIRE(a_pitch % 8 == 0 && b_pitch % 8 == 0 && N % (out_f32 ? 4 : 8) == 0,
+             "rf_gemm_bf16: M / N / K pitches must be multiples of 8 elements (got M %d N %d K %d)", M, N, K);
+  const int BN = N <= 64 ? 64 : 128;
+  CUtensorMap ta, tb;
+  int rc;
+  if (a_mn_major)   // stored [K, M]: box = 64 m (inner) x 64 k
+    rc = make_tmap_3d(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a, (uint64_t)M, (uint64_t)K, 1, (uint64_t)M * 2, (uint64_t)M * K * 2, 64, 64);
+  else              // stored [M, K]: box = 64 k (inner) x 128 m
+    rc = make_tmap_3d(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a, (uint64_t)K, (uint64_t)M, 1, (uint64_t)K * 2, (uint64_t)M * K * 2, 64, GM_BM);
+  if (rc != RF_OK) return rc;
+  if (b_mn_major)
+    rc = make_tmap_3d(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, b, (uint64_t)N, (uint64_t)K, 1, (uint64_t)N * 2, (uint64_t)N * K * 2, 64, 64);
+  else
+    rc = make_tmap_3d(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, b, (uint64_t)K, (uint64_t)N, 1, (uint64_t)K * 2, (uint64_t)N * K * 2, 64, (uint32_t)BN);
+  if (rc != RF_OK) return rc;
+  GmParams p;
+  p.bias = bias;
+  p.out = out;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.m_tiles = (M + GM_BM - 1) / GM_BM;
+  p.n_tiles = (N + BN - 1) / BN;
+  p.k_blocks = (K + GM_BK - 1) / GM_BK;
+  p.out_f32 = out_f32;
+  p.accumulate = accumulate;
+  // split the contraction only for accumulating fp32 outputs (the weight gradient: few output tiles, a contraction over
+  // every token): enough (tile, split) items for ~2 per SM, at least 4 k-blocks each
+  p.splits = 1;
+  if (accumulate) {
+    const long tiles = (long)p.m_tiles * p.n_tiles;
+    long s = (2l * kNumSMs + tiles - 1) / tiles;
+    if (s > p.k_blocks / 4) s = p.k_blocks / 4;
+    if (s < 1) s = 1;
+    p.splits = (int)s;
+  }
+  p.kb_per_split = (p.k_blocks + p.splits - 1) / p.splits;
+  p.splits = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;
+  cudaStream_t st = (cudaStream_t)stream;
+#define RF_GM(BN_)                                                                        \
+  (a_mn_major ? (b_mn_major ? gemm_launch<BN_, true, true>(ta, tb, p, st) : gemm_launch<BN_, true, false>(ta, tb, p, st)) \
+              : (b_mn_major ? gemm_launch<BN_, false, true>(ta, tb, p, st) : gemm_launch<BN_, false, false>(ta, tb, p, st)))
+  return BN == 64 ? RF_GM(64) : RF_GM(128);
+#undef RF_GM
+}

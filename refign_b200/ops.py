@@ -538,6 +538,33 @@ def colsum(g2d, out=None):
     return out
 
 
+OWN_GEMM = True     # Linear layers on the tcgen05 GEMM (csrc/gemm_bf16.cu); False = library GEMMs (comparison arm)
+
+
+def gemm_bf16(a, b, bias=None, out=None, a_mn_major=False, b_mn_major=False, out_dtype=torch.bfloat16, accumulate=False):
+    """out[m,n] (+)= sum_k A(m,k) B(n,k) (+ bias[n]) on the tcgen05 GEMM kernel.  ``a`` is [M,K] (or [K,M] with
+    a_mn_major), ``b`` [N,K] (or [K,N] with b_mn_major), both contiguous bf16; ``out`` bf16 / f32 [M,N]."""
+    require_cuda(a, b)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.is_contiguous() and b.is_contiguous()
+    K, M = (a.shape[0], a.shape[1]) if a_mn_major else (a.shape[1], a.shape[0])
+    Kb, N = (b.shape[0], b.shape[1]) if b_mn_major else (b.shape[1], b.shape[0])
+    assert K == Kb, (a.shape, b.shape)
+    if out is None:
+        assert not accumulate
+        out = torch.empty(M, N, device=a.device, dtype=out_dtype)
+    assert out.is_contiguous() and out.shape == (M, N) and out.dtype in (torch.bfloat16, torch.float32)
+    bias_f = None if bias is None else _f32c(bias)
+    with torch.cuda.device(a.device):
+        _run("rf_gemm_bf16", ptr(a), ptr(b), ptr(bias_f), ptr(out), M, N, K, int(a_mn_major), int(b_mn_major),
+             int(out.dtype == torch.float32), int(accumulate), _stream(),
+             work=(2 * (M * K + N * K) + out.element_size() * M * N, 2 * M * N * K), tag="gemm_bf16")
+    return out
+
+
+def gemm_bf16_supported(M, N, K):
+    return M > 0 and N % 8 == 0 and K % 8 == 0 and M % 8 == 0
+
+
 def _bf16_autocast():
     return torch.is_autocast_enabled() and torch.get_autocast_dtype('cuda') == torch.bfloat16
 
@@ -551,7 +578,13 @@ class _LinearShadow(torch.autograd.Function):
     def forward(ctx, x, weight, bias, wb, bb, gw_t=None, gb_t=None):
         with torch.autocast('cuda', enabled=False):
             xb = x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
-            y = F.linear(xb, wb, bb)
+            x2 = xb.reshape(-1, xb.shape[-1])
+            own = OWN_GEMM and x2.is_contiguous() and gemm_bf16_supported(x2.shape[0], wb.shape[0], wb.shape[1])
+            if own:   # bias added in fp32 from the master bias inside the GEMM epilogue
+                y = gemm_bf16(x2, wb, bias).view(*xb.shape[:-1], wb.shape[0])
+            else:
+                y = F.linear(xb, wb, bb)
+        ctx.own = own
         ctx.save_for_backward(xb, wb)
         ctx.x_dtype = x.dtype
         ctx.has_bias = bias is not None
@@ -570,13 +603,23 @@ class _LinearShadow(torch.autograd.Function):
                 go2 = go2.contiguous()
             x2 = xb.reshape(-1, xb.shape[-1])
             dx = dw = db = None
+            own = ctx.own
             if ctx.needs_input_grad[0]:
-                dx = (go2 @ wb).view(xb.shape)
+                if own:    # dx = dy W: W [N,K] read MN-major in place
+                    dx = gemm_bf16(go2, wb, b_mn_major=True).view(xb.shape)
+                else:
+                    dx = (go2 @ wb).view(xb.shape)
                 if dx.dtype != ctx.x_dtype:
                     dx = dx.to(ctx.x_dtype)
             gw_t, gb_t = ctx.targets
             if ctx.needs_input_grad[1]:
-                if gw_t is not None:
+                if own:    # dW += dy^T x: both operands read MN-major in place, fp32 partial sums red.add'ed into the target
+                    if gw_t is not None:
+                        gemm_bf16(go2, x2, out=gw_t.view(wb.shape), a_mn_major=True, b_mn_major=True, accumulate=True)
+                    else:
+                        dw = torch.zeros(wb.shape, device=wb.device, dtype=torch.float32)
+                        gemm_bf16(go2, x2, out=dw, a_mn_major=True, b_mn_major=True, accumulate=True)
+                elif gw_t is not None:
                     _mm_f32_acc(gw_t, go2.t(), x2)
                 else:
                     dw = _mm_f32(go2.t(), x2)

@@ -1,0 +1,76 @@
+"""tcgen05 bf16 GEMM (csrc/gemm_bf16.cu through ops.gemm_bf16) against a plain PyTorch fp32 reference of the same
+product on the same bf16 operands: every operand-layout variant the Linear layers use (forward: K-major x K-major;
+input gradient: K-major x MN-major; weight gradient: MN-major x MN-major, fp32 accumulate with split contraction),
+ragged M / N / K, the MiT-B5 layer shapes, and ops.linear's autograd (forward, dx, dW, db) against F.linear.
+Tolerances: fp32 accumulation of bf16 products -> 2e-3 of the output scale for bf16 outputs (one bf16 rounding),
+1e-4 for fp32 outputs."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from refign_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+SHAPES = [  # M, N, K
+    (128, 128, 64), (256, 64, 64), (384, 320, 128), (1000, 136, 72), (8192, 1280, 320), (8192, 320, 1280),
+    (2048, 512, 2048), (4096, 64, 64), (520, 2048, 512), (131072, 64, 64),
+]
+
+
+def _close(got, want, tol, what):
+    scale = float(want.abs().max()) + 1e-6
+    err = float((got.float() - want).abs().max())
+    assert err <= tol * scale, (what, err, scale)
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_gemm_forward_layout(shape):
+    M, N, K = shape
+    torch.manual_seed(M + N + K)
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    b = (torch.randn(N, K, device=DEV) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device=DEV)
+    want = a.float() @ b.float().t() + bias
+    _close(ops.gemm_bf16(a, b, bias), want, 4e-3, "bf16 out + bias")
+    _close(ops.gemm_bf16(a, b, None, out_dtype=torch.float32), want - bias, 1e-4, "f32 out")
+
+
+@pytest.mark.parametrize("shape", SHAPES[:9])
+def test_gemm_dgrad_and_wgrad_layouts(shape):
+    T, N, K = shape            # y [T,N] = x [T,K] W[N,K]^T
+    torch.manual_seed(T + N + K + 1)
+    x = torch.randn(T, K, device=DEV).bfloat16()
+    w = (torch.randn(N, K, device=DEV) / K ** 0.5).bfloat16()
+    dy = torch.randn(T, N, device=DEV).bfloat16()
+    # dx = dy W  (B = W read MN-major)
+    _close(ops.gemm_bf16(dy, w, b_mn_major=True), dy.float() @ w.float(), 4e-3, "dx")
+    # dW += dy^T x  (both MN-major, fp32 accumulate onto an existing gradient, split contraction)
+    g0 = torch.randn(N, K, device=DEV)
+    g = g0.clone()
+    ops.gemm_bf16(dy, x, out=g, a_mn_major=True, b_mn_major=True, accumulate=True)
+    _close(g, g0 + dy.float().t() @ x.float(), 2e-4, "dW accumulate")
+
+
+def test_linear_autograd_matches_library():
+    """ops.linear with bf16 shadow weights under autocast: forward, dx, dW (accumulated into the bound fp32 gradient), db."""
+    torch.manual_seed(3)
+    lin = torch.nn.Linear(320, 1280).to(DEV)
+    lin.weight._rf_bf16 = lin.weight.detach().bfloat16()
+    lin.bias._rf_bf16 = lin.bias.detach().bfloat16()
+    x = torch.randn(2, 1024, 320, device=DEV).bfloat16().requires_grad_(True)
+    gy = torch.randn(2, 1024, 1280, device=DEV).bfloat16()
+    with torch.autocast('cuda', dtype=torch.bfloat16):
+        y = ops.linear(x, lin.weight, lin.bias)
+    assert y.dtype == torch.bfloat16
+    y.backward(gy)
+    xr = x.detach().float().requires_grad_(True)
+    wr = lin.weight.detach().bfloat16().float().requires_grad_(True)
+    br = lin.bias.detach().clone().requires_grad_(True)
+    yr = F.linear(xr, wr, br)
+    yr.backward(gy.float())
+    _close(y, yr, 4e-3, "y")
+    _close(x.grad, xr.grad, 4e-3, "dx")
+    _close(lin.weight.grad, wr.grad, 2e-4, "dW")
+    _close(lin.bias.grad, br.grad, 1e-3, "db")
