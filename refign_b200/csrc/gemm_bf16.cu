@@ -10,30 +10,38 @@
 // Both operand layouts are consumed in place through TMA + UMMA shared-memory descriptors (128-byte swizzle; an
 // MN-major operand is a set of [64 k x 64 m] boxes, 8 KiB each): no transposed copies of weights or activations.
 //
-// Persistent, warp-specialised: warp 4 = TMA producer, warp 5 = MMA issuer, warps 0-3 = epilogue (thread = accumulator
-// row).  128 x BN output tiles (BN = 128, or 64 for narrow outputs), BK = 64, a ring of smem stages, and the 512 TMEM
+// Persistent, warp-specialised: warp 8 = TMA producer, warp 9 = MMA issuer, warps 0-7 = two epilogue warpgroups (thread =
+// accumulator row, alternate 128-byte column chunks).  128 x BN output tiles (BN = 128, or 64 for narrow outputs), BK = 64, a ring of smem stages, and the 512 TMEM
 // columns as 4 (BN = 128) / 8 (BN = 64) accumulator buffers so the MMA warp runs ahead of the epilogue.  Tiles are
 // walked n-fastest so consecutive CTAs share the A rows in L2.  All barrier arrivals are one per warp / tcgen05.commit.
+// The epilogue leaves through swizzled shared-memory chunks and TMA stores (cp.reduce.async.bulk .add for the weight
+// gradient): full 128-byte lines whatever the output pitch (per-thread row stores ran at 2 TB/s on 128 k x 256 outputs).
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
 #include "rf_common.cuh"
 #include "rf_sm100.cuh"
+#include "rf_trace.cuh"
 
 namespace rf {
 using namespace sm100;
 
 constexpr int GM_BM = 128, GM_BK = 64;
-constexpr int GM_THREADS = 192;
+constexpr int GM_THREADS = 320;   // 2 epilogue warpgroups (warps 0-7) + TMA warp (8) + MMA warp (9)
 constexpr int GM_A_BYTES = GM_BM * GM_BK * 2;          // 16 KiB per stage
 
 template <int BN>
 struct GmCfg {
   static constexpr int B_BYTES = BN * GM_BK * 2;
   static constexpr int STAGE = GM_A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN == 128 ? 6 : 8;
-  static constexpr int ACC = 512 / BN;                 // accumulator buffers in TMEM
-  static constexpr int SMEM = STAGES * STAGE + 1024 + 512;
+#ifdef WS_TRACE
+  static constexpr int STAGES = BN == 256 ? 3 : (BN == 192 ? 4 : (BN == 128 ? 5 : 6));   // (the trace log takes 22 KiB of static smem)
+#else
+  static constexpr int STAGES = BN == 256 ? 4 : (BN == 192 ? 4 : (BN == 128 ? 6 : 8));   // <= 192 KiB of operand stages
+#endif
+  static constexpr int ACC = 512 / BN;                 // accumulator buffers in TMEM (2 for BN = 192 / 256)
+  static constexpr int STAGING = 2 * 16384;            // one [128 rows x 128 B] output chunk per epilogue warpgroup (TMA store sources)
+  static constexpr int SMEM = STAGES * STAGE + STAGING + 1024 + 320 + 1024;   // + alignment slack, barriers, bias slice   // + alignment slack, barriers, bias slice
 };
 
 struct GmBars {
@@ -63,39 +71,45 @@ __device__ __forceinline__ void gm_load(void* smem_dst, const CUtensorMap* tm, u
 
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GM_THREADS, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GmParams p) {
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                 const __grid_constant__ CUtensorMap tm_out, const GmParams p) {
   using Cfg = GmCfg<BN>;
+  WS_T_INIT();
+  WS_T(0);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  GmBars* bars = reinterpret_cast<GmBars*>(smem + Cfg::STAGES * Cfg::STAGE);
+  uint8_t* staging = smem + Cfg::STAGES * Cfg::STAGE;
+  GmBars* bars = reinterpret_cast<GmBars*>(staging + Cfg::STAGING);
   const int tid = threadIdx.x, warp = tid >> 5;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (elect_one()) {
       tma_prefetch_desc(&tm_a);
       tma_prefetch_desc(&tm_b);
+      tma_prefetch_desc(&tm_out);
       for (int s = 0; s < Cfg::STAGES; ++s) {
         mbar_init(&bars->full[s], 1);
         mbar_init(&bars->empty[s], 1);
       }
       for (int s = 0; s < Cfg::ACC; ++s) {
         mbar_init(&bars->acc_full[s], 1);
-        mbar_init(&bars->acc_empty[s], 4);
+        mbar_init(&bars->acc_empty[s], 8);
       }
       fence_barrier_init();
     }
     __syncwarp();
   }
-  if (warp == 5) tmem_alloc<512>(&bars->tmem_base);
+  if (warp == 9) tmem_alloc<512>(&bars->tmem_base);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = uniform_u32(bars->tmem_base);
+  WS_T(1);
 
   const int tiles = p.m_tiles * p.n_tiles;
   const long items = (long)tiles * p.splits;          // work items: (tile, k split), tile-major
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ------------------------------------------------------------------ TMA producer
     int it = 0;
     for (long w = blockIdx.x; w < items; w += gridDim.x) {
@@ -112,9 +126,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           gm_load<B_MN>(stage + GM_A_BYTES, &tm_b, &bars->full[st], n0, kb * GM_BK, BN);
         }
         __syncwarp();
+        WS_T(30);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t IDESC = make_idesc(FMT_BF16, GM_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
     constexpr uint64_t STEP = (uint64_t)(Cfg::STAGE >> 4);
@@ -134,6 +149,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const int st = it % Cfg::STAGES;
         mbar_wait(&bars->full[st], (it / Cfg::STAGES) & 1);
         tc_fence_after();
+        WS_T(20);
         const uint64_t dA = dA0 + st * STEP, dB = dB0 + st * STEP;
         if (elect_one()) {
 #pragma unroll
@@ -143,89 +159,109 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           if (kb == kb1 - 1) tc_commit(&bars->acc_full[buf]);
         }
         __syncwarp();
+        WS_T(21);
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps (thread = accumulator row)
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    // ------------------------------------------------------------------ epilogue warpgroups (thread = accumulator row)
+    // TMEM -> registers (+ bias, -> bf16) -> swizzled smem chunk [128 rows x 128 B] -> TMA store (or TMA reduce-add for
+    // the accumulating fp32 output): full 128-byte lines leave the SM whatever the row pitch, the tensor map clips
+    // ragged M / N edges, and the stores run asynchronously.  Two warpgroups take alternate 128-byte column chunks of
+    // every tile (measured: one warpgroup needs ~1 200 cycles per chunk and was the kernel's bottleneck).
+    const int wg = warp >> 2, r = tid & 127;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const int cpc = p.out_f32 ? 32 : 64;                 // output columns per 128-byte chunk
+    const int nchunk = BN / cpc;
+    const uint32_t sw = (uint32_t)(r & 7);
+    uint8_t* sbuf = staging + wg * 16384;
+    float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 320);   // BN floats behind the barrier block
+    const bool issuer = r == 0;
     int local = 0;
     for (long w = blockIdx.x; w < items; w += gridDim.x, ++local) {
       const int tile = (int)(w / p.splits);
       const int m0 = (tile / p.n_tiles) * GM_BM, n0 = (tile % p.n_tiles) * BN;
       const int buf = local % Cfg::ACC;
+      if (p.bias) {   // this tile's bias slice, zero beyond N, read back as broadcast shared-memory vectors
+        asm volatile("bar.sync 3, 256;" ::: "memory");      // both warpgroups are done with the previous tile's slice
+        for (int i = tid; i < BN; i += 256) sbias[i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+      }
       mbar_wait(&bars->acc_full[buf], (local / Cfg::ACC) & 1);
       tc_fence_after();
-      const int row = m0 + tid;
+      WS_T(10);
       const uint32_t t = tmem + lane_off + buf * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(t + c * 32, v);
-        tc_wait_ld();
-        const int col = n0 + c * 32;
-        if (row < p.M && col < p.N) {
-          if (p.out_f32) {
-            float* o = reinterpret_cast<float*>(p.out) + (long)row * p.N + col;
-            const bool full = col + 32 <= p.N;
-            if (p.accumulate && p.splits > 1) {
-              if (full) {
+      for (int c = wg; c < nchunk; c += 2) {
+        const int col = n0 + c * cpc;
+        uint32_t pk[32];
+        if (p.out_f32) {
+          tmem_ld32(t + c * 32, pk);
+          tc_wait_ld();
+          if (p.bias) {
 #pragma unroll
-                for (int e = 0; e < 32; e += 4)
-                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + e), "f"(__uint_as_float(v[e])),
-                               "f"(__uint_as_float(v[e + 1])), "f"(__uint_as_float(v[e + 2])), "f"(__uint_as_float(v[e + 3]))
-                               : "memory");
-              } else {
-#pragma unroll
-                for (int e = 0; e < 32; ++e)
-                  if (col + e < p.N) atomicAdd(o + e, __uint_as_float(v[e]));
-              }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 32; ++e) {
-                if (col + e < p.N) {
-                  float r = __uint_as_float(v[e]) + (p.bias ? __ldg(p.bias + col + e) : 0.f);
-                  if (p.accumulate) r += o[e];
-                  o[e] = r;
-                }
-              }
+            for (int e = 0; e < 32; e += 4) {
+              const float4 bv = *reinterpret_cast<const float4*>(sbias + c * 32 + e);
+              pk[e] = __float_as_uint(__uint_as_float(pk[e]) + bv.x);
+              pk[e + 1] = __float_as_uint(__uint_as_float(pk[e + 1]) + bv.y);
+              pk[e + 2] = __float_as_uint(__uint_as_float(pk[e + 2]) + bv.z);
+              pk[e + 3] = __float_as_uint(__uint_as_float(pk[e + 3]) + bv.w);
             }
-          } else {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long)row * p.N + col;
-            if (col + 32 <= p.N) {
-              uint32_t pk[16];
+          }
+        } else {
+          uint32_t v[2][32];
+          tmem_ld32(t + c * 64, v[0]);
+          tmem_ld32(t + c * 64 + 32, v[1]);
+          tc_wait_ld();
 #pragma unroll
-              for (int e = 0; e < 16; ++e) {
-                float a = __uint_as_float(v[2 * e]), b = __uint_as_float(v[2 * e + 1]);
-                if (p.bias) {
-                  a += __ldg(p.bias + col + 2 * e);
-                  b += __ldg(p.bias + col + 2 * e + 1);
-                }
-                const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-                pk[e] = *reinterpret_cast<const uint32_t*>(&h);
-              }
-              uint4* o4 = reinterpret_cast<uint4*>(o);
+          for (int h = 0; h < 2; ++h) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) o4[e] = make_uint4(pk[4 * e], pk[4 * e + 1], pk[4 * e + 2], pk[4 * e + 3]);
-            } else {
-#pragma unroll
-              for (int e = 0; e < 32; ++e)
-                if (col + e < p.N) o[e] = __float2bfloat16(__uint_as_float(v[e]) + (p.bias ? __ldg(p.bias + col + e) : 0.f));
+            for (int e = 0; e < 16; e += 2) {
+              float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.bias) bv = *reinterpret_cast<const float4*>(sbias + c * 64 + h * 32 + 2 * e);
+              const __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(v[h][2 * e]) + bv.x, __uint_as_float(v[h][2 * e + 1]) + bv.y);
+              const __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(v[h][2 * e + 2]) + bv.z, __uint_as_float(v[h][2 * e + 3]) + bv.w);
+              pk[h * 16 + e] = *reinterpret_cast<const uint32_t*>(&h0);
+              pk[h * 16 + e + 1] = *reinterpret_cast<const uint32_t*>(&h1);
             }
           }
         }
+        if (c + 2 >= nchunk) {   // this warpgroup's share of the accumulator is in registers: hand the TMEM buffer back
+          tc_fence_before();
+          __syncwarp();
+          if ((tid & 31) == 0) mbar_arrive(&bars->acc_empty[buf]);
+        }
+        if (issuer) tma_store_wait_read<0>();            // the previous store of this warpgroup is done with the buffer
+        if (wg == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+        uint4* srow = reinterpret_cast<uint4*>(sbuf + r * 128);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) srow[q ^ sw] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        fence_proxy_async();
+        if (wg == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (issuer && col < p.N) {
+          if (p.accumulate) tma_reduce_add_3d(&tm_out, sbuf, col, m0, 0);
+          else tma_store_3d(&tm_out, sbuf, col, m0, 0);
+          WS_T(11);
+          tma_store_commit();
+        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if ((tid & 31) == 0) mbar_arrive(&bars->acc_empty[buf]);
+      if (nchunk == 1 && wg == 1) {   // BN = 64 bf16: a single chunk, warpgroup 1 only releases the accumulator
+        tc_fence_before();
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&bars->acc_empty[buf]);
+      }
     }
+    if (issuer) tma_store_wait_read<0>();   // the staging smem may go away; the global writes complete with the grid
+    WS_T(12);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc<512>(tmem);
+  WS_T(2);
+  WS_T_FLUSH();
+  if (warp == 9) tmem_dealloc<512>(tmem);
 }
 
 template <int BN, bool A_MN, bool B_MN>
-static int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, GmParams p, cudaStream_t st) {
+static int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, GmParams p, cudaStream_t st) {
   using Cfg = GmCfg<BN>;
   static bool attr = false;
   if (!attr) {
@@ -234,7 +270,7 @@ static int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, GmParams p,
   }
   const long items = (long)p.m_tiles * p.n_tiles * p.splits;
   const int grid = (int)(items < kNumSMs ? items : kNumSMs);
-  gemm_bf16_kernel<BN, A_MN, B_MN><<<grid, GM_THREADS, Cfg::SMEM, st>>>(ta, tb, p);
+  gemm_bf16_kernel<BN, A_MN, B_MN><<<grid, GM_THREADS, Cfg::SMEM, st>>>(ta, tb, to, p);
   RF_CHECK_LAUNCH("gemm_bf16_kernel");
   return RF_OK;
 }
@@ -253,7 +289,22 @@ extern "C" int rf_gemm_bf16(const void* a, const void* b, const float* bias, voi
   const long a_pitch = a_mn_major ? M : K, b_pitch = b_mn_major ? N : K;
   RF_REQUIRE(a_pitch % 8 == 0 && b_pitch % 8 == 0 && N % (out_f32 ? 4 : 8) == 0,
              "rf_gemm_bf16: M / N / K pitches must be multiples of 8 elements (got M %d N %d K %d)", M, N, K);
-  const int BN = N <= 64 ? 64 : 128;
+  // Tile width: these small-K GEMMs are bound by the operand traffic L2 -> SM (~50 B/clk per SM measured) and by wave
+  // quantisation over the 148 persistent CTAs, so pick the BN in {64, 128, 192, 256} that minimises
+  //   rounds(tiles / 148) x (128 + BN)         [bytes per k-block of one CTA, all CTAs in lockstep]
+  int BN = 64;
+  if (N > 64) {
+    const long m_tiles = (M + GM_BM - 1) / GM_BM;
+    long best = -1;
+    for (int cand : {256, 192, 128}) {
+      const long tiles = m_tiles * ((N + cand - 1) / cand);
+      const long cost = ((tiles + kNumSMs - 1) / kNumSMs) * (128 + cand);
+      if (best < 0 || cost < best) {
+        best = cost;
+        BN = cand;
+      }
+    }
+  }
   CUtensorMap ta, tb;
   int rc;
   if (a_mn_major)   // stored [K, M]: box = 64 m (inner) x 64 k
@@ -265,6 +316,12 @@ extern "C" int rf_gemm_bf16(const void* a, const void* b, const float* bias, voi
     rc = make_tmap_3d(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, b, (uint64_t)N, (uint64_t)K, 1, (uint64_t)N * 2, (uint64_t)N * K * 2, 64, 64);
   else
     rc = make_tmap_3d(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, b, (uint64_t)K, (uint64_t)N, 1, (uint64_t)K * 2, (uint64_t)N * K * 2, 64, (uint32_t)BN);
+  if (rc != RF_OK) return rc;
+  CUtensorMap to;   // output [M, N]: 128-byte chunks of 128 rows
+  if (out_f32)
+    rc = make_tmap_3d(&to, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out, (uint64_t)N, (uint64_t)M, 1, (uint64_t)N * 4, (uint64_t)M * N * 4, 32, GM_BM);
+  else
+    rc = make_tmap_3d(&to, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out, (uint64_t)N, (uint64_t)M, 1, (uint64_t)N * 2, (uint64_t)M * N * 2, 64, GM_BM);
   if (rc != RF_OK) return rc;
   GmParams p;
   p.bias = bias;
@@ -282,7 +339,7 @@ extern "C" int rf_gemm_bf16(const void* a, const void* b, const float* bias, voi
   p.splits = 1;
   if (accumulate) {
     const long tiles = (long)p.m_tiles * p.n_tiles;
-    long s = (2l * kNumSMs + tiles - 1) / tiles;
+    long s = (2l * kNumSMs) / tiles;          // floor: (tile, split) items must not spill into a third round
     if (s > p.k_blocks / 4) s = p.k_blocks / 4;
     if (s < 1) s = 1;
     p.splits = (int)s;
@@ -291,8 +348,8 @@ extern "C" int rf_gemm_bf16(const void* a, const void* b, const float* bias, voi
   p.splits = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;
   cudaStream_t st = (cudaStream_t)stream;
 #define RF_GM(BN_)                                                                        \
-  (a_mn_major ? (b_mn_major ? gemm_launch<BN_, true, true>(ta, tb, p, st) : gemm_launch<BN_, true, false>(ta, tb, p, st)) \
-              : (b_mn_major ? gemm_launch<BN_, false, true>(ta, tb, p, st) : gemm_launch<BN_, false, false>(ta, tb, p, st)))
-  return BN == 64 ? RF_GM(64) : RF_GM(128);
+  (a_mn_major ? (b_mn_major ? gemm_launch<BN_, true, true>(ta, tb, to, p, st) : gemm_launch<BN_, true, false>(ta, tb, to, p, st)) \
+              : (b_mn_major ? gemm_launch<BN_, false, true>(ta, tb, to, p, st) : gemm_launch<BN_, false, false>(ta, tb, to, p, st)))
+  return BN == 64 ? RF_GM(64) : (BN == 128 ? RF_GM(128) : (BN == 192 ? RF_GM(192) : RF_GM(256)));
 #undef RF_GM
 }

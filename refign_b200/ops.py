@@ -538,7 +538,8 @@ def colsum(g2d, out=None):
     return out
 
 
-OWN_GEMM = True     # Linear layers on the tcgen05 GEMM (csrc/gemm_bf16.cu); False = library GEMMs (comparison arm)
+import os as _os
+OWN_GEMM = _os.environ.get('RF_OWN_GEMM', '1') != '0'   # Linear layers on the tcgen05 GEMM (csrc/gemm_bf16.cu); RF_OWN_GEMM=0 = library GEMMs (comparison arm)
 
 
 def gemm_bf16(a, b, bias=None, out=None, a_mn_major=False, b_mn_major=False, out_dtype=torch.bfloat16, accumulate=False):

@@ -1,6 +1,5 @@
 #!/bin/bash
 # builds the sm_100a micro-benchmarks (tools/_bin/ is git-ignored; the binary travels with gpurun)
-set -e
 cd "$(dirname "$0")/.."
 mkdir -p tools/_bin
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo --expt-relaxed-constexpr -ccbin /usr/bin/g++ \
@@ -9,3 +8,5 @@ nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo --expt-rel
   tools/trace_attn_bwd.cu refign_b200/csrc/tensormap.cu -o tools/_bin/trace_attn_bwd
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo --expt-relaxed-constexpr -ccbin /usr/bin/g++ \
   tools/trace_attn_fwd.cu refign_b200/csrc/tensormap.cu -o tools/_bin/trace_attn_fwd
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo --expt-relaxed-constexpr -ccbin /usr/bin/g++ \
+  tools/trace_gemm.cu refign_b200/csrc/tensormap.cu -o tools/_bin/trace_gemm
