@@ -56,7 +56,15 @@ struct GmParams {
   int M, N, K;
   int m_tiles, n_tiles, k_blocks, splits, kb_per_split;
   int out_f32, accumulate;
+  // implicit-GEMM 3x3 convolution (MODE 1: forward / input gradient, MODE 2: weight gradient)
+  int taps;                // 1 (GEMM, MODE 1) or 9 (MODE 2: one output tile set per filter tap)
+  int H, W, tiles_h, tiles_w;      // MODE 1: pixel tiles of 8 x 16;  MODE 2: pixel k-blocks of 4 x 16
+  int cin_blocks;          // MODE 1: 64-channel blocks per tap
+  int act;                 // MODE 1 epilogue: 0 none, 1 ReLU, 2 LeakyReLU(slope)
+  float slope;
 };
+
+enum { GM_GEMM = 0, GM_CONV = 1, GM_CONV_WGRAD = 2 };
 
 // A / B tiles of one k-block: K-major = one box [rows x 64 k]; MN-major = rows/64 boxes [64 k x 64 rows]
 template <bool MN>
@@ -69,7 +77,7 @@ __device__ __forceinline__ void gm_load(void* smem_dst, const CUtensorMap* tm, u
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int MODE>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_out, const GmParams p) {
@@ -106,7 +114,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const uint32_t tmem = uniform_u32(bars->tmem_base);
   WS_T(1);
 
-  const int tiles = p.m_tiles * p.n_tiles;
+  const int tiles = p.taps * p.m_tiles * p.n_tiles;
   const long items = (long)tiles * p.splits;          // work items: (tile, k split), tile-major
 
   if (warp == 8) {
@@ -114,16 +122,37 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     int it = 0;
     for (long w = blockIdx.x; w < items; w += gridDim.x) {
       const int tile = (int)(w / p.splits), split = (int)(w % p.splits);
-      const int m0 = (tile / p.n_tiles) * GM_BM, n0 = (tile % p.n_tiles) * BN;
+      const int tap = tile / (p.m_tiles * p.n_tiles);                 // MODE 2 only (else 0)
+      const int mt = (tile / p.n_tiles) % p.m_tiles;
+      const int m0 = mt * GM_BM, n0 = (tile % p.n_tiles) * BN;
       const int kb0 = split * p.kb_per_split, kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
+      // MODE 1: the 128 output pixels of this tile are the 8 x 16 patch (th, tw) of image b
+      const int cb_img = mt / (p.tiles_h * p.tiles_w), cth = (mt / p.tiles_w) % p.tiles_h, ctw = mt % p.tiles_w;
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int st = it % Cfg::STAGES;
         if (it >= Cfg::STAGES) mbar_wait(&bars->empty[st], ((it / Cfg::STAGES) - 1) & 1);
         uint8_t* stage = smem + st * Cfg::STAGE;
         if (elect_one()) {
           mbar_expect_tx(&bars->full[st], Cfg::STAGE);
-          gm_load<A_MN>(stage, &tm_a, &bars->full[st], m0, kb * GM_BK, GM_BM);
-          gm_load<B_MN>(stage + GM_A_BYTES, &tm_b, &bars->full[st], n0, kb * GM_BK, BN);
+          if (MODE == GM_GEMM) {
+            gm_load<A_MN>(stage, &tm_a, &bars->full[st], m0, kb * GM_BK, GM_BM);
+            gm_load<B_MN>(stage + GM_A_BYTES, &tm_b, &bars->full[st], n0, kb * GM_BK, BN);
+          } else if (MODE == GM_CONV) {
+            // k-block = (filter tap, 64 input channels): the activation box is shifted by the tap, rows / columns
+            // outside the image are zero-filled by TMA (= the convolution's zero padding)
+            const int ctap = kb / p.cin_blocks, cb = kb % p.cin_blocks;
+            tma_load_4d(stage, &tm_a, &bars->full[st], cb * 64, ctw * 16 + ctap % 3 - 1, cth * 8 + ctap / 3 - 1, cb_img);
+            tma_load_3d(stage + GM_A_BYTES, &tm_b, &bars->full[st], cb * 64, ctap, n0);
+          } else {
+            // weight gradient: k-block = 4 x 16 pixels of one image; A = dy (output channels m0.. as MN-major blocks),
+            // B = x shifted by the tap (input channels n0..)
+            const int kw = kb % p.tiles_w, kh = (kb / p.tiles_w) % p.tiles_h, kimg = kb / (p.tiles_w * p.tiles_h);
+            for (int blk = 0; blk < GM_BM / 64; ++blk)
+              tma_load_4d(stage + blk * 8192, &tm_a, &bars->full[st], m0 + blk * 64, kw * 16, kh * 4, kimg);
+            for (int blk = 0; blk < BN / 64; ++blk)
+              tma_load_4d(stage + GM_A_BYTES + blk * 8192, &tm_b, &bars->full[st], n0 + blk * 64, kw * 16 + tap % 3 - 1,
+                          kh * 4 + tap / 3 - 1, kimg);
+          }
         }
         __syncwarp();
         WS_T(30);
@@ -179,7 +208,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     int local = 0;
     for (long w = blockIdx.x; w < items; w += gridDim.x, ++local) {
       const int tile = (int)(w / p.splits);
-      const int m0 = (tile / p.n_tiles) * GM_BM, n0 = (tile % p.n_tiles) * BN;
+      const int tap = tile / (p.m_tiles * p.n_tiles);
+      const int mt = (tile / p.n_tiles) % p.m_tiles;
+      const int m0 = mt * GM_BM, n0 = (tile % p.n_tiles) * BN;
+      const int cb_img = mt / (p.tiles_h * p.tiles_w), cth = (mt / p.tiles_w) % p.tiles_h, ctw = mt % p.tiles_w;
       const int buf = local % Cfg::ACC;
       if (p.bias) {   // this tile's bias slice, zero beyond N, read back as broadcast shared-memory vectors
         asm volatile("bar.sync 3, 256;" ::: "memory");      // both warpgroups are done with the previous tile's slice
@@ -207,6 +239,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               pk[e + 3] = __float_as_uint(__uint_as_float(pk[e + 3]) + bv.w);
             }
           }
+          if (MODE == GM_CONV && p.act) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const float x = __uint_as_float(pk[e]);
+              pk[e] = __float_as_uint(x > 0.f ? x : (p.act == 1 ? 0.f : x * p.slope));
+            }
+          }
         } else {
           uint32_t v[2][32];
           tmem_ld32(t + c * 64, v[0]);
@@ -218,8 +257,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             for (int e = 0; e < 16; e += 2) {
               float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
               if (p.bias) bv = *reinterpret_cast<const float4*>(sbias + c * 64 + h * 32 + 2 * e);
-              const __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(v[h][2 * e]) + bv.x, __uint_as_float(v[h][2 * e + 1]) + bv.y);
-              const __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(v[h][2 * e + 2]) + bv.z, __uint_as_float(v[h][2 * e + 3]) + bv.w);
+              float4 x = make_float4(__uint_as_float(v[h][2 * e]) + bv.x, __uint_as_float(v[h][2 * e + 1]) + bv.y,
+                                     __uint_as_float(v[h][2 * e + 2]) + bv.z, __uint_as_float(v[h][2 * e + 3]) + bv.w);
+              if (MODE == GM_CONV && p.act) {   // fused ReLU / LeakyReLU of the frozen conv stacks
+                const float ng = p.act == 1 ? 0.f : p.slope;
+                x.x = x.x > 0.f ? x.x : x.x * ng;
+                x.y = x.y > 0.f ? x.y : x.y * ng;
+                x.z = x.z > 0.f ? x.z : x.z * ng;
+                x.w = x.w > 0.f ? x.w : x.w * ng;
+              }
+              const __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y);
+              const __nv_bfloat162 h1 = __floats2bfloat162_rn(x.z, x.w);
               pk[h * 16 + e] = *reinterpret_cast<const uint32_t*>(&h0);
               pk[h * 16 + e + 1] = *reinterpret_cast<const uint32_t*>(&h1);
             }
@@ -238,7 +286,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         fence_proxy_async();
         if (wg == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
         if (issuer && col < p.N) {
-          if (p.accumulate) tma_reduce_add_3d(&tm_out, sbuf, col, m0, 0);
+          if (MODE == GM_CONV) tma_store_4d(&tm_out, sbuf, col, ctw * 16, cth * 8, cb_img);
+          else if (MODE == GM_CONV_WGRAD) tma_reduce_add_3d(&tm_out, sbuf, col, tap, m0);
+          else if (p.accumulate) tma_reduce_add_3d(&tm_out, sbuf, col, m0, 0);
           else tma_store_3d(&tm_out, sbuf, col, m0, 0);
           WS_T(11);
           tma_store_commit();
@@ -260,17 +310,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   if (warp == 9) tmem_dealloc<512>(tmem);
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int MODE = GM_GEMM>
 static int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, GmParams p, cudaStream_t st) {
   using Cfg = GmCfg<BN>;
   static bool attr = false;
   if (!attr) {
-    RF_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    RF_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, A_MN, B_MN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr = true;
   }
-  const long items = (long)p.m_tiles * p.n_tiles * p.splits;
+  const long items = (long)p.taps * p.m_tiles * p.n_tiles * p.splits;
   const int grid = (int)(items < kNumSMs ? items : kNumSMs);
-  gemm_bf16_kernel<BN, A_MN, B_MN><<<grid, GM_THREADS, Cfg::SMEM, st>>>(ta, tb, to, p);
+  gemm_bf16_kernel<BN, A_MN, B_MN, MODE><<<grid, GM_THREADS, Cfg::SMEM, st>>>(ta, tb, to, p);
   RF_CHECK_LAUNCH("gemm_bf16_kernel");
   return RF_OK;
 }
@@ -334,6 +384,10 @@ extern "C" int rf_gemm_bf16(const void* a, const void* b, const float* bias, voi
   p.k_blocks = (K + GM_BK - 1) / GM_BK;
   p.out_f32 = out_f32;
   p.accumulate = accumulate;
+  p.taps = 1;
+  p.H = p.W = p.tiles_h = p.tiles_w = p.cin_blocks = 1;
+  p.act = 0;
+  p.slope = 0.f;
   // split the contraction only for accumulating fp32 outputs (the weight gradient: few output tiles, a contraction over
   // every token): enough (tile, split) items for ~2 per SM, at least 4 k-blocks each
   p.splits = 1;
@@ -352,4 +406,130 @@ extern "C" int rf_gemm_bf16(const void* a, const void* b, const float* bias, voi
               : (b_mn_major ? gemm_launch<BN_, false, true>(ta, tb, to, p, st) : gemm_launch<BN_, false, false>(ta, tb, to, p, st)))
   return BN == 64 ? RF_GM(64) : (BN == 128 ? RF_GM(128) : (BN == 192 ? RF_GM(192) : RF_GM(256)));
 #undef RF_GM
+}
+
+// ---------------------------------------------------------------------------------------------------- 3x3 convolution
+static int pick_bn(long m_tiles, int N) {
+  if (N <= 64) return 64;
+  int BN = 128;
+  long best = -1;
+  for (int cand : {256, 192, 128}) {
+    const long tiles = m_tiles * ((N + cand - 1) / cand);
+    const long cost = ((tiles + kNumSMs - 1) / kNumSMs) * (128 + cand);
+    if (best < 0 || cost < best) {
+      best = cost;
+      BN = cand;
+    }
+  }
+  return BN;
+}
+
+// channels-last activation [B, H, W, C] as a rank-4 map (C, W, H, B) with box (64, 16, bh, 1)
+static int act_map(CUtensorMap* m, const void* base, int B, int H, int W, int C, int bh, CUtensorMapDataType dt, int elem,
+                   uint32_t box0) {
+  const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  const uint64_t str[3] = {(uint64_t)C * elem, (uint64_t)W * C * elem, (uint64_t)H * W * C * elem};
+  const uint32_t box[4] = {box0, 16, (uint32_t)bh, 1};
+  return make_tmap_nd(m, dt, elem, base, 4, dims, str, box);
+}
+// channels-last filter [Cout][3][3][Cin] as a rank-3 map (Cin, tap, Cout)
+static int filt_map(CUtensorMap* m, const void* base, int Cin, int Cout, CUtensorMapDataType dt, int elem, uint32_t box0,
+                    uint32_t rows) {
+  const uint64_t dims[3] = {(uint64_t)Cin, 9, (uint64_t)Cout};
+  const uint64_t str[2] = {(uint64_t)Cin * elem, (uint64_t)9 * Cin * elem};
+  const uint32_t box[3] = {box0, 1, rows};
+  return make_tmap_nd(m, dt, elem, base, 3, dims, str, box);
+}
+
+extern "C" int rf_conv3x3_bf16(const void* x, const void* w, const float* bias, void* out, int B, int H, int W, int Cin,
+                               int Cout, int out_f32, int act, float slope, void* stream) {
+  RF_REQUIRE(x && w && out && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "rf_conv3x3_bf16: bad arguments");
+  RF_REQUIRE((((uintptr_t)x | (uintptr_t)w | (uintptr_t)out) & 15) == 0, "rf_conv3x3_bf16: operands must be 16-byte aligned");
+  RF_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0, "rf_conv3x3_bf16: channel counts must be multiples of 8 (got %d -> %d)", Cin, Cout);
+  RF_REQUIRE(act >= 0 && act <= 2, "rf_conv3x3_bf16: act must be 0 (none), 1 (ReLU) or 2 (LeakyReLU)");
+  GmParams p;
+  p.bias = bias;
+  p.out = out;
+  p.tiles_h = (H + 7) / 8;
+  p.tiles_w = (W + 15) / 16;
+  p.m_tiles = B * p.tiles_h * p.tiles_w;
+  p.M = p.m_tiles * GM_BM;
+  p.N = Cout;
+  p.K = 9 * Cin;
+  const int BN = pick_bn(p.m_tiles, Cout);
+  p.n_tiles = (Cout + BN - 1) / BN;
+  p.cin_blocks = (Cin + 63) / 64;
+  p.k_blocks = 9 * p.cin_blocks;
+  p.splits = 1;
+  p.kb_per_split = p.k_blocks;
+  p.out_f32 = out_f32;
+  p.accumulate = 0;
+  p.taps = 1;
+  p.H = H;
+  p.W = W;
+  p.act = act;
+  p.slope = slope;
+  CUtensorMap ta, tb, to;
+  int rc = act_map(&ta, x, B, H, W, Cin, 8, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 64);
+  if (rc != RF_OK) return rc;
+  rc = filt_map(&tb, w, Cin, Cout, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 64, (uint32_t)BN);
+  if (rc != RF_OK) return rc;
+  rc = out_f32 ? act_map(&to, out, B, H, W, Cout, 8, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 32)
+               : act_map(&to, out, B, H, W, Cout, 8, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 64);
+  if (rc != RF_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (BN) {
+    case 64: return gemm_launch<64, false, false, GM_CONV>(ta, tb, to, p, st);
+    case 128: return gemm_launch<128, false, false, GM_CONV>(ta, tb, to, p, st);
+    case 192: return gemm_launch<192, false, false, GM_CONV>(ta, tb, to, p, st);
+    default: return gemm_launch<256, false, false, GM_CONV>(ta, tb, to, p, st);
+  }
+}
+
+// dw[co][tap][ci] (fp32, channels-last filter layout) += sum over pixels dy[.., co] * x[.. shifted by tap .., ci]
+extern "C" int rf_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dw, int B, int H, int W, int Cin, int Cout,
+                                     void* stream) {
+  RF_REQUIRE(dy && x && dw && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "rf_conv3x3_wgrad_bf16: bad arguments");
+  RF_REQUIRE((((uintptr_t)dy | (uintptr_t)x | (uintptr_t)dw) & 15) == 0, "rf_conv3x3_wgrad_bf16: operands must be 16-byte aligned");
+  RF_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0, "rf_conv3x3_wgrad_bf16: channel counts must be multiples of 8");
+  GmParams p;
+  p.bias = nullptr;
+  p.out = dw;
+  p.taps = 9;
+  p.M = Cout;
+  p.N = Cin;
+  p.m_tiles = (Cout + GM_BM - 1) / GM_BM;
+  const int BN = pick_bn(9l * p.m_tiles, Cin);
+  p.n_tiles = (Cin + BN - 1) / BN;
+  p.tiles_h = (H + 3) / 4;            // pixel k-blocks of 4 x 16
+  p.tiles_w = (W + 15) / 16;
+  p.k_blocks = B * p.tiles_h * p.tiles_w;
+  p.K = p.k_blocks * GM_BK;
+  p.cin_blocks = 1;
+  p.H = H;
+  p.W = W;
+  p.out_f32 = 1;
+  p.accumulate = 1;
+  p.act = 0;
+  p.slope = 0.f;
+  const long tiles = 9l * p.m_tiles * p.n_tiles;
+  long s = (2l * kNumSMs) / tiles;
+  if (s > p.k_blocks / 4) s = p.k_blocks / 4;
+  if (s < 1) s = 1;
+  p.kb_per_split = (int)((p.k_blocks + s - 1) / s);
+  p.splits = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;
+  CUtensorMap ta, tb, to;
+  int rc = act_map(&ta, dy, B, H, W, Cout, 4, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 64);
+  if (rc != RF_OK) return rc;
+  rc = act_map(&tb, x, B, H, W, Cin, 4, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 64);
+  if (rc != RF_OK) return rc;
+  rc = filt_map(&to, dw, Cin, Cout, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 32, GM_BM);
+  if (rc != RF_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (BN) {
+    case 64: return gemm_launch<64, true, true, GM_CONV_WGRAD>(ta, tb, to, p, st);
+    case 128: return gemm_launch<128, true, true, GM_CONV_WGRAD>(ta, tb, to, p, st);
+    case 192: return gemm_launch<192, true, true, GM_CONV_WGRAD>(ta, tb, to, p, st);
+    default: return gemm_launch<256, true, true, GM_CONV_WGRAD>(ta, tb, to, p, st);
+  }
 }

@@ -42,4 +42,32 @@ int make_tmap_3d(CUtensorMap* out, CUtensorMapDataType dt, int elem_bytes, const
   return RF_OK;
 }
 
+int make_tmap_nd(CUtensorMap* out, CUtensorMapDataType dt, int elem_bytes, const void* base, int rank, const uint64_t* dims,
+                 const uint64_t* strides, const uint32_t* box, CUtensorMapSwizzle swizzle) {
+  rf_encode_tiled_fn enc = get_encode_tiled();
+  if (enc == nullptr) return RF_ECUDA;
+  RF_REQUIRE(rank >= 2 && rank <= 5, "tensor map: rank must be 2..5");
+  RF_REQUIRE(((uintptr_t)base & 15) == 0, "tensor map: base address must be 16-byte aligned");
+  RF_REQUIRE((uint64_t)box[0] * elem_bytes <= 128, "tensor map: inner box exceeds the 128-byte swizzle span");
+  cuuint64_t d[5], st[4];
+  cuuint32_t b[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    d[i] = dims[i];
+    b[i] = box[i];
+    es[i] = 1;
+    RF_REQUIRE(box[i] >= 1 && box[i] <= 256, "tensor map: box dimension out of range");
+    if (i + 1 < rank) {
+      st[i] = strides[i];
+      RF_REQUIRE(strides[i] % 16 == 0, "tensor map: strides must be multiples of 16 bytes");
+    }
+  }
+  CUresult r = enc(out, dt, (cuuint32_t)rank, const_cast<void*>(base), d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d) for a rank-%d map", (int)r, rank);
+    return RF_ECUDA;
+  }
+  return RF_OK;
+}
+
 }  // namespace rf

@@ -103,6 +103,11 @@ class ConvBNReLU(nn.Module):
             if self._is_depthwise3x3():
                 # channels-last depthwise kernel (cuDNN's grouped-direct path is ~100x off the HBM roofline here)
                 x = ops.dwconv3x3_nhwc(x, conv.weight, conv.bias, conv.dilation[0])
+            elif (x.is_cuda and x.dtype == torch.bfloat16 and conv.bias is None and ops.conv3x3_supported(x, conv)
+                  and getattr(conv.weight, '_rf_bf16', None) is not None):
+                x = ops.conv3x3_train(x, conv)        # DAFormer bottleneck: tcgen05 implicit GEMM (fwd, dgrad, wgrad)
+            elif ops.conv1x1_supported(x, conv):
+                x = ops.conv1x1_train(x, conv)        # ASPP 1x1 / pointwise convolutions: tcgen05 GEMM on the pixel rows
             else:
                 x = conv(x)
             if self.use_norm:

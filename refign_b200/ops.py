@@ -566,6 +566,116 @@ def gemm_bf16_supported(M, N, K):
     return M > 0 and N % 8 == 0 and K % 8 == 0 and M % 8 == 0
 
 
+def conv3x3_nhwc_raw(x, w_cl, bias=None, act=0, slope=0.0, out_dtype=torch.bfloat16):
+    """3x3 / stride 1 / padding 1 convolution of a contiguous channels-last bf16 tensor x [B,H,W,Cin] with the
+    channels-last bf16 filter w_cl [Cout,3,3,Cin] (+ f32 bias, + fused ReLU / LeakyReLU) on the tcgen05 implicit GEMM."""
+    require_cuda(x, w_cl)
+    assert x.dtype == torch.bfloat16 and w_cl.dtype == torch.bfloat16 and x.is_contiguous() and w_cl.is_contiguous()
+    B, H, W, Cin = x.shape
+    Cout = w_cl.shape[0]
+    assert w_cl.shape == (Cout, 3, 3, Cin)
+    out = torch.empty(B, H, W, Cout, device=x.device, dtype=out_dtype)
+    bias_f = None if bias is None else _f32c(bias)
+    with torch.cuda.device(x.device):
+        _run("rf_conv3x3_bf16", ptr(x), ptr(w_cl), ptr(bias_f), ptr(out), B, H, W, Cin, Cout,
+             int(out_dtype == torch.float32), int(act), float(slope), _stream(),
+             work=(2 * x.numel() + 2 * w_cl.numel() + out.numel() * out.element_size(), 2 * 9 * out.numel() * Cin),
+             tag="conv3x3")
+    return out
+
+
+def conv3x3_supported(x_nchw, conv):
+    """The implicit-GEMM kernel covers 3x3 / stride 1 / padding 1 / dilation 1 / groups 1 convolutions with channel
+    counts that are multiples of 8 on CUDA tensors."""
+    return (OWN_GEMM and x_nchw.is_cuda and x_nchw.dim() == 4 and conv.kernel_size == (3, 3) and conv.stride == (1, 1)
+            and conv.padding == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1 and conv.padding_mode == 'zeros'
+            and conv.in_channels % 8 == 0 and conv.out_channels % 8 == 0)
+
+
+class _Conv3x3(torch.autograd.Function):
+    """Trainable 3x3 convolution (the DAFormer bottleneck) on the implicit-GEMM kernel: forward, input gradient (same
+    kernel with the flipped / transposed filter) and weight gradient (accumulated in fp32 into the flat gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, w_cl, w_dgrad, gw_t):
+        # x: logical NCHW bf16 held channels-last -> the [B,H,W,C] view is contiguous
+        xh = x.permute(0, 2, 3, 1)
+        if not xh.is_contiguous():
+            xh = xh.contiguous()
+        y = conv3x3_nhwc_raw(xh, w_cl)
+        ctx.save_for_backward(xh, w_dgrad)
+        ctx.gw_t = gw_t
+        ctx.wshape = weight.shape
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        xh, w_dgrad = ctx.saved_tensors
+        gh = gy.permute(0, 2, 3, 1)
+        if gh.dtype != torch.bfloat16:
+            gh = gh.to(torch.bfloat16)
+        if not gh.is_contiguous():
+            gh = gh.contiguous()
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = conv3x3_nhwc_raw(gh, w_dgrad).permute(0, 3, 1, 2)
+        if ctx.needs_input_grad[1]:
+            Co, Ci = ctx.wshape[0], ctx.wshape[1]
+            B, H, W, _ = xh.shape
+            dwc = torch.zeros(Co, 3, 3, Ci, device=xh.device, dtype=torch.float32)
+            with torch.cuda.device(xh.device):
+                _run("rf_conv3x3_wgrad_bf16", ptr(gh), ptr(xh), ptr(dwc), B, H, W, Ci, Co, _stream(),
+                     work=(2 * (gh.numel() + xh.numel()) + 4 * dwc.numel(), 2 * 9 * gh.numel() * Ci), tag="conv3x3_wgrad")
+            if ctx.gw_t is not None:
+                ctx.gw_t.add_(dwc.permute(0, 3, 1, 2))
+            else:
+                dw = dwc.permute(0, 3, 1, 2).contiguous()
+        return dx, dw, None, None, None
+
+
+def conv1x1_train(x, conv):
+    """conv(x) for a 1x1 / stride 1 convolution of a channels-last bf16 tensor as the tcgen05 GEMM on its
+    [B*H*W, Cin] view (forward, dgrad, wgrad, bias through ops.linear's autograd function)."""
+    B, Ci, H, W = x.shape
+    Co = conv.out_channels
+    x2 = x.permute(0, 2, 3, 1).reshape(B * H * W, Ci)
+    w2 = conv.weight.view(Co, Ci)
+    wb = conv.weight._rf_bf16.view(Co, Ci)
+    bb = getattr(conv.bias, '_rf_bf16', None) if conv.bias is not None else None
+    gw = grad_target(conv.weight)
+    y2 = _LinearShadow.apply(x2, w2, conv.bias, wb, bb, None if gw is None else gw.view(Co, Ci), grad_target(conv.bias))
+    return y2.view(B, H, W, Co).permute(0, 3, 1, 2)
+
+
+def conv1x1_supported(x, conv):
+    return (OWN_GEMM and x.is_cuda and x.dim() == 4 and x.dtype == torch.bfloat16 and conv.kernel_size == (1, 1)
+            and conv.stride == (1, 1) and conv.padding == (0, 0) and conv.groups == 1 and conv.in_channels % 8 == 0
+            and conv.out_channels % 8 == 0 and getattr(conv.weight, '_rf_bf16', None) is not None
+            and (conv.bias is None or getattr(conv.bias, '_rf_bf16', None) is not None)
+            and x.permute(0, 2, 3, 1).is_contiguous() and (x.shape[0] * x.shape[2] * x.shape[3]) % 8 == 0)
+
+
+def conv3x3_train(x, conv):
+    """conv(x) for a trainable bias-free 3x3 convolution with bf16 shadow weights (see conv3x3_supported)."""
+    wb = conv.weight._rf_bf16
+    w_cl = getattr(conv.weight, '_rf_cl', None)
+    if w_cl is None:
+        w_cl = conv.weight._rf_cl = torch.empty(wb.shape[0], 3, 3, wb.shape[1], device=wb.device, dtype=torch.bfloat16)
+        w_dg = conv.weight._rf_dg = torch.empty(wb.shape[1], 3, 3, wb.shape[0], device=wb.device, dtype=torch.bfloat16)
+        _DERIVED_CONV.append((wb, w_cl, w_dg))
+        _derive_conv(wb, w_cl, w_dg)
+    return _Conv3x3.apply(x, conv.weight, w_cl, conv.weight._rf_dg, grad_target(conv.weight))
+
+
+_DERIVED_CONV = []   # [bf16 shadow [Co,Ci,3,3], channels-last filter [Co,3,3,Ci], flipped transposed filter [Ci,3,3,Co]]
+
+
+def _derive_conv(wb, w_cl, w_dg):
+    w_cl.copy_(wb.permute(0, 2, 3, 1))
+    w_dg.copy_(wb.flip(2, 3).permute(1, 2, 3, 0))
+
+
 def _bf16_autocast():
     return torch.is_autocast_enabled() and torch.get_autocast_dtype('cuda') == torch.bfloat16
 
@@ -711,13 +821,15 @@ def refresh_derived(flat_shadow=None):
     for src, wp in _DERIVED:
         if flat_shadow is None or lo <= src.data_ptr() < hi:
             wp.view(src.shape[0], src.shape[2], src.shape[3], src.shape[1]).copy_(src.permute(0, 2, 3, 1))
+    for src, w_cl, w_dg in _DERIVED_CONV:
+        if flat_shadow is None or lo <= src.data_ptr() < hi:
+            _derive_conv(src, w_cl, w_dg)
 
 
 def conv_bias_act(x, weight, bias, stride, padding, dilation, groups, act=None):
     """``act(conv2d(x, weight) + bias)`` for the frozen (no-grad) conv stacks: library convolution without
     bias + one in-place 16-byte-vector bias/activation kernel (the library path runs a broadcast add and a
     separate activation pass over the full-resolution tensors).  ``act``: None, nn.ReLU or nn.LeakyReLU."""
-    y = F.conv2d(x, weight, None, stride, padding, dilation, groups)
     code, slope = 0, 0.0
     if isinstance(act, torch.nn.ReLU):
         code = 1
@@ -725,6 +837,19 @@ def conv_bias_act(x, weight, bias, stride, padding, dilation, groups, act=None):
         code, slope = 2, float(act.negative_slope)
     elif act is not None:
         raise RuntimeError("conv_bias_act: unsupported activation %r" % (act,))
+    pair = lambda v: (v, v) if isinstance(v, int) else tuple(v)
+    if (OWN_GEMM and x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and x.dim() == 4
+            and tuple(weight.shape[2:]) == (3, 3) and pair(stride) == (1, 1) and pair(padding) == (1, 1)
+            and pair(dilation) == (1, 1) and groups == 1 and weight.shape[0] % 8 == 0 and weight.shape[1] % 8 == 0):
+        # tcgen05 implicit GEMM on the channels-last tensors, bias + activation in its epilogue (VGG-16 3x3 stacks)
+        xh = x.permute(0, 2, 3, 1)
+        if not xh.is_contiguous():
+            xh = xh.contiguous()
+        w_cl = weight.permute(0, 2, 3, 1)
+        if not w_cl.is_contiguous():
+            w_cl = w_cl.contiguous()
+        return conv3x3_nhwc_raw(xh, w_cl, bias, act=code, slope=slope).permute(0, 3, 1, 2)
+    y = F.conv2d(x, weight, None, stride, padding, dilation, groups)
     N, C, H, W = y.shape
     if y.is_contiguous():
         inner = H * W

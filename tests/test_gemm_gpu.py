@@ -74,3 +74,48 @@ def test_linear_autograd_matches_library():
     _close(x.grad, xr.grad, 4e-3, "dx")
     _close(lin.weight.grad, wr.grad, 2e-4, "dW")
     _close(lin.bias.grad, br.grad, 1e-3, "db")
+
+
+CONV_SHAPES = [  # B, H, W, Cin, Cout
+    (1, 8, 16, 64, 64), (2, 24, 40, 64, 128), (1, 19, 21, 128, 72), (2, 32, 32, 1024, 256), (1, 64, 64, 256, 512),
+    (1, 16, 48, 72, 64),
+]
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+def test_conv3x3_forward_bias_act(shape):
+    """Implicit-GEMM 3x3 convolution (+ bias + ReLU / LeakyReLU) vs F.conv2d in fp32 on the same bf16 operands."""
+    B, H, W, Ci, Co = shape
+    torch.manual_seed(sum(shape))
+    x = torch.randn(B, H, W, Ci, device=DEV).bfloat16()
+    w = (torch.randn(Co, Ci, 3, 3, device=DEV) / (3 * Ci ** 0.5)).bfloat16()
+    b = torch.randn(Co, device=DEV)
+    w_cl = w.permute(0, 2, 3, 1).contiguous()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1)
+    for act, slope, fn in ((0, 0.0, lambda t: t), (1, 0.0, torch.relu), (2, 0.1, lambda t: F.leaky_relu(t, 0.1))):
+        got = ops.conv3x3_nhwc_raw(x, w_cl, b, act=act, slope=slope)
+        _close(got.permute(0, 3, 1, 2), fn(ref), 4e-3, "conv act %d" % act)
+    got32 = ops.conv3x3_nhwc_raw(x, w_cl, None, out_dtype=torch.float32)
+    _close(got32.permute(0, 3, 1, 2), ref - b.view(1, -1, 1, 1), 1e-4, "conv f32")
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES[:5])
+def test_conv3x3_autograd(shape):
+    """_Conv3x3: forward, input gradient (flipped / transposed filter through the same kernel) and weight gradient
+    (accumulated into the bound fp32 gradient) vs autograd of F.conv2d."""
+    B, H, W, Ci, Co = shape
+    torch.manual_seed(sum(shape) + 1)
+    conv = torch.nn.Conv2d(Ci, Co, 3, padding=1, bias=False).to(DEV)
+    conv.weight._rf_bf16 = conv.weight.detach().bfloat16()
+    x = torch.randn(B, Ci, H, W, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    gy = torch.randn(B, Co, H, W, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    assert ops.conv3x3_supported(x, conv)
+    y = ops.conv3x3_train(x, conv)
+    y.backward(gy)
+    xr = x.detach().float().requires_grad_(True)
+    wr = conv.weight.detach().bfloat16().float().requires_grad_(True)
+    yr = F.conv2d(xr, wr, padding=1)
+    yr.backward(gy.float())
+    _close(y, yr, 4e-3, "y")
+    _close(x.grad, xr.grad, 4e-3, "dx")
+    _close(conv.weight.grad, wr.grad, 3e-4, "dW")
