@@ -77,7 +77,7 @@ __device__ __forceinline__ void gm_load(void* smem_dst, const CUtensorMap* tm, u
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int MODE>
+template <int BN, bool A_MN, bool B_MN, int MODE, bool CL2>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_out, const GmParams p) {
@@ -97,7 +97,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       tma_prefetch_desc(&tm_out);
       for (int s = 0; s < Cfg::STAGES; ++s) {
         mbar_init(&bars->full[s], 1);
-        mbar_init(&bars->empty[s], 1);
+        mbar_init(&bars->empty[s], CL2 ? 2 : 1);   // CTA pair: a stage is free when BOTH CTAs' MMAs have read it
       }
       for (int s = 0; s < Cfg::ACC; ++s) {
         mbar_init(&bars->acc_full[s], 1);
@@ -110,20 +110,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   if (warp == 9) tmem_alloc<512>(&bars->tmem_base);
   tc_fence_before();
   __syncthreads();
+  if (CL2) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast into this CTA
   tc_fence_after();
   const uint32_t tmem = uniform_u32(bars->tmem_base);
   WS_T(1);
 
-  const int tiles = p.taps * p.m_tiles * p.n_tiles;
+  // CTA pairs (CL2): the two CTAs of a cluster work on the m-tiles 2 mp and 2 mp + 1 of the SAME n-tile, each loads
+  // half of the shared B tile and multicasts it to both -- operand traffic per CTA and k-block drops from
+  // (128 + BN) to (128 + BN / 2) rows (these GEMMs are bound by the L2 -> SM operand path).  An m-tile beyond the
+  // tensor loads zeros and stores nothing (TMA fills / clips), so the pair never diverges.
+  const int rank = CL2 ? (int)cluster_ctarank() : 0;
+  const int m_units = CL2 ? (p.m_tiles + 1) / 2 : p.m_tiles;
+  const int tiles = p.taps * m_units * p.n_tiles;
   const long items = (long)tiles * p.splits;          // work items: (tile, k split), tile-major
+  const long w_first = CL2 ? blockIdx.x / 2 : blockIdx.x, w_step = CL2 ? gridDim.x / 2 : gridDim.x;
 
   if (warp == 8) {
     // ------------------------------------------------------------------ TMA producer
     int it = 0;
-    for (long w = blockIdx.x; w < items; w += gridDim.x) {
+    for (long w = w_first; w < items; w += w_step) {
       const int tile = (int)(w / p.splits), split = (int)(w % p.splits);
-      const int tap = tile / (p.m_tiles * p.n_tiles);                 // MODE 2 only (else 0)
-      const int mt = (tile / p.n_tiles) % p.m_tiles;
+      const int tap = tile / (m_units * p.n_tiles);                   // MODE 2 only (else 0)
+      const int mt = ((tile / p.n_tiles) % m_units) * (CL2 ? 2 : 1) + rank;
       const int m0 = mt * GM_BM, n0 = (tile % p.n_tiles) * BN;
       const int kb0 = split * p.kb_per_split, kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
       // MODE 1: the 128 output pixels of this tile are the 8 x 16 patch (th, tw) of image b
@@ -134,24 +142,38 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         uint8_t* stage = smem + st * Cfg::STAGE;
         if (elect_one()) {
           mbar_expect_tx(&bars->full[st], Cfg::STAGE);
+          uint8_t* sB = stage + GM_A_BYTES;
           if (MODE == GM_GEMM) {
             gm_load<A_MN>(stage, &tm_a, &bars->full[st], m0, kb * GM_BK, GM_BM);
-            gm_load<B_MN>(stage + GM_A_BYTES, &tm_b, &bars->full[st], n0, kb * GM_BK, BN);
+            if (!CL2) {
+              gm_load<B_MN>(sB, &tm_b, &bars->full[st], n0, kb * GM_BK, BN);
+            } else if (!B_MN) {     // this CTA's half of the rows, to both CTAs
+              tma_load_3d_mc(sB + rank * (BN / 2) * 128, &tm_b, &bars->full[st], kb * GM_BK, n0 + rank * (BN / 2), 0, 3);
+            } else {                // this CTA's half of the 64-column blocks
+              for (int blk = rank * (BN / 128); blk < (rank + 1) * (BN / 128); ++blk)
+                tma_load_3d_mc(sB + blk * 8192, &tm_b, &bars->full[st], n0 + blk * 64, kb * GM_BK, 0, 3);
+            }
           } else if (MODE == GM_CONV) {
             // k-block = (filter tap, 64 input channels): the activation box is shifted by the tap, rows / columns
             // outside the image are zero-filled by TMA (= the convolution's zero padding)
             const int ctap = kb / p.cin_blocks, cb = kb % p.cin_blocks;
             tma_load_4d(stage, &tm_a, &bars->full[st], cb * 64, ctw * 16 + ctap % 3 - 1, cth * 8 + ctap / 3 - 1, cb_img);
-            tma_load_3d(stage + GM_A_BYTES, &tm_b, &bars->full[st], cb * 64, ctap, n0);
+            if (!CL2) tma_load_3d(sB, &tm_b, &bars->full[st], cb * 64, ctap, n0);
+            else tma_load_3d_mc(sB + rank * (BN / 2) * 128, &tm_b, &bars->full[st], cb * 64, ctap, n0 + rank * (BN / 2), 3);
           } else {
             // weight gradient: k-block = 4 x 16 pixels of one image; A = dy (output channels m0.. as MN-major blocks),
             // B = x shifted by the tap (input channels n0..)
             const int kw = kb % p.tiles_w, kh = (kb / p.tiles_w) % p.tiles_h, kimg = kb / (p.tiles_w * p.tiles_h);
             for (int blk = 0; blk < GM_BM / 64; ++blk)
               tma_load_4d(stage + blk * 8192, &tm_a, &bars->full[st], m0 + blk * 64, kw * 16, kh * 4, kimg);
-            for (int blk = 0; blk < BN / 64; ++blk)
-              tma_load_4d(stage + GM_A_BYTES + blk * 8192, &tm_b, &bars->full[st], n0 + blk * 64, kw * 16 + tap % 3 - 1,
-                          kh * 4 + tap / 3 - 1, kimg);
+            if (!CL2) {
+              for (int blk = 0; blk < BN / 64; ++blk)
+                tma_load_4d(sB + blk * 8192, &tm_b, &bars->full[st], n0 + blk * 64, kw * 16 + tap % 3 - 1, kh * 4 + tap / 3 - 1, kimg);
+            } else {
+              for (int blk = rank * (BN / 128); blk < (rank + 1) * (BN / 128); ++blk)
+                tma_load_4d_mc(sB + blk * 8192, &tm_b, &bars->full[st], n0 + blk * 64, kw * 16 + tap % 3 - 1, kh * 4 + tap / 3 - 1,
+                               kimg, 3);
+            }
           }
         }
         __syncwarp();
@@ -167,7 +189,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const uint64_t dB0 = B_MN ? make_sdesc_sw128(base + GM_A_BYTES, 8192, 1024) : make_sdesc_sw128(base + GM_A_BYTES, 16, 1024);
     constexpr uint64_t KA = A_MN ? 128 : 2, KB = B_MN ? 128 : 2;   // descriptor advance per 16-element k step
     int it = 0, local = 0;
-    for (long w = blockIdx.x; w < items; w += gridDim.x, ++local) {
+    for (long w = w_first; w < items; w += w_step, ++local) {
       const int split = (int)(w % p.splits);
       const int kb0 = split * p.kb_per_split, kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
       const int buf = local % Cfg::ACC;
@@ -184,7 +206,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
           for (int k = 0; k < GM_BK / 16; ++k)
             mma_f16_ss(d, dA + k * KA, dB + k * KB, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
-          tc_commit(&bars->empty[st]);
+          if (CL2) tc_commit_mc(&bars->empty[st], 3); else tc_commit(&bars->empty[st]);
           if (kb == kb1 - 1) tc_commit(&bars->acc_full[buf]);
         }
         __syncwarp();
@@ -206,10 +228,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 320);   // BN floats behind the barrier block
     const bool issuer = r == 0;
     int local = 0;
-    for (long w = blockIdx.x; w < items; w += gridDim.x, ++local) {
+    for (long w = w_first; w < items; w += w_step, ++local) {
       const int tile = (int)(w / p.splits);
-      const int tap = tile / (p.m_tiles * p.n_tiles);
-      const int mt = (tile / p.n_tiles) % p.m_tiles;
+      const int tap = tile / (m_units * p.n_tiles);
+      const int mt = ((tile / p.n_tiles) % m_units) * (CL2 ? 2 : 1) + rank;
       const int m0 = mt * GM_BM, n0 = (tile % p.n_tiles) * BN;
       const int cb_img = mt / (p.tiles_h * p.tiles_w), cth = (mt / p.tiles_w) % p.tiles_h, ctw = mt % p.tiles_w;
       const int buf = local % Cfg::ACC;
@@ -305,24 +327,84 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (CL2) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it / arrive on its barriers
   WS_T(2);
   WS_T_FLUSH();
   if (warp == 9) tmem_dealloc<512>(tmem);
 }
 
-template <int BN, bool A_MN, bool B_MN, int MODE = GM_GEMM>
-static int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, GmParams p, cudaStream_t st) {
+// CTA pairs need a B tile that splits in two halves of whole swizzle groups / 64-column blocks
+constexpr bool gm_pairable(int BN, bool B_MN) { return B_MN ? (BN % 128 == 0) : (BN % 16 == 0); }
+
+template <int BN, bool A_MN, bool B_MN, int MODE, bool CL2>
+static int gemm_launch_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, GmParams p, cudaStream_t st) {
   using Cfg = GmCfg<BN>;
   static bool attr = false;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, MODE, CL2>;
   if (!attr) {
-    RF_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, A_MN, B_MN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    RF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr = true;
   }
-  const long items = (long)p.taps * p.m_tiles * p.n_tiles * p.splits;
-  const int grid = (int)(items < kNumSMs ? items : kNumSMs);
-  gemm_bf16_kernel<BN, A_MN, B_MN, MODE><<<grid, GM_THREADS, Cfg::SMEM, st>>>(ta, tb, to, p);
-  RF_CHECK_LAUNCH("gemm_bf16_kernel");
+  const long m_units = CL2 ? (p.m_tiles + 1) / 2 : p.m_tiles;
+  const long items = (long)p.taps * m_units * p.n_tiles * p.splits;
+  const int per = CL2 ? 2 : 1;
+  const long slots = kNumSMs / per;
+  const int grid = (int)((items < slots ? items : slots) * per);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(GM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = per;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  RF_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, p));
   return RF_OK;
+}
+
+static bool gm_use_pairs() {   // opt-in (RF_GEMM_PAIRS=1): measured neutral in isolation, -1.6 % on the train step
+  static const bool on = [] { const char* e = getenv("RF_GEMM_PAIRS"); return e && e[0] == '1'; }();
+  return on;
+}
+
+template <int BN, bool A_MN, bool B_MN, int MODE = GM_GEMM>
+static int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, GmParams p, cudaStream_t st,
+                       bool pairs = false) {
+  if constexpr (gm_pairable(BN, B_MN)) {
+    if (pairs) return gemm_launch_impl<BN, A_MN, B_MN, MODE, true>(ta, tb, to, p, st);
+  }
+  return gemm_launch_impl<BN, A_MN, B_MN, MODE, false>(ta, tb, to, p, st);
+}
+
+// Tile width: these small-K GEMMs are bound by the operand traffic L2 -> SM (~50 B/clk per SM measured) and by wave
+// quantisation over the persistent CTAs, so pick the BN in {64, 128, 192, 256} that minimises
+//   rounds x (operand rows per CTA and k-block)  =  rounds x (128 + BN)        single CTAs, 148 slots
+//                                                   rounds x (128 + BN / 2)    CTA pairs sharing B, 74 slots
+static int pick_bn(long m_tiles, int N, bool b_mn, bool* pairs_out) {
+  const bool want_pairs = gm_use_pairs() && m_tiles >= 2;
+  int BN = 64;
+  bool pr = want_pairs && gm_pairable(64, b_mn);
+  if (N > 64) {
+    long best = -1;
+    for (int cand : {256, 192, 128}) {
+      const bool cp = want_pairs && gm_pairable(cand, b_mn);
+      const long n_tiles = (N + cand - 1) / cand;
+      const long rounds = cp ? (((m_tiles + 1) / 2) * n_tiles + kNumSMs / 2 - 1) / (kNumSMs / 2)
+                             : (m_tiles * n_tiles + kNumSMs - 1) / kNumSMs;
+      const long cost = rounds * (128 + (cp ? cand / 2 : cand));
+      if (best < 0 || cost < best) {
+        best = cost;
+        BN = cand;
+        pr = cp;
+      }
+    }
+  }
+  *pairs_out = pr;
+  return BN;
 }
 
 }  // namespace rf
@@ -339,22 +421,8 @@ extern "C" int rf_gemm_bf16(const void* a, const void* b, const float* bias, voi
   const long a_pitch = a_mn_major ? M : K, b_pitch = b_mn_major ? N : K;
   RF_REQUIRE(a_pitch % 8 == 0 && b_pitch % 8 == 0 && N % (out_f32 ? 4 : 8) == 0,
              "rf_gemm_bf16: M / N / K pitches must be multiples of 8 elements (got M %d N %d K %d)", M, N, K);
-  // Tile width: these small-K GEMMs are bound by the operand traffic L2 -> SM (~50 B/clk per SM measured) and by wave
-  // quantisation over the 148 persistent CTAs, so pick the BN in {64, 128, 192, 256} that minimises
-  //   rounds(tiles / 148) x (128 + BN)         [bytes per k-block of one CTA, all CTAs in lockstep]
-  int BN = 64;
-  if (N > 64) {
-    const long m_tiles = (M + GM_BM - 1) / GM_BM;
-    long best = -1;
-    for (int cand : {256, 192, 128}) {
-      const long tiles = m_tiles * ((N + cand - 1) / cand);
-      const long cost = ((tiles + kNumSMs - 1) / kNumSMs) * (128 + cand);
-      if (best < 0 || cost < best) {
-        best = cost;
-        BN = cand;
-      }
-    }
-  }
+  bool pairs = false;
+  const int BN = pick_bn((M + GM_BM - 1) / GM_BM, N, b_mn_major != 0, &pairs);
   CUtensorMap ta, tb;
   int rc;
   if (a_mn_major)   // stored [K, M]: box = 64 m (inner) x 64 k
@@ -365,7 +433,8 @@ extern "C" int rf_gemm_bf16(const void* a, const void* b, const float* bias, voi
   if (b_mn_major)
     rc = make_tmap_3d(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, b, (uint64_t)N, (uint64_t)K, 1, (uint64_t)N * 2, (uint64_t)N * K * 2, 64, 64);
   else
-    rc = make_tmap_3d(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, b, (uint64_t)K, (uint64_t)N, 1, (uint64_t)K * 2, (uint64_t)N * K * 2, 64, (uint32_t)BN);
+    rc = make_tmap_3d(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, b, (uint64_t)K, (uint64_t)N, 1, (uint64_t)K * 2, (uint64_t)N * K * 2, 64,
+                      (uint32_t)(pairs ? BN / 2 : BN));   // a CTA pair loads half of the rows each
   if (rc != RF_OK) return rc;
   CUtensorMap to;   // output [M, N]: 128-byte chunks of 128 rows
   if (out_f32)
@@ -392,8 +461,8 @@ extern "C" int rf_gemm_bf16(const void* a, const void* b, const float* bias, voi
   // every token): enough (tile, split) items for ~2 per SM, at least 4 k-blocks each
   p.splits = 1;
   if (accumulate) {
-    const long tiles = (long)p.m_tiles * p.n_tiles;
-    long s = (2l * kNumSMs) / tiles;          // floor: (tile, split) items must not spill into a third round
+    const long tiles = (long)(pairs ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;
+    long s = (2l * (pairs ? kNumSMs / 2 : kNumSMs)) / tiles;          // floor: (tile, split) items must not spill into a third round
     if (s > p.k_blocks / 4) s = p.k_blocks / 4;
     if (s < 1) s = 1;
     p.splits = (int)s;
@@ -402,28 +471,13 @@ extern "C" int rf_gemm_bf16(const void* a, const void* b, const float* bias, voi
   p.splits = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;
   cudaStream_t st = (cudaStream_t)stream;
 #define RF_GM(BN_)                                                                        \
-  (a_mn_major ? (b_mn_major ? gemm_launch<BN_, true, true>(ta, tb, to, p, st) : gemm_launch<BN_, true, false>(ta, tb, to, p, st)) \
-              : (b_mn_major ? gemm_launch<BN_, false, true>(ta, tb, to, p, st) : gemm_launch<BN_, false, false>(ta, tb, to, p, st)))
+  (a_mn_major ? (b_mn_major ? gemm_launch<BN_, true, true>(ta, tb, to, p, st, pairs) : gemm_launch<BN_, true, false>(ta, tb, to, p, st, pairs)) \
+              : (b_mn_major ? gemm_launch<BN_, false, true>(ta, tb, to, p, st, pairs) : gemm_launch<BN_, false, false>(ta, tb, to, p, st, pairs)))
   return BN == 64 ? RF_GM(64) : (BN == 128 ? RF_GM(128) : (BN == 192 ? RF_GM(192) : RF_GM(256)));
 #undef RF_GM
 }
 
 // ---------------------------------------------------------------------------------------------------- 3x3 convolution
-static int pick_bn(long m_tiles, int N) {
-  if (N <= 64) return 64;
-  int BN = 128;
-  long best = -1;
-  for (int cand : {256, 192, 128}) {
-    const long tiles = m_tiles * ((N + cand - 1) / cand);
-    const long cost = ((tiles + kNumSMs - 1) / kNumSMs) * (128 + cand);
-    if (best < 0 || cost < best) {
-      best = cost;
-      BN = cand;
-    }
-  }
-  return BN;
-}
-
 // channels-last activation [B, H, W, C] as a rank-4 map (C, W, H, B) with box (64, 16, bh, 1)
 static int act_map(CUtensorMap* m, const void* base, int B, int H, int W, int C, int bh, CUtensorMapDataType dt, int elem,
                    uint32_t box0) {
@@ -456,7 +510,8 @@ extern "C" int rf_conv3x3_bf16(const void* x, const void* w, const float* bias, 
   p.M = p.m_tiles * GM_BM;
   p.N = Cout;
   p.K = 9 * Cin;
-  const int BN = pick_bn(p.m_tiles, Cout);
+  bool pairs = false;
+  const int BN = pick_bn(p.m_tiles, Cout, false, &pairs);
   p.n_tiles = (Cout + BN - 1) / BN;
   p.cin_blocks = (Cin + 63) / 64;
   p.k_blocks = 9 * p.cin_blocks;
@@ -472,17 +527,17 @@ extern "C" int rf_conv3x3_bf16(const void* x, const void* w, const float* bias, 
   CUtensorMap ta, tb, to;
   int rc = act_map(&ta, x, B, H, W, Cin, 8, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 64);
   if (rc != RF_OK) return rc;
-  rc = filt_map(&tb, w, Cin, Cout, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 64, (uint32_t)BN);
+  rc = filt_map(&tb, w, Cin, Cout, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 64, (uint32_t)(pairs ? BN / 2 : BN));
   if (rc != RF_OK) return rc;
   rc = out_f32 ? act_map(&to, out, B, H, W, Cout, 8, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 32)
                : act_map(&to, out, B, H, W, Cout, 8, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 64);
   if (rc != RF_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   switch (BN) {
-    case 64: return gemm_launch<64, false, false, GM_CONV>(ta, tb, to, p, st);
-    case 128: return gemm_launch<128, false, false, GM_CONV>(ta, tb, to, p, st);
-    case 192: return gemm_launch<192, false, false, GM_CONV>(ta, tb, to, p, st);
-    default: return gemm_launch<256, false, false, GM_CONV>(ta, tb, to, p, st);
+    case 64: return gemm_launch<64, false, false, GM_CONV>(ta, tb, to, p, st, pairs);
+    case 128: return gemm_launch<128, false, false, GM_CONV>(ta, tb, to, p, st, pairs);
+    case 192: return gemm_launch<192, false, false, GM_CONV>(ta, tb, to, p, st, pairs);
+    default: return gemm_launch<256, false, false, GM_CONV>(ta, tb, to, p, st, pairs);
   }
 }
 
@@ -499,7 +554,8 @@ extern "C" int rf_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dw, i
   p.M = Cout;
   p.N = Cin;
   p.m_tiles = (Cout + GM_BM - 1) / GM_BM;
-  const int BN = pick_bn(9l * p.m_tiles, Cin);
+  bool pairs = false;
+  int BN = pick_bn(p.m_tiles, Cin, true, &pairs);     // pairs: the two CTAs take adjacent 128-channel slices of Cout
   p.n_tiles = (Cin + BN - 1) / BN;
   p.tiles_h = (H + 3) / 4;            // pixel k-blocks of 4 x 16
   p.tiles_w = (W + 15) / 16;
@@ -512,8 +568,8 @@ extern "C" int rf_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dw, i
   p.accumulate = 1;
   p.act = 0;
   p.slope = 0.f;
-  const long tiles = 9l * p.m_tiles * p.n_tiles;
-  long s = (2l * kNumSMs) / tiles;
+  const long tiles = 9l * (pairs ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;
+  long s = (2l * (pairs ? kNumSMs / 2 : kNumSMs)) / tiles;
   if (s > p.k_blocks / 4) s = p.k_blocks / 4;
   if (s < 1) s = 1;
   p.kb_per_split = (int)((p.k_blocks + s - 1) / s);
@@ -527,9 +583,9 @@ extern "C" int rf_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dw, i
   if (rc != RF_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   switch (BN) {
-    case 64: return gemm_launch<64, true, true, GM_CONV_WGRAD>(ta, tb, to, p, st);
-    case 128: return gemm_launch<128, true, true, GM_CONV_WGRAD>(ta, tb, to, p, st);
-    case 192: return gemm_launch<192, true, true, GM_CONV_WGRAD>(ta, tb, to, p, st);
-    default: return gemm_launch<256, true, true, GM_CONV_WGRAD>(ta, tb, to, p, st);
+    case 64: return gemm_launch<64, true, true, GM_CONV_WGRAD>(ta, tb, to, p, st, pairs);
+    case 128: return gemm_launch<128, true, true, GM_CONV_WGRAD>(ta, tb, to, p, st, pairs);
+    case 192: return gemm_launch<192, true, true, GM_CONV_WGRAD>(ta, tb, to, p, st, pairs);
+    default: return gemm_launch<256, true, true, GM_CONV_WGRAD>(ta, tb, to, p, st, pairs);
   }
 }
