@@ -414,7 +414,19 @@ def main():
     timer = ops.KernelTimer()
     ops.set_timer(timer)
     ksteps = max(1, min(args.steps, 3))
-    ms_kpass = timed(ksteps, lambda i: model.training_step(batch, 2 + i))
+
+    def kstep(i):
+        # Serial, device-bound conditions for the event pairs: (1) the side-stream branches are switched off for this
+        # pass (a kernel timed while three other streams share the SMs reports its stretched duration); (2) a spin
+        # kernel ahead of the step keeps the device BEHIND the host, so the host gap between the two event records of
+        # a short kernel (tensor-map encode + launch) is not counted as kernel time.
+        torch.cuda._sleep(int(0.7 * 1.9e9))    # ~0.7 s: longer than the host needs to issue one eager step
+        model.training_step(batch, 2 + i)
+
+    concurrent = getattr(model, "concurrent_branches", False)
+    model.concurrent_branches = False
+    ms_kpass = timed(ksteps, kstep)
+    model.concurrent_branches = concurrent
     ops.set_timer(None)
     kern = timer.summary()
     launches = timer.launches // ksteps
@@ -428,7 +440,12 @@ def main():
         model.training_step(batch, step0 + i)
     # ---- timed region: inputs resident in HBM -------------------------------------------------------
     sampler = ClockSampler(local) if rank == 0 else None
+    prof_range = bool(os.environ.get("RF_PROFILER_RANGE"))   # `ncu --profile-from-start off`: launch list of the timed region only
+    if prof_range:
+        torch.cuda.profiler.start()
     ms = timed(args.steps, lambda i: model.training_step(batch, step0 + args.warmup + i))
+    if prof_range:
+        torch.cuda.profiler.stop()
     clocks = sampler.stop() if sampler else None
     loss = float(model._logged["train_loss_src"])
     ms_step = ms / args.steps
@@ -472,7 +489,7 @@ def main():
     if kern:
         name, d = max(kern.items(), key=lambda kv: kv[1]["ms"])
         per_ms = d["ms"] / d["calls"]
-        tensor_bound = name.startswith("sr_attention") or name.startswith("global_corr_umma")
+        tensor_bound = name.startswith(("sr_attention", "global_corr_umma", "gemm_bf16", "conv3x3"))
         if tensor_bound:
             ach = d["flops"] / d["calls"] / (per_ms * 1e-3) / 1e12
             t = NCU_TRAFFIC.get(name)
@@ -487,7 +504,7 @@ def main():
                     "frac": ach / hbm, "traffic": None}
         roof.update({"peak_source": which, "avg_launch_us": per_ms * 1e3, "calls_per_step": d["calls"] / ksteps,
                      "share_of_step": d["ms"] / ksteps / ms_step,
-                     "timed_in": "eager per-kernel pass of %d step(s) (CUDA events around every C-ABI call)" % ksteps})
+                     "timed_in": "eager per-kernel pass of %d step(s): CUDA events around every C-ABI call, side-stream branches off, launch queue pre-filled" % ksteps})
     own = {k: {"calls_per_step": v["calls"] / ksteps, "ms_per_step": v["ms"] / ksteps,
                "GBps": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 and v["bytes"] else None,
                "TFLOPs": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 and v["flops"] else None}

@@ -27,26 +27,34 @@ namespace rf {
 using namespace sm100;
 
 constexpr int GM_BM = 128, GM_BK = 64;
-constexpr int GM_THREADS = 320;   // 2 epilogue warpgroups (warps 0-7) + TMA warp (8) + MMA warp (9)
+constexpr int GM_THREADS = 352;   // 2 epilogue warpgroups (warps 0-7) + TMA-load warp (8) + MMA warp (9) + TMA-store warp (10)
 constexpr int GM_A_BYTES = GM_BM * GM_BK * 2;          // 16 KiB per stage
 
-template <int BN>
+template <int BN, int MODE>
 struct GmCfg {
   static constexpr int B_BYTES = BN * GM_BK * 2;
   static constexpr int STAGE = GM_A_BYTES + B_BYTES;
+  // Staging buffers per epilogue warpgroup ([128 rows x 128 B] TMA-store sources).  A TMA store takes ~1 500 cycles from
+  // issue until its shared-memory source may be rewritten (timeline traces: 2 000 cycles per chunk with one buffer,
+  // the epilogue of a K = 320 tile longer than its MMAs), so two buffers alternate and a chunk only waits for the store
+  // before the previous one.  The long-K 256-wide convolution tiles keep the fourth operand stage instead (their
+  // epilogue hides behind 144 k-blocks of MMAs).
+  static constexpr int EPI = (MODE == 1 && BN == 256) ? 1 : 2;
 #ifdef WS_TRACE
-  static constexpr int STAGES = BN == 256 ? 3 : (BN == 192 ? 4 : (BN == 128 ? 5 : 6));   // (the trace log takes 22 KiB of static smem)
+  static constexpr int STAGES = BN == 256 ? 2 : (BN == 192 ? 3 : (BN == 128 ? 4 : 5));   // (the trace log takes 22 KiB of static smem)
 #else
-  static constexpr int STAGES = BN == 256 ? 4 : (BN == 192 ? 4 : (BN == 128 ? 6 : 8));   // <= 192 KiB of operand stages
+  static constexpr int STAGES = BN == 256 ? (EPI == 1 ? 4 : 3) : (BN == 192 ? 4 : (BN == 128 ? 5 : 6));
 #endif
   static constexpr int ACC = 512 / BN;                 // accumulator buffers in TMEM (2 for BN = 192 / 256)
-  static constexpr int STAGING = 2 * 16384;            // one [128 rows x 128 B] output chunk per epilogue warpgroup (TMA store sources)
-  static constexpr int SMEM = STAGES * STAGE + STAGING + 1024 + 320 + 1024;   // + alignment slack, barriers, bias slice   // + alignment slack, barriers, bias slice
+  static constexpr int STAGING = 2 * EPI * 16384;
+  static constexpr int BIAS_BYTES = EPI * BN * 4;       // one bias slice per tile in flight
+  static constexpr int SMEM = STAGES * STAGE + STAGING + 1024 + 384 + BIAS_BYTES;   // + alignment slack, barrier block
 };
 
 struct GmBars {
   uint64_t full[8], empty[8];
   uint64_t acc_full[8], acc_empty[8];
+  uint64_t st_full[4], st_free[4];     // epilogue staging buffers [warpgroup * 2 + buffer]: filled by 4 warps / read out by the TMA store
   uint32_t tmem_base;
 };
 
@@ -81,7 +89,7 @@ template <int BN, bool A_MN, bool B_MN, int MODE, bool CL2>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_out, const GmParams p) {
-  using Cfg = GmCfg<BN>;
+  using Cfg = GmCfg<BN, MODE>;
   WS_T_INIT();
   WS_T(0);
   extern __shared__ uint8_t smem_raw[];
@@ -102,6 +110,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       for (int s = 0; s < Cfg::ACC; ++s) {
         mbar_init(&bars->acc_full[s], 1);
         mbar_init(&bars->acc_empty[s], 8);
+      }
+      for (int s = 0; s < 4; ++s) {
+        mbar_init(&bars->st_full[s], 4);
+        mbar_init(&bars->st_free[s], 1);
       }
       fence_barrier_init();
     }
@@ -213,32 +225,90 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         WS_T(21);
       }
     }
-  } else {
-    // ------------------------------------------------------------------ epilogue warpgroups (thread = accumulator row)
-    // TMEM -> registers (+ bias, -> bf16) -> swizzled smem chunk [128 rows x 128 B] -> TMA store (or TMA reduce-add for
-    // the accumulating fp32 output): full 128-byte lines leave the SM whatever the row pitch, the tensor map clips
-    // ragged M / N edges, and the stores run asynchronously.  Two warpgroups take alternate 128-byte column chunks of
-    // every tile (measured: one warpgroup needs ~1 200 cycles per chunk and was the kernel's bottleneck).
-    const int wg = warp >> 2, r = tid & 127;
-    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    const int cpc = p.out_f32 ? 32 : 64;                 // output columns per 128-byte chunk
+  } else if (warp == 10) {
+    // ------------------------------------------------------------------ TMA-store issuer
+    // One thread turns the staging chunks the epilogue warps fill into TMA stores (or TMA reduce-adds for the accumulating
+    // fp32 outputs).  Timeline traces showed why this is a warp of its own: issuing one bulk store costs the issuing thread
+    // 300-500 cycles and its shared-memory source is only reusable ~1 500 cycles later; with the issue inside the epilogue
+    // warpgroups (and a bar.sync around it) every 128-byte column chunk cost ~2 300 cycles and the epilogue of a K = 320
+    // tile took longer than its MMAs.
+    const int cpc = p.out_f32 ? 32 : 64;
     const int nchunk = BN / cpc;
-    const uint32_t sw = (uint32_t)(r & 7);
-    uint8_t* sbuf = staging + wg * 16384;
-    float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 320);   // BN floats behind the barrier block
-    const bool issuer = r == 0;
-    int local = 0;
-    for (long w = w_first; w < items; w += w_step, ++local) {
+    const int lane = tid & 31;
+    int cnt0 = 0, cnt1 = 0;              // chunks stored so far per warpgroup (mirrors the epilogue warps' counters)
+    int prev = -1;                       // staging buffer of the most recently issued store
+    for (long w = w_first; w < items; w += w_step) {
       const int tile = (int)(w / p.splits);
       const int tap = tile / (m_units * p.n_tiles);
       const int mt = ((tile / p.n_tiles) % m_units) * (CL2 ? 2 : 1) + rank;
       const int m0 = mt * GM_BM, n0 = (tile % p.n_tiles) * BN;
       const int cb_img = mt / (p.tiles_h * p.tiles_w), cth = (mt / p.tiles_w) % p.tiles_h, ctw = mt % p.tiles_w;
+#pragma unroll 1
+      for (int c = 0; c < nchunk; ++c) {
+        const int wg = c & 1;
+        const int cnt = wg ? cnt1 : cnt0;
+        if (wg) ++cnt1; else ++cnt0;
+        const int b = Cfg::EPI == 2 ? (cnt & 1) : 0, use = cnt / Cfg::EPI;
+        const int slot = wg * 2 + b;
+        mbar_wait(&bars->st_full[slot], use & 1);
+        if (lane == 0) {
+          const uint8_t* sbuf = staging + (wg * Cfg::EPI + b) * 16384;
+          const int col = n0 + c * cpc;
+          if (col < p.N) {
+            if (MODE == GM_CONV) tma_store_4d(&tm_out, sbuf, col, ctw * 16, cth * 8, cb_img);
+            else if (MODE == GM_CONV_WGRAD) tma_reduce_add_3d(&tm_out, sbuf, col, tap, m0);
+            else if (p.accumulate) tma_reduce_add_3d(&tm_out, sbuf, col, m0, 0);
+            else tma_store_3d(&tm_out, sbuf, col, m0, 0);
+          }
+          tma_store_commit();            // one group per chunk, empty or not: wait_group.read<1> counts groups
+          WS_T(11);
+          if (prev >= 0) {               // every store but the one just issued has read its source: hand that buffer back
+            tma_store_wait_read<1>();
+            mbar_arrive(&bars->st_free[prev]);
+          }
+        }
+        prev = slot;
+        __syncwarp();
+      }
+    }
+    if (lane == 0) tma_store_wait_read<0>();   // the staging smem may go away; the global writes complete with the grid
+    WS_T(12);
+  } else {
+    // ------------------------------------------------------------------ epilogue warpgroups (thread = accumulator row)
+    // TMEM -> registers (+ bias, -> bf16) -> swizzled smem chunk [128 rows x 128 B], handed to the store warp: full
+    // 128-byte lines leave the SM whatever the row pitch, the tensor map clips ragged M / N edges, and the stores run
+    // asynchronously.  Two warpgroups take alternate 128-byte column chunks of every tile; each warp runs on its own
+    // (mbarrier hand-offs per staging buffer, no CTA-wide barrier inside a tile).
+    const int wg = warp >> 2, r = tid & 127;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const int cpc = p.out_f32 ? 32 : 64;                 // output columns per 128-byte chunk
+    const int nchunk = BN / cpc;
+    const uint32_t sw = (uint32_t)(r & 7);
+    uint8_t* const sbuf0 = staging + wg * (Cfg::EPI * 16384);
+    int nstore = 0;                      // chunks this warpgroup has handed over so far (selects the staging buffer)
+    float* const sbias0 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 384);   // EPI slices of BN floats
+    auto bias_at = [&](long ww) -> float {   // this thread's element of the bias slice of work item ww (0 beyond N / the end)
+      if (ww >= items || tid >= BN) return 0.f;
+      const int nn = (int)((ww / p.splits) % p.n_tiles) * BN + tid;
+      return nn < p.N ? __ldg(p.bias + nn) : 0.f;
+    };
+    float bias_next = 0.f;
+    if (p.bias && Cfg::EPI == 2 && tid < BN) sbias0[tid] = bias_at(w_first);
+    int local = 0;
+    for (long w = w_first; w < items; w += w_step, ++local) {
       const int buf = local % Cfg::ACC;
+      const float* sbias = sbias0 + (Cfg::EPI == 2 ? (local & 1) * BN : 0);
       if (p.bias) {   // this tile's bias slice, zero beyond N, read back as broadcast shared-memory vectors
-        asm volatile("bar.sync 3, 256;" ::: "memory");      // both warpgroups are done with the previous tile's slice
-        for (int i = tid; i < BN; i += 256) sbias[i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
-        asm volatile("bar.sync 3, 256;" ::: "memory");
+        if (Cfg::EPI == 2) {
+          // slice `local` was written during the previous tile (or before the loop); the next tile's element is
+          // fetched now and stored when this tile is done, so no global-load latency sits in front of a tile
+          asm volatile("bar.sync 3, 256;" ::: "memory");
+          bias_next = bias_at(w + w_step);
+        } else {
+          asm volatile("bar.sync 3, 256;" ::: "memory");      // both warpgroups are done with the previous tile's slice
+          if (tid < BN) sbias0[tid] = bias_at(w);
+          asm volatile("bar.sync 3, 256;" ::: "memory");
+        }
       }
       mbar_wait(&bars->acc_full[buf], (local / Cfg::ACC) & 1);
       tc_fence_after();
@@ -246,7 +316,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const uint32_t t = tmem + lane_off + buf * BN;
 #pragma unroll 1
       for (int c = wg; c < nchunk; c += 2) {
-        const int col = n0 + c * cpc;
         uint32_t pk[32];
         if (p.out_f32) {
           tmem_ld32(t + c * 32, pk);
@@ -300,30 +369,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           __syncwarp();
           if ((tid & 31) == 0) mbar_arrive(&bars->acc_empty[buf]);
         }
-        if (issuer) tma_store_wait_read<0>();            // the previous store of this warpgroup is done with the buffer
-        if (wg == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
-        uint4* srow = reinterpret_cast<uint4*>(sbuf + r * 128);
+        WS_T(13);
+        const int b = Cfg::EPI == 2 ? (nstore & 1) : 0, use = nstore / Cfg::EPI;
+        ++nstore;
+        if (use > 0) mbar_wait(&bars->st_free[wg * 2 + b], (use - 1) & 1);   // the store that last used this buffer has read it
+        WS_T(14);
+        uint4* srow = reinterpret_cast<uint4*>(sbuf0 + b * 16384 + r * 128);
 #pragma unroll
         for (int q = 0; q < 8; ++q) srow[q ^ sw] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
         fence_proxy_async();
-        if (wg == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
-        if (issuer && col < p.N) {
-          if (MODE == GM_CONV) tma_store_4d(&tm_out, sbuf, col, ctw * 16, cth * 8, cb_img);
-          else if (MODE == GM_CONV_WGRAD) tma_reduce_add_3d(&tm_out, sbuf, col, tap, m0);
-          else if (p.accumulate) tma_reduce_add_3d(&tm_out, sbuf, col, m0, 0);
-          else tma_store_3d(&tm_out, sbuf, col, m0, 0);
-          WS_T(11);
-          tma_store_commit();
-        }
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&bars->st_full[wg * 2 + b]);
+        WS_T(15);
       }
       if (nchunk == 1 && wg == 1) {   // BN = 64 bf16: a single chunk, warpgroup 1 only releases the accumulator
         tc_fence_before();
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(&bars->acc_empty[buf]);
       }
+      if (p.bias && Cfg::EPI == 2 && tid < BN) sbias0[((local + 1) & 1) * BN + tid] = bias_next;
     }
-    if (issuer) tma_store_wait_read<0>();   // the staging smem may go away; the global writes complete with the grid
-    WS_T(12);
   }
   tc_fence_before();
   __syncthreads();
@@ -338,7 +403,7 @@ constexpr bool gm_pairable(int BN, bool B_MN) { return B_MN ? (BN % 128 == 0) : 
 
 template <int BN, bool A_MN, bool B_MN, int MODE, bool CL2>
 static int gemm_launch_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, GmParams p, cudaStream_t st) {
-  using Cfg = GmCfg<BN>;
+  using Cfg = GmCfg<BN, MODE>;
   static bool attr = false;
   auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, MODE, CL2>;
   if (!attr) {

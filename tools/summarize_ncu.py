@@ -70,8 +70,7 @@ def full(reps, out):
 
 
 if __name__ == "__main__":
-    launches(sys.argv[1], sys.argv[2],
-             "ncu --metrics gpu__time_duration.sum --clock-control none -s 28000 -c 11000 python bench.py --steps 1 --warmup 0 "
-             "--no-cpu-baseline --no-e2e --no-graphs (eager step; the profiling window was cut by the 900 s limit after "
-             "~8 800 launches = most of one step); cold-cache serialised times: compare SHARES")
+    import os
+    launches(sys.argv[1], sys.argv[2], os.environ.get("NCU_NOTE", "ncu --metrics gpu__time_duration.sum --clock-control none "
+                                                      "<bench command>; cold-cache serialised times: compare SHARES"))
     full(sys.argv[4:], sys.argv[3])
