@@ -373,17 +373,22 @@ int rf_adamw_step_dev(float* param, const float* grad, float* exp_avg, float* ex
 int rf_gemm_bf16(const void* a, const void* b, const float* bias, void* out, int M, int N, int K, int a_mn_major,
                  int b_mn_major, int out_f32, int accumulate, void* stream);
 
-/* ---- 3x3 convolution (stride 1, padding 1) as an implicit GEMM on the same tcgen05 kernel --------------------- */
-/* Replaces the library convolutions of the DAFormer bottleneck (models/heads/daformer.py:102-108, modules.py:16-56)
- * and the VGG-16 alignment backbone (models/backbones/vgg.py:108-120) on channels-last bf16 tensors:
+/* ---- 3x3 convolution (stride 1, padding = dilation) as an implicit GEMM on the same tcgen05 kernel ------------- */
+/* Replaces the library convolutions of the DAFormer bottleneck (models/heads/daformer.py:102-108, modules.py:16-56),
+ * the VGG-16 alignment backbone (models/backbones/vgg.py:108-120) and the BN-folded flow decoders / dilated
+ * RefinementModule of the alignment head (models/modules.py:395-477; dilation 1..16) on channels-last bf16 tensors:
  *   x   : bf16 [B,H,W,Cin]   w : bf16 [Cout,3,3,Cin] (the channels-last filter)   bias : f32 [Cout] or NULL
  *   out : bf16 or f32 [B,H,W,Cout];  act: 0 none, 1 ReLU, 2 LeakyReLU(slope) fused in the epilogue
  * The input gradient is the same call on dy with the flipped, transposed filter [Cin,3,3,Cout].
  * rf_conv3x3_wgrad_bf16: dw f32 [Cout,3,3,Cin] += sum over pixels dy[..,co] * x[.. shifted ..,ci] (split over the
  * pixels, partial sums reduce-added).  Cin, Cout multiples of 8. */
 int rf_conv3x3_bf16(const void* x, const void* w, const float* bias, void* out, int B, int H, int W, int Cin, int Cout,
-                    int out_f32, int act, float slope, void* stream);
+                    int out_f32, int act, float slope, int dilation, void* stream);
 int rf_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dw, int B, int H, int W, int Cin, int Cout, void* stream);
+
+/* nn.MaxPool2d(2, 2) of VGG.forward (models/backbones/vgg.py:108-120) on a channels-last bf16 tensor:
+ * x [B,H,W,C] -> y [B,H/2,W/2,C] (floor); C a multiple of 8. */
+int rf_maxpool2x2_nhwc_bf16(const void* x, void* y, int B, int H, int W, int C, void* stream);
 
 /* ---- DACS strong transform (class mix + colour jitter + gaussian blur) ---------------------------------- */
 /* Replaces get_dacs_mix's per-image loop over helpers/dacs_transforms.py strong_transform

@@ -70,6 +70,7 @@ struct GmParams {
   int cin_blocks;          // MODE 1: 64-channel blocks per tap
   int act;                 // MODE 1 epilogue: 0 none, 1 ReLU, 2 LeakyReLU(slope)
   float slope;
+  int dil;                 // MODE 1: dilation (= padding) of the 3x3 filter
 };
 
 enum { GM_GEMM = 0, GM_CONV = 1, GM_CONV_WGRAD = 2 };
@@ -169,7 +170,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             // k-block = (filter tap, 64 input channels): the activation box is shifted by the tap, rows / columns
             // outside the image are zero-filled by TMA (= the convolution's zero padding)
             const int ctap = kb / p.cin_blocks, cb = kb % p.cin_blocks;
-            tma_load_4d(stage, &tm_a, &bars->full[st], cb * 64, ctw * 16 + ctap % 3 - 1, cth * 8 + ctap / 3 - 1, cb_img);
+            tma_load_4d(stage, &tm_a, &bars->full[st], cb * 64, ctw * 16 + (ctap % 3 - 1) * p.dil, cth * 8 + (ctap / 3 - 1) * p.dil, cb_img);
             if (!CL2) tma_load_3d(sB, &tm_b, &bars->full[st], cb * 64, ctap, n0);
             else tma_load_3d_mc(sB + rank * (BN / 2) * 128, &tm_b, &bars->full[st], cb * 64, ctap, n0 + rank * (BN / 2), 3);
           } else {
@@ -522,6 +523,7 @@ extern "C" int rf_gemm_bf16(const void* a, const void* b, const float* bias, voi
   p.H = p.W = p.tiles_h = p.tiles_w = p.cin_blocks = 1;
   p.act = 0;
   p.slope = 0.f;
+  p.dil = 1;
   // split the contraction only for accumulating fp32 outputs (the weight gradient: few output tiles, a contraction over
   // every token): enough (tile, split) items for ~2 per SM, at least 4 k-blocks each
   p.splits = 1;
@@ -561,11 +563,12 @@ static int filt_map(CUtensorMap* m, const void* base, int Cin, int Cout, CUtenso
 }
 
 extern "C" int rf_conv3x3_bf16(const void* x, const void* w, const float* bias, void* out, int B, int H, int W, int Cin,
-                               int Cout, int out_f32, int act, float slope, void* stream) {
+                               int Cout, int out_f32, int act, float slope, int dilation, void* stream) {
   RF_REQUIRE(x && w && out && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "rf_conv3x3_bf16: bad arguments");
   RF_REQUIRE((((uintptr_t)x | (uintptr_t)w | (uintptr_t)out) & 15) == 0, "rf_conv3x3_bf16: operands must be 16-byte aligned");
   RF_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0, "rf_conv3x3_bf16: channel counts must be multiples of 8 (got %d -> %d)", Cin, Cout);
   RF_REQUIRE(act >= 0 && act <= 2, "rf_conv3x3_bf16: act must be 0 (none), 1 (ReLU) or 2 (LeakyReLU)");
+  RF_REQUIRE(dilation >= 1 && dilation <= 64, "rf_conv3x3_bf16: dilation must be in [1, 64]");
   GmParams p;
   p.bias = bias;
   p.out = out;
@@ -589,6 +592,7 @@ extern "C" int rf_conv3x3_bf16(const void* x, const void* w, const float* bias, 
   p.W = W;
   p.act = act;
   p.slope = slope;
+  p.dil = dilation;
   CUtensorMap ta, tb, to;
   int rc = act_map(&ta, x, B, H, W, Cin, 8, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 64);
   if (rc != RF_OK) return rc;
@@ -633,6 +637,7 @@ extern "C" int rf_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dw, i
   p.accumulate = 1;
   p.act = 0;
   p.slope = 0.f;
+  p.dil = 1;
   const long tiles = 9l * (pairs ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;
   long s = (2l * (pairs ? kNumSMs / 2 : kNumSMs)) / tiles;
   if (s > p.k_blocks / 4) s = p.k_blocks / 4;

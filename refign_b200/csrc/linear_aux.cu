@@ -189,6 +189,33 @@ bias_act_scalar_kernel(T* __restrict__ y, const float* __restrict__ bias, long n
   }
 }
 
+// 2x2 / stride 2 max-pool of a channels-last bf16 tensor [B,H,W,C] -> [B,H/2,W/2,C] (floor, as nn.MaxPool2d(2, 2)):
+// one thread per 8 channels of one output pixel, four 16-byte loads, packed bf16 max (VGG.forward, vgg.py:108-120)
+__global__ void __launch_bounds__(256) maxpool2x2_nhwc_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, long nchunks,
+                                                              int cpp, int Ho, int Wo, int H, int W) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= nchunks) return;
+  const int c = (int)(i % cpp);
+  long pix = i / cpp;
+  const int xo = (int)(pix % Wo);
+  pix /= Wo;
+  const int yo = (int)(pix % Ho);
+  const long b = pix / Ho;
+  const uint4* r0 = x + ((b * H + 2 * yo) * (long)W + 2 * xo) * cpp + c;
+  const uint4* r1 = r0 + (long)W * cpp;
+  uint4 v[4] = {__ldg(r0), __ldg(r0 + cpp), __ldg(r1), __ldg(r1 + cpp)};
+  uint4 o;
+  uint32_t* po = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    __nv_bfloat162 m = *reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const uint32_t*>(&v[0]) + k);
+#pragma unroll
+    for (int q = 1; q < 4; ++q) m = __hmax2(m, *reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const uint32_t*>(&v[q]) + k));
+    po[k] = *reinterpret_cast<const uint32_t*>(&m);
+  }
+  y[i] = o;
+}
+
 }  // namespace rf
 
 using namespace rf;
@@ -269,5 +296,18 @@ extern "C" int rf_bias_act(void* y, const float* bias, int64_t numel, int C, int
   else
     bias_act_kernel<float, 4><<<(unsigned)blocks, 256, 0, st>>>((float*)y, bias, nvec, C, chan_inner, act, slope);
   RF_CHECK_LAUNCH("bias_act_kernel");
+  return RF_OK;
+}
+
+extern "C" int rf_maxpool2x2_nhwc_bf16(const void* x, void* y, int B, int H, int W, int C, void* stream) {
+  RF_REQUIRE(x && y && B > 0 && H >= 2 && W >= 2 && C > 0, "rf_maxpool2x2_nhwc_bf16: bad argument");
+  RF_REQUIRE(C % 8 == 0, "rf_maxpool2x2_nhwc_bf16: C=%d must be a multiple of 8", C);
+  RF_REQUIRE((((uintptr_t)x | (uintptr_t)y) & 15) == 0, "rf_maxpool2x2_nhwc_bf16: buffers must be 16-byte aligned");
+  const int cpp = C / 8, Ho = H / 2, Wo = W / 2;
+  const long nchunks = (long)B * Ho * Wo * cpp;
+  const long blocks = (nchunks + 255) / 256;
+  RF_REQUIRE(blocks < (1l << 31), "rf_maxpool2x2_nhwc_bf16: tensor too large");
+  maxpool2x2_nhwc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, nchunks, cpp, Ho, Wo, H, W);
+  RF_CHECK_LAUNCH("maxpool2x2_nhwc_kernel");
   return RF_OK;
 }

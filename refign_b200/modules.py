@@ -97,7 +97,8 @@ class ConvBNReLU(nn.Module):
             act = self.activation if self.use_activation else None
             if x.is_cuda and (act is None or isinstance(act, (nn.ReLU, nn.LeakyReLU))):
                 # frozen block: library conv + ONE fused bias / activation sweep
-                return ops.conv_bias_act(x, w.to(x.dtype), b, conv.stride, conv.padding, conv.dilation, conv.groups, act)
+                return ops.conv_bias_act(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups, act,
+                                         cache_filter=self._folded is not None)
             x = F.conv2d(x, w.to(x.dtype), b.to(x.dtype), conv.stride, conv.padding, conv.dilation, conv.groups)
         else:
             if self._is_depthwise3x3():
@@ -212,7 +213,7 @@ class OpticalFlowEstimatorResidualConnection(nn.Module):
         x2 = x2 + self.conv0_skip(x0)
         x4 = self.conv_4(self.conv_3(F.leaky_relu(x2, 0.1)))
         x4 = F.leaky_relu(x4 + self.conv2_skip(x2), 0.1)
-        mapping = self.predict_mapping(x4)
+        mapping = ops.conv2d_frozen(x4, self.predict_mapping)
         return (mapping, x4) if self.output_x else mapping
 
 
@@ -231,7 +232,9 @@ class RefinementModule(nn.Module):
         self.dc_convs = nn.Sequential(*layers)
 
     def forward(self, x):
-        return self.dc_convs(x)
+        for layer in self.dc_convs:
+            x = ops.conv2d_frozen(x, layer) if isinstance(layer, nn.Conv2d) else layer(x)
+        return x
 
 
 class UncertaintyModule(nn.Module):
@@ -274,4 +277,4 @@ class UncertaintyModule(nn.Module):
             x = torch.cat((x, feat, up_previous_uncertainty, up_previous_flow), 1)
         else:
             x = torch.cat((x, feat), 1)
-        return self.predict_uncertainty_final(self.pred_conv_1(self.pred_conv_0(x)))
+        return ops.conv2d_frozen(self.pred_conv_1(self.pred_conv_0(x)), self.predict_uncertainty_final)

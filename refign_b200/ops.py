@@ -566,8 +566,8 @@ def gemm_bf16_supported(M, N, K):
     return M > 0 and N % 8 == 0 and K % 8 == 0 and M % 8 == 0
 
 
-def conv3x3_nhwc_raw(x, w_cl, bias=None, act=0, slope=0.0, out_dtype=torch.bfloat16):
-    """3x3 / stride 1 / padding 1 convolution of a contiguous channels-last bf16 tensor x [B,H,W,Cin] with the
+def conv3x3_nhwc_raw(x, w_cl, bias=None, act=0, slope=0.0, out_dtype=torch.bfloat16, dilation=1):
+    """3x3 / stride 1 / padding = dilation convolution of a contiguous channels-last bf16 tensor x [B,H,W,Cin] with the
     channels-last bf16 filter w_cl [Cout,3,3,Cin] (+ f32 bias, + fused ReLU / LeakyReLU) on the tcgen05 implicit GEMM."""
     require_cuda(x, w_cl)
     assert x.dtype == torch.bfloat16 and w_cl.dtype == torch.bfloat16 and x.is_contiguous() and w_cl.is_contiguous()
@@ -578,7 +578,7 @@ def conv3x3_nhwc_raw(x, w_cl, bias=None, act=0, slope=0.0, out_dtype=torch.bfloa
     bias_f = None if bias is None else _f32c(bias)
     with torch.cuda.device(x.device):
         _run("rf_conv3x3_bf16", ptr(x), ptr(w_cl), ptr(bias_f), ptr(out), B, H, W, Cin, Cout,
-             int(out_dtype == torch.float32), int(act), float(slope), _stream(),
+             int(out_dtype == torch.float32), int(act), float(slope), int(dilation), _stream(),
              work=(2 * x.numel() + 2 * w_cl.numel() + out.numel() * out.element_size(), 2 * 9 * out.numel() * Cin),
              tag="conv3x3")
     return out
@@ -826,7 +826,69 @@ def refresh_derived(flat_shadow=None):
             _derive_conv(src, w_cl, w_dg)
 
 
-def conv_bias_act(x, weight, bias, stride, padding, dilation, groups, act=None):
+_FROZEN_FILTERS = {}
+
+
+def _frozen_filter(weight, bias, cache=True):
+    """Channels-last bf16 copy of a frozen conv filter [Cout,Cin,kh,kw] -> [Cout8,kh,kw,Cin8] ([Cout8,Cin8] for 1x1) with
+    both channel counts zero-padded to multiples of 8, + the f32 bias padded alike.  Cached per weight tensor: the callers
+    are the frozen (no-grad) stacks, whose folded weights are themselves cached (ConvBNReLU._fold) or parameters;
+    ``cache=False`` for weights that are re-derived on every call (trainable blocks evaluated under no_grad)."""
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape), weight.dtype,
+           None if bias is None else (bias.data_ptr(), bias._version))
+    hit = _FROZEN_FILTERS.get(key) if cache else None
+    if hit is not None:
+        return hit[:3]
+    co, ci, kh, kw = weight.shape
+    co8, ci8 = (co + 7) // 8 * 8, (ci + 7) // 8 * 8
+    w = torch.zeros(co8, kh, kw, ci8, device=weight.device, dtype=torch.bfloat16)
+    w[:co, :, :, :ci] = weight.detach().permute(0, 2, 3, 1)
+    if kh == 1 and kw == 1:
+        w = w.view(co8, ci8)
+    b = None
+    if bias is not None:
+        b = torch.zeros(co8, device=weight.device, dtype=torch.float32)
+        b[:co] = bias.detach().float()
+    if cache:
+        if len(_FROZEN_FILTERS) > 512:
+            _FROZEN_FILTERS.clear()
+        # the entry keeps the source tensors alive, so their addresses cannot be handed to other tensors while it exists
+        _FROZEN_FILTERS[key] = (w, b, co, weight, bias)
+    return w, b, co
+
+
+def _nhwc_padded(x, c8):
+    """Logical-NCHW bf16 tensor -> contiguous [B,H,W,c8] (a view when it already is channels-last with c8 channels)."""
+    xh = x.permute(0, 2, 3, 1)
+    if xh.shape[3] == c8:
+        return xh if xh.is_contiguous() else xh.contiguous()
+    out = torch.zeros(xh.shape[0], xh.shape[1], xh.shape[2], c8, device=x.device, dtype=x.dtype)
+    out[..., :xh.shape[3]] = xh
+    return out
+
+
+def max_pool2x2(x):
+    """nn.MaxPool2d(2, 2) on a logical-NCHW tensor; channels-last bf16 CUDA tensors take the 16-byte-vector kernel."""
+    xh = x.permute(0, 2, 3, 1)
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and xh.is_contiguous() and x.shape[1] % 8 == 0
+            and x.shape[2] >= 2 and x.shape[3] >= 2 and not (torch.is_grad_enabled() and x.requires_grad)):
+        return F.max_pool2d(x, 2, 2)
+    B, H, W, C = xh.shape
+    y = torch.empty(B, H // 2, W // 2, C, device=x.device, dtype=x.dtype)
+    with torch.cuda.device(x.device):
+        _run("rf_maxpool2x2_nhwc_bf16", ptr(xh), ptr(y), B, H, W, C, _stream(), work=(2 * xh.numel() + 2 * y.numel(), 0),
+             tag="maxpool2x2")
+    return y.permute(0, 3, 1, 2)
+
+
+def conv2d_frozen(x, conv):
+    """A plain nn.Conv2d of a frozen stack (the prediction layers of the alignment decoders) through conv_bias_act."""
+    if x.is_cuda and not torch.is_grad_enabled() and conv.padding_mode == 'zeros':
+        return conv_bias_act(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups, None)
+    return conv(x)
+
+
+def conv_bias_act(x, weight, bias, stride, padding, dilation, groups, act=None, cache_filter=True):
     """``act(conv2d(x, weight) + bias)`` for the frozen (no-grad) conv stacks: library convolution without
     bias + one in-place 16-byte-vector bias/activation kernel (the library path runs a broadcast add and a
     separate activation pass over the full-resolution tensors).  ``act``: None, nn.ReLU or nn.LeakyReLU."""
@@ -838,18 +900,26 @@ def conv_bias_act(x, weight, bias, stride, padding, dilation, groups, act=None):
     elif act is not None:
         raise RuntimeError("conv_bias_act: unsupported activation %r" % (act,))
     pair = lambda v: (v, v) if isinstance(v, int) else tuple(v)
-    if (OWN_GEMM and x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and x.dim() == 4
-            and tuple(weight.shape[2:]) == (3, 3) and pair(stride) == (1, 1) and pair(padding) == (1, 1)
-            and pair(dilation) == (1, 1) and groups == 1 and weight.shape[0] % 8 == 0 and weight.shape[1] % 8 == 0):
-        # tcgen05 implicit GEMM on the channels-last tensors, bias + activation in its epilogue (VGG-16 3x3 stacks)
-        xh = x.permute(0, 2, 3, 1)
-        if not xh.is_contiguous():
-            xh = xh.contiguous()
-        w_cl = weight.permute(0, 2, 3, 1)
-        if not w_cl.is_contiguous():
-            w_cl = w_cl.contiguous()
-        return conv3x3_nhwc_raw(xh, w_cl, bias, act=code, slope=slope).permute(0, 3, 1, 2)
-    y = F.conv2d(x, weight, None, stride, padding, dilation, groups)
+    if (OWN_GEMM and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and groups == 1 and pair(stride) == (1, 1)
+            and not torch.is_grad_enabled()):
+        ks, dil, pad = tuple(weight.shape[2:]), pair(dilation), pair(padding)
+        if ks == (3, 3) and dil[0] == dil[1] and pad == dil and 1 <= dil[0] <= 64:
+            # tcgen05 implicit GEMM on the channels-last tensors, bias + activation in its epilogue (VGG-16 stacks, the
+            # BN-folded flow decoders and the dilated RefinementModule).  Channel counts that are not multiples of 8
+            # (decoder inputs 81 + 2 + 1 ..., the 2- / 1-channel prediction layers) are zero-padded: the input once while
+            # it is made channels-last, the filter once per weight (cached).
+            w_cl, b_pad, cout = _frozen_filter(weight, bias, cache_filter)
+            y = conv3x3_nhwc_raw(_nhwc_padded(x, w_cl.shape[3]), w_cl, b_pad, act=code, slope=slope, dilation=dil[0])
+            return y.permute(0, 3, 1, 2)[:, :cout]
+        if ks == (1, 1) and pad == (0, 0) and code == 0:
+            # 1x1 skip convolutions of the decoders: the tcgen05 GEMM on the pixel rows, bias in its epilogue
+            w_cl, b_pad, cout = _frozen_filter(weight, bias, cache_filter)
+            xh = _nhwc_padded(x, w_cl.shape[1])
+            B_, H_, W_, Ci = xh.shape
+            if (B_ * H_ * W_) % 8 == 0:
+                y = gemm_bf16(xh.view(-1, Ci), w_cl, bias=b_pad)
+                return y.view(B_, H_, W_, -1).permute(0, 3, 1, 2)[:, :cout]
+    y = F.conv2d(x, weight.to(x.dtype), None, stride, padding, dilation, groups)
     N, C, H, W = y.shape
     if y.is_contiguous():
         inner = H * W

@@ -96,6 +96,10 @@ class VGG(nn.Module):
                         m._rf_w_bf16, m._rf_w_version = w, m.weight._version
                 x = ops.conv_bias_act(x, w, m.bias, m.stride, m.padding, m.dilation, m.groups, nxt)
                 i += 2
+            elif isinstance(m, nn.MaxPool2d) and m.kernel_size in (2, (2, 2)) and m.stride in (2, (2, 2)) \
+                    and m.padding in (0, (0, 0)) and m.dilation in (1, (1, 1)) and not m.ceil_mode:
+                x = ops.max_pool2x2(x)          # 16-byte-vector channels-last kernel (ATen's NHWC pool otherwise)
+                i += 1
             else:
                 x = m(x)
                 i += 1

@@ -119,3 +119,45 @@ def test_conv3x3_autograd(shape):
     _close(y, yr, 4e-3, "y")
     _close(x.grad, xr.grad, 4e-3, "dx")
     _close(conv.weight.grad, wr.grad, 3e-4, "dW")
+
+
+@pytest.mark.parametrize("spec", [  # B, Cin, Cout, H, W, kernel, dilation, act
+    (2, 84, 128, 32, 32, 3, 1, None), (2, 86, 128, 24, 40, 3, 1, "leaky"), (1, 32, 2, 64, 64, 3, 1, None),
+    (2, 128, 128, 32, 32, 3, 2, "leaky"), (1, 128, 96, 40, 24, 3, 16, "leaky"), (2, 16, 1, 16, 16, 3, 1, None),
+    (2, 128, 96, 32, 32, 1, 1, None), (1, 96, 32, 24, 40, 1, 1, None), (1, 41, 32, 16, 16, 3, 4, "relu"),
+])
+def test_frozen_decoder_convs_on_the_implicit_gemm(spec):
+    """conv_bias_act on the shapes of the alignment decoders (reference models/modules.py:395-477): channel counts that
+    are not multiples of 8 (zero-padded), dilated 3x3 filters of the RefinementModule (padding = dilation through TMA's
+    out-of-bounds zero fill), 1x1 skip convolutions on the GEMM -- against conv2d in fp32 on the same bf16 operands."""
+    import torch.nn as nn
+    B, Ci, Co, H, W, k, dil, actname = spec
+    torch.manual_seed(Ci * Co + H + dil)
+    act = {"relu": nn.ReLU(), "leaky": nn.LeakyReLU(0.1), None: None}[actname]
+    x = torch.randn(B, Ci, H, W, device=DEV).bfloat16()
+    w = (torch.randn(Co, Ci, k, k, device=DEV) / (k * Ci ** 0.5))
+    b = torch.randn(Co, device=DEV)
+    pad = dil if k == 3 else 0
+    want = F.conv2d(x.float(), w.bfloat16().float(), b, padding=pad, dilation=dil)
+    if act is not None:
+        want = act(want)
+    timer = ops.KernelTimer()
+    ops.set_timer(timer)
+    try:
+        with torch.no_grad():
+            got = ops.conv_bias_act(x, w, b, 1, pad, dil, 1, act)
+    finally:
+        ops.set_timer(None)
+    names = {r[0] for r in timer.records}
+    assert names & {"conv3x3", "gemm_bf16"}, names          # the own kernel ran, not the library convolution
+    assert got.shape == want.shape and got.dtype == torch.bfloat16
+    _close(got, want, 6e-3, "frozen conv")
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 32, 48), (1, 128, 17, 31), (4, 8, 2, 2)])
+def test_maxpool2x2_channels_last(shape):
+    B, C, H, W = shape
+    x = torch.randn(B, C, H, W, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        got = ops.max_pool2x2(x)
+    assert torch.equal(got, F.max_pool2d(x, 2, 2))
