@@ -386,6 +386,17 @@ int rf_conv3x3_bf16(const void* x, const void* w, const float* bias, void* out, 
                     int out_f32, int act, float slope, int dilation, void* stream);
 int rf_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dw, int B, int H, int W, int Cin, int Cout, void* stream);
 
+/* ---- UncertaintyModule patch CNN (models/modules.py:534-561: the four "valid" 3x3 convolutions over the B*H*W
+ * single-channel s x s patches of the correlation volume, eval-mode BatchNorm folded, LeakyReLU(slope), 2x2 max-pool after
+ * conv_0 when s = 16) fused into one kernel, every intermediate in shared memory:
+ *   corr   : f32 [B, s*s, H, W] (the displacement planes as produced by the correlation layers), s = search_size in {9, 16}
+ *   params : rf_uncertainty_cnn_param_bytes() bytes, 16-byte aligned: f32 w0[9][32] b0[32] b1[32] b2[16] w3[6][9][16] b3[8],
+ *            bf16 w1[32][296] (k = tap*32 + cin, 288 used), bf16 w2[16][296]  (built by UncertaintyModule._fused_params)
+ *   out    : bf16 [B, H, W, 6]  (= predict_uncertainty's output, channels-last) */
+int rf_uncertainty_cnn_param_bytes(void);
+int rf_uncertainty_cnn_fwd(const float* corr, const void* params, void* out_bf16, int B, int H, int W, int search_size,
+                           float slope, void* stream);
+
 /* nn.MaxPool2d(2, 2) of VGG.forward (models/backbones/vgg.py:108-120) on a channels-last bf16 tensor:
  * x [B,H,W,C] -> y [B,H/2,W/2,C] (floor); C a multiple of 8. */
 int rf_maxpool2x2_nhwc_bf16(const void* x, void* y, int B, int H, int W, int C, void* stream);

@@ -263,9 +263,50 @@ class UncertaintyModule(nn.Module):
         self.pred_conv_1 = cbr(32, 16, 3)
         self.predict_uncertainty_final = nn.Conv2d(16, out_channels, 3, 1, 1, bias=True)
 
+    def _fused_params(self):
+        """Parameter block of ops.uncertainty_patch_cnn (layout: csrc/uncertainty_cnn.cu): the BN-folded filters of
+        conv_0 / conv_1 / conv_2 and predict_uncertainty, cached like the folded weights themselves (frozen module)."""
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters()) + tuple(
+            (b.data_ptr(), b._version) for b in self.buffers())
+        hit = getattr(self, '_rf_fused', None)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        with torch.no_grad():
+            w0, b0 = self.conv_0._fold()
+            w1, b1 = self.conv_1._fold()
+            w2, b2 = self.conv_2._fold()
+            w3, b3 = self.predict_uncertainty.weight.float(), self.predict_uncertainty.bias.float()
+            dev = w0.device
+
+            def tap_major(w):     # [n, cin, 3, 3] -> bf16 [n, 296]: k = tap * cin_count + cin, zero-padded
+                n = w.shape[0]
+                out = torch.zeros(n, 296, device=dev, dtype=torch.bfloat16)
+                out[:, :288] = w.permute(0, 2, 3, 1).reshape(n, 288)
+                return out
+
+            f32 = [w0.reshape(32, 9).t().contiguous(), b0, b1, b2, w3.permute(0, 2, 3, 1).reshape(6, 144).contiguous(),
+                   torch.cat((b3, b3.new_zeros(2)))]
+            parts = [t.contiguous().view(-1).view(torch.uint8) for t in f32]
+            parts += [tap_major(w1).view(-1).view(torch.uint8), tap_major(w2).view(-1).view(torch.uint8)]
+            block = torch.cat(parts).contiguous()
+        self._rf_fused = (key, block)
+        return block
+
+    def _fused_ok(self, corr):
+        cbrs = (self.conv_0, self.conv_1, self.conv_2)
+        return (ops.OWN_GEMM and corr.is_cuda and not torch.is_grad_enabled() and ops._bf16_autocast()
+                and all(not m.depthwise_separable and m.use_norm and isinstance(m.bn, nn.BatchNorm2d)
+                        and not m.bn.training and m.bn.track_running_stats and m.use_activation
+                        and isinstance(m.activation, nn.LeakyReLU) for m in cbrs)
+                and len({m.activation.negative_slope for m in cbrs}) == 1 and self.conv_0.conv.in_channels == 1)
+
     def forward(self, corr, feat, up_previous_uncertainty=None, up_previous_flow=None):
         b, _, h, w = corr.shape
         s = self.search_size
+        if self._fused_ok(corr):
+            # bf16 mode on the GPU: the four patch convolutions as ONE kernel, intermediates in shared memory
+            x = ops.uncertainty_patch_cnn(corr, self._fused_params(), s, self.conv_0.activation.negative_slope)
+            return self._tail(x, feat, up_previous_uncertainty, up_previous_flow)
         # channels-last view of the volume == [B*H*W, 1, s, s] patches; one transpose copy
         x = corr.permute(0, 2, 3, 1).reshape(b * h * w, 1, s, s)
         x = self.conv_0(x)
@@ -273,6 +314,9 @@ class UncertaintyModule(nn.Module):
             x = self.maxpool(x)
         x = self.predict_uncertainty(self.conv_2(self.conv_1(x)))
         x = x.reshape(b, h, w, -1).permute(0, 3, 1, 2)
+        return self._tail(x, feat, up_previous_uncertainty, up_previous_flow)
+
+    def _tail(self, x, feat, up_previous_uncertainty, up_previous_flow):
         if self.feed_in_previous:
             x = torch.cat((x, feat, up_previous_uncertainty, up_previous_flow), 1)
         else:

@@ -881,6 +881,21 @@ def max_pool2x2(x):
     return y.permute(0, 3, 1, 2)
 
 
+def uncertainty_patch_cnn(corr, params, search_size, slope=0.1):
+    """The per-pixel patch CNN of UncertaintyModule (reference models/modules.py:534-556) on the correlation volume
+    corr f32 [B, s*s, H, W] with the packed, BN-folded parameter block -> bf16 [B, 6, H, W] (channels-last storage)."""
+    require_cuda(corr, params)
+    corr = _f32c(corr)
+    B, P, H, W = corr.shape
+    assert P == search_size * search_size and params.dtype == torch.uint8 and params.is_contiguous()
+    out = torch.empty(B, H, W, 6, device=corr.device, dtype=torch.bfloat16)
+    flops = 2 * B * H * W * (49 * 32 * 9 * (4 if search_size == 16 else 1) + 25 * 32 * 288 + 9 * 16 * 288 + 6 * 144)
+    with torch.cuda.device(corr.device):
+        _run("rf_uncertainty_cnn_fwd", ptr(corr), ptr(params), ptr(out), B, H, W, int(search_size), float(slope), _stream(),
+             work=(4 * corr.numel() + 2 * out.numel(), flops), tag="uncertainty_cnn")
+    return out.permute(0, 3, 1, 2)
+
+
 def conv2d_frozen(x, conv):
     """A plain nn.Conv2d of a frozen stack (the prediction layers of the alignment decoders) through conv_bias_act."""
     if x.is_cuda and not torch.is_grad_enabled() and conv.padding_mode == 'zeros':
