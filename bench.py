@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-size", type=int, default=1024,
                     help="crop size of the bounded CPU sample (default: the benched 1024 -- ~23 s per 1-pair step on 16 cores)")
+    ap.add_argument("--workload", default="daformer", choices=["daformer", "hrda"],
+                    help="daformer = the headline configuration (BASELINE configs[2] at the metric's 1024x1024); hrda = "
+                         "BASELINE configs[3] (HRDA multi-resolution + Refign; eager: the detail-crop box changes per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-corr-sweep", action="store_true", help="skip the correlation-volume GB/s sweep (N=1 only)")
@@ -52,11 +55,18 @@ def parse():
     return ap.parse_args()
 
 
-def build_model(model_type, precision, device):
+def build_model(model_type, precision, device, workload="daformer"):
     import torch
     import refign_b200 as P
     dims = P.MixVisionTransformer.arch_settings[model_type]['embed_dims']
     torch.manual_seed(0)  # identical weights on every rank
+    hrda = {}
+    if workload == "hrda":
+        # BASELINE config 4 (configs/cityscapes_acdc/refign_hrda_star.yaml): half-resolution context view + one random
+        # full-resolution detail crop for the student, sliding-window detail crops for the EMA teacher, SegFormerHead
+        # scale attention, hr_loss_weight 0.1
+        hrda = dict(use_hrda=True, hrda_scale_attention=P.SegFormerHead(dims, [0, 1, 2, 3], 19, 'multiple_select'),
+                    hr_loss_weight=0.1)
     model = P.DomainAdaptationSegmentationModel(
         optimizer_init=OPT, lr_scheduler_init=SCH,
         backbone=P.MixVisionTransformer(model_type),
@@ -65,7 +75,7 @@ def build_model(model_type, precision, device):
         alignment_backbone=P.VGG('vgg16', out_indices=[2, 3, 4]),
         alignment_head=P.UAWarpCHead(in_index=[0, 1], input_transform='multiple_select', estimate_uncertainty=True),
         backbone_lr_factor=0.1, enable_fdist=True, use_refign=True, adapt_to_ref=False, gamma=0.25,
-        precision=precision)
+        precision=precision, **hrda)
     return model.to(device).train()
 
 
@@ -385,7 +395,10 @@ def main():
     torch.backends.cuda.matmul.allow_tf32 = True
     torch.backends.cudnn.allow_tf32 = True
 
-    model = build_model(args.model, args.precision, dev)
+    if args.workload == "hrda":     # not CUDA-graph-captured (host-side crop box per step); no CPU port of this configuration
+        args.no_graphs = True
+        args.no_cpu_baseline = True
+    model = build_model(args.model, args.precision, dev, args.workload)
     model.setup_runtime(process_group=group, world_size=world)
     batch = synth_batch(args.size, PAIRS_PER_GPU, 100 + rank, dev)
 
@@ -428,7 +441,8 @@ def main():
     ms_kpass = timed(ksteps, kstep)
     model.concurrent_branches = concurrent
     ops.set_timer(None)
-    kern = timer.summary()
+    pair_overhead_ms = ops.KernelTimer.calibrate(dev)
+    kern = timer.summary(pair_overhead_ms)
     launches = timer.launches // ksteps
     step0 = 2 + ksteps
     if not args.no_graphs:
@@ -504,7 +518,8 @@ def main():
                     "frac": ach / hbm, "traffic": None}
         roof.update({"peak_source": which, "avg_launch_us": per_ms * 1e3, "calls_per_step": d["calls"] / ksteps,
                      "share_of_step": d["ms"] / ksteps / ms_step,
-                     "timed_in": "eager per-kernel pass of %d step(s): CUDA events around every C-ABI call, side-stream branches off, launch queue pre-filled" % ksteps})
+                     "event_pair_overhead_us": pair_overhead_ms * 1e3, "avg_launch_us_raw": d["raw_ms"] / d["calls"] * 1e3,
+                     "timed_in": "eager per-kernel pass of %d step(s): CUDA events around every C-ABI call, side-stream branches off, launch queue pre-filled, the event-pair overhead measured on an empty launch subtracted per call" % ksteps})
     own = {k: {"calls_per_step": v["calls"] / ksteps, "ms_per_step": v["ms"] / ksteps,
                "GBps": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 and v["bytes"] else None,
                "TFLOPs": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 and v["flops"] else None}
@@ -547,7 +562,8 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.precision if args.precision != "fp32" else "f32", "data": "synthetic",
-            "config": {"workload": "%s_%dx%d_b%d" % (WORKLOAD, args.size, args.size, PAIRS_PER_GPU),
+            "config": {"workload": "%s_%dx%d_b%d" % (WORKLOAD if args.workload == "daformer" else "refign_hrda_mitb5_train_step",
+                                                     args.size, args.size, PAIRS_PER_GPU),
                        "model": args.model, "pairs_per_gpu": PAIRS_PER_GPU, "source_images_per_gpu": PAIRS_PER_GPU,
                        "global_batch_pairs": world * PAIRS_PER_GPU, "parallelism": "dp%d" % world,
                        "l2": "working set per step (>= 340 MB of parameters + activations) exceeds the 126 MB L2",

@@ -30,25 +30,30 @@ constexpr int GM_BM = 128, GM_BK = 64;
 constexpr int GM_THREADS = 352;   // 2 epilogue warpgroups (warps 0-7) + TMA-load warp (8) + MMA warp (9) + TMA-store warp (10)
 constexpr int GM_A_BYTES = GM_BM * GM_BK * 2;          // 16 KiB per stage
 
-template <int BN, int MODE>
+template <int BN, int MODE, bool CL2 = false>
 struct GmCfg {
-  static constexpr int B_BYTES = BN * GM_BK * 2;
+  // CTA pair (CL2, one cta_group::2 MMA over two SMs): every CTA stages its own 128 rows of A and HALF of the B tile
+  static constexpr int B_BYTES = BN * GM_BK * 2 / (CL2 ? 2 : 1);
   static constexpr int STAGE = GM_A_BYTES + B_BYTES;
   // Staging buffers per epilogue warpgroup ([128 rows x 128 B] TMA-store sources).  A TMA store takes ~1 500 cycles from
   // issue until its shared-memory source may be rewritten (timeline traces: 2 000 cycles per chunk with one buffer,
   // the epilogue of a K = 320 tile longer than its MMAs), so two buffers alternate and a chunk only waits for the store
   // before the previous one.  The long-K 256-wide convolution tiles keep the fourth operand stage instead (their
   // epilogue hides behind 144 k-blocks of MMAs).
-  static constexpr int EPI = (MODE == 1 && BN == 256) ? 1 : 2;
-#ifdef WS_TRACE
-  static constexpr int STAGES = BN == 256 ? 2 : (BN == 192 ? 3 : (BN == 128 ? 4 : 5));   // (the trace log takes 22 KiB of static smem)
-#else
-  static constexpr int STAGES = BN == 256 ? (EPI == 1 ? 4 : 3) : (BN == 192 ? 4 : (BN == 128 ? 5 : 6));
-#endif
+  static constexpr int EPI = (MODE == 1 && BN == 256 && !CL2) ? 1 : 2;
   static constexpr int ACC = 512 / BN;                 // accumulator buffers in TMEM (2 for BN = 192 / 256)
   static constexpr int STAGING = 2 * EPI * 16384;
   static constexpr int BIAS_BYTES = EPI * BN * 4;       // one bias slice per tile in flight
-  static constexpr int SMEM = STAGES * STAGE + STAGING + 1024 + 384 + BIAS_BYTES;   // + alignment slack, barrier block
+  static constexpr int FIXED = STAGING + 1024 + 384 + BIAS_BYTES;   // + alignment slack, barrier block
+#ifdef WS_TRACE
+  static constexpr int BUDGET = 232448 - 22528;        // (the trace log takes 22 KiB of static smem)
+#else
+  static constexpr int BUDGET = 232448;
+#endif
+  static constexpr int FIT = (BUDGET - FIXED) / STAGE;
+  static constexpr int STAGES = FIT > 8 ? 8 : FIT;
+  static constexpr int SMEM = STAGES * STAGE + FIXED;
+  static_assert(STAGES >= 2, "operand ring too small");
 };
 
 struct GmBars {
@@ -90,7 +95,7 @@ template <int BN, bool A_MN, bool B_MN, int MODE, bool CL2>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_out, const GmParams p) {
-  using Cfg = GmCfg<BN, MODE>;
+  using Cfg = GmCfg<BN, MODE, CL2>;
   WS_T_INIT();
   WS_T(0);
   extern __shared__ uint8_t smem_raw[];
@@ -105,12 +110,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       tma_prefetch_desc(&tm_b);
       tma_prefetch_desc(&tm_out);
       for (int s = 0; s < Cfg::STAGES; ++s) {
-        mbar_init(&bars->full[s], 1);
-        mbar_init(&bars->empty[s], CL2 ? 2 : 1);   // CTA pair: a stage is free when BOTH CTAs' MMAs have read it
+        mbar_init(&bars->full[s], 1);              // CTA pair: the leader's barrier collects both CTAs' loads
+        mbar_init(&bars->empty[s], 1);
       }
       for (int s = 0; s < Cfg::ACC; ++s) {
         mbar_init(&bars->acc_full[s], 1);
-        mbar_init(&bars->acc_empty[s], 8);
+        // CTA pair: the leader's MMAs also wait for ONE forwarded arrival per tile from the peer CTA (see the MMA warp)
+        mbar_init(&bars->acc_empty[s], (CL2 && cluster_ctarank() == 0) ? 9 : 8);
       }
       for (int s = 0; s < 4; ++s) {
         mbar_init(&bars->st_full[s], 4);
@@ -120,18 +126,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
     __syncwarp();
   }
-  if (warp == 9) tmem_alloc<512>(&bars->tmem_base);
+  if (warp == 9) {
+    if (CL2) tmem_alloc_2cta<512>(&bars->tmem_base); else tmem_alloc<512>(&bars->tmem_base);
+  }
   tc_fence_before();
   __syncthreads();
-  if (CL2) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast into this CTA
+  if (CL2) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem = uniform_u32(bars->tmem_base);
   WS_T(1);
 
-  // CTA pairs (CL2): the two CTAs of a cluster work on the m-tiles 2 mp and 2 mp + 1 of the SAME n-tile, each loads
-  // half of the shared B tile and multicasts it to both -- operand traffic per CTA and k-block drops from
-  // (128 + BN) to (128 + BN / 2) rows (these GEMMs are bound by the L2 -> SM operand path).  An m-tile beyond the
-  // tensor loads zeros and stores nothing (TMA fills / clips), so the pair never diverges.
+  // CTA pairs (CL2): the two CTAs of a cluster work on the m-tiles 2 mp and 2 mp + 1 of the SAME n-tile as ONE
+  // tcgen05.mma.cta_group::2 of M = 256: each CTA stages its own A tile and half of the B tile (the tensor core reads
+  // both halves), so the operand traffic per SM and k-block drops from (128 + BN) to (128 + BN / 2) rows -- these GEMMs
+  // are bound by the L2 -> SM operand path (~50 B/clk per SM measured).  The leader (rank 0) issues the MMAs and its
+  // commits arrive on both CTAs' barriers; each CTA's epilogue drains its own 128 accumulator rows.  An m-tile beyond
+  // the tensor loads zeros and stores nothing (TMA fills / clips), so the pair never diverges.
   const int rank = CL2 ? (int)cluster_ctarank() : 0;
   const int m_units = CL2 ? (p.m_tiles + 1) / 2 : p.m_tiles;
   const int tiles = p.taps * m_units * p.n_tiles;
@@ -154,38 +164,55 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         if (it >= Cfg::STAGES) mbar_wait(&bars->empty[st], ((it / Cfg::STAGES) - 1) & 1);
         uint8_t* stage = smem + st * Cfg::STAGE;
         if (elect_one()) {
-          mbar_expect_tx(&bars->full[st], Cfg::STAGE);
           uint8_t* sB = stage + GM_A_BYTES;
-          if (MODE == GM_GEMM) {
-            gm_load<A_MN>(stage, &tm_a, &bars->full[st], m0, kb * GM_BK, GM_BM);
-            if (!CL2) {
+          if (!CL2) {
+            mbar_expect_tx(&bars->full[st], Cfg::STAGE);
+            if (MODE == GM_GEMM) {
+              gm_load<A_MN>(stage, &tm_a, &bars->full[st], m0, kb * GM_BK, GM_BM);
               gm_load<B_MN>(sB, &tm_b, &bars->full[st], n0, kb * GM_BK, BN);
-            } else if (!B_MN) {     // this CTA's half of the rows, to both CTAs
-              tma_load_3d_mc(sB + rank * (BN / 2) * 128, &tm_b, &bars->full[st], kb * GM_BK, n0 + rank * (BN / 2), 0, 3);
-            } else {                // this CTA's half of the 64-column blocks
-              for (int blk = rank * (BN / 128); blk < (rank + 1) * (BN / 128); ++blk)
-                tma_load_3d_mc(sB + blk * 8192, &tm_b, &bars->full[st], n0 + blk * 64, kb * GM_BK, 0, 3);
-            }
-          } else if (MODE == GM_CONV) {
-            // k-block = (filter tap, 64 input channels): the activation box is shifted by the tap, rows / columns
-            // outside the image are zero-filled by TMA (= the convolution's zero padding)
-            const int ctap = kb / p.cin_blocks, cb = kb % p.cin_blocks;
-            tma_load_4d(stage, &tm_a, &bars->full[st], cb * 64, ctw * 16 + (ctap % 3 - 1) * p.dil, cth * 8 + (ctap / 3 - 1) * p.dil, cb_img);
-            if (!CL2) tma_load_3d(sB, &tm_b, &bars->full[st], cb * 64, ctap, n0);
-            else tma_load_3d_mc(sB + rank * (BN / 2) * 128, &tm_b, &bars->full[st], cb * 64, ctap, n0 + rank * (BN / 2), 3);
-          } else {
-            // weight gradient: k-block = 4 x 16 pixels of one image; A = dy (output channels m0.. as MN-major blocks),
-            // B = x shifted by the tap (input channels n0..)
-            const int kw = kb % p.tiles_w, kh = (kb / p.tiles_w) % p.tiles_h, kimg = kb / (p.tiles_w * p.tiles_h);
-            for (int blk = 0; blk < GM_BM / 64; ++blk)
-              tma_load_4d(stage + blk * 8192, &tm_a, &bars->full[st], m0 + blk * 64, kw * 16, kh * 4, kimg);
-            if (!CL2) {
+            } else if (MODE == GM_CONV) {
+              // k-block = (filter tap, 64 input channels): the activation box is shifted by the tap, rows / columns
+              // outside the image are zero-filled by TMA (= the convolution's zero padding)
+              const int ctap = kb / p.cin_blocks, cb = kb % p.cin_blocks;
+              tma_load_4d(stage, &tm_a, &bars->full[st], cb * 64, ctw * 16 + (ctap % 3 - 1) * p.dil, cth * 8 + (ctap / 3 - 1) * p.dil, cb_img);
+              tma_load_3d(sB, &tm_b, &bars->full[st], cb * 64, ctap, n0);
+            } else {
+              // weight gradient: k-block = 4 x 16 pixels of one image; A = dy (output channels m0.. as MN-major blocks),
+              // B = x shifted by the tap (input channels n0..)
+              const int kw = kb % p.tiles_w, kh = (kb / p.tiles_w) % p.tiles_h, kimg = kb / (p.tiles_w * p.tiles_h);
+              for (int blk = 0; blk < GM_BM / 64; ++blk)
+                tma_load_4d(stage + blk * 8192, &tm_a, &bars->full[st], m0 + blk * 64, kw * 16, kh * 4, kimg);
               for (int blk = 0; blk < BN / 64; ++blk)
                 tma_load_4d(sB + blk * 8192, &tm_b, &bars->full[st], n0 + blk * 64, kw * 16 + tap % 3 - 1, kh * 4 + tap / 3 - 1, kimg);
+            }
+          } else {
+            // both CTAs' loads complete on the LEADER's barrier, which the leader arms with the bytes of both (a remote
+            // arrive.expect_tx from the peer cost ~1 000 cycles per k-block in the timeline trace); the peer cannot run a
+            // phase ahead: its next load into this stage waits for the commit of the MMAs that consumed this one
+            const uint32_t fb = mapa_u32(smem_u32(&bars->full[st]), 0);
+            if (rank == 0) mbar_expect_tx(&bars->full[st], 2 * Cfg::STAGE);
+            const int nh = n0 + rank * (BN / 2);            // this CTA's half of the B tile
+            if (MODE == GM_GEMM) {
+              if (!A_MN) {
+                tma_load_3d_2cta(stage, &tm_a, fb, kb * GM_BK, m0, 0);
+              } else {
+                for (int blk = 0; blk < GM_BM / 64; ++blk) tma_load_3d_2cta(stage + blk * 8192, &tm_a, fb, m0 + blk * 64, kb * GM_BK, 0);
+              }
+              if (!B_MN) {
+                tma_load_3d_2cta(sB, &tm_b, fb, kb * GM_BK, nh, 0);
+              } else {
+                for (int blk = 0; blk < BN / 128; ++blk) tma_load_3d_2cta(sB + blk * 8192, &tm_b, fb, nh + blk * 64, kb * GM_BK, 0);
+              }
+            } else if (MODE == GM_CONV) {
+              const int ctap = kb / p.cin_blocks, cb = kb % p.cin_blocks;
+              tma_load_4d_2cta(stage, &tm_a, fb, cb * 64, ctw * 16 + (ctap % 3 - 1) * p.dil, cth * 8 + (ctap / 3 - 1) * p.dil, cb_img);
+              tma_load_3d_2cta(sB, &tm_b, fb, cb * 64, ctap, nh);
             } else {
-              for (int blk = rank * (BN / 128); blk < (rank + 1) * (BN / 128); ++blk)
-                tma_load_4d_mc(sB + blk * 8192, &tm_b, &bars->full[st], n0 + blk * 64, kw * 16 + tap % 3 - 1, kh * 4 + tap / 3 - 1,
-                               kimg, 3);
+              const int kw = kb % p.tiles_w, kh = (kb / p.tiles_w) % p.tiles_h, kimg = kb / (p.tiles_w * p.tiles_h);
+              for (int blk = 0; blk < GM_BM / 64; ++blk)
+                tma_load_4d_2cta(stage + blk * 8192, &tm_a, fb, m0 + blk * 64, kw * 16, kh * 4, kimg);
+              for (int blk = 0; blk < BN / 128; ++blk)
+                tma_load_4d_2cta(sB + blk * 8192, &tm_b, fb, nh + blk * 64, kw * 16 + tap % 3 - 1, kh * 4 + tap / 3 - 1, kimg);
             }
           }
         }
@@ -195,14 +222,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
   } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t IDESC = make_idesc(FMT_BF16, GM_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    constexpr uint32_t IDESC = make_idesc(FMT_BF16, CL2 ? 2 * GM_BM : GM_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
     constexpr uint64_t STEP = (uint64_t)(Cfg::STAGE >> 4);
     const uint32_t base = smem_u32(smem);
     const uint64_t dA0 = A_MN ? make_sdesc_sw128(base, 8192, 1024) : make_sdesc_sw128(base, 16, 1024);
     const uint64_t dB0 = B_MN ? make_sdesc_sw128(base + GM_A_BYTES, 8192, 1024) : make_sdesc_sw128(base + GM_A_BYTES, 16, 1024);
     constexpr uint64_t KA = A_MN ? 128 : 2, KB = B_MN ? 128 : 2;   // descriptor advance per 16-element k step
     int it = 0, local = 0;
-    for (long w = w_first; w < items; w += w_step, ++local) {
+    if (CL2 && rank != 0) {
+      // Peer CTA of a pair: no MMAs to issue.  This warp forwards "my epilogue has drained accumulator buffer b" to the
+      // leader, so the (slow: ~2 000 cycles with release semantics at cluster scope) remote arrival is not paid by the
+      // eight epilogue warps inside their tile loop.
+      for (long w = w_first; w < items; w += w_step, ++local) {
+        const int buf = local % Cfg::ACC;
+        mbar_wait(&bars->acc_empty[buf], (local / Cfg::ACC) & 1);
+        if (elect_one()) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->acc_empty[buf]), 0));
+        __syncwarp();
+      }
+    }
+    for (long w = (CL2 && rank != 0) ? items : w_first; w < items; w += w_step, ++local) {   // pair: the leader issues
       const int split = (int)(w % p.splits);
       const int kb0 = split * p.kb_per_split, kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
       const int buf = local % Cfg::ACC;
@@ -217,10 +255,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const uint64_t dA = dA0 + st * STEP, dB = dB0 + st * STEP;
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < GM_BK / 16; ++k)
-            mma_f16_ss(d, dA + k * KA, dB + k * KB, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
-          if (CL2) tc_commit_mc(&bars->empty[st], 3); else tc_commit(&bars->empty[st]);
-          if (kb == kb1 - 1) tc_commit(&bars->acc_full[buf]);
+          for (int k = 0; k < GM_BK / 16; ++k) {
+            if (CL2) mma_f16_ss_2cta(d, dA + k * KA, dB + k * KB, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+            else mma_f16_ss(d, dA + k * KA, dB + k * KB, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          if (CL2) tc_commit_2cta(&bars->empty[st], 3); else tc_commit(&bars->empty[st]);
+          if (kb == kb1 - 1) {
+            if (CL2) tc_commit_2cta(&bars->acc_full[buf], 3); else tc_commit(&bars->acc_full[buf]);
+          }
         }
         __syncwarp();
         WS_T(21);
@@ -287,38 +329,86 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const uint32_t sw = (uint32_t)(r & 7);
     uint8_t* const sbuf0 = staging + wg * (Cfg::EPI * 16384);
     int nstore = 0;                      // chunks this warpgroup has handed over so far (selects the staging buffer)
-    float* const sbias0 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 384);   // EPI slices of BN floats
-    auto bias_at = [&](long ww) -> float {   // this thread's element of the bias slice of work item ww (0 beyond N / the end)
-      if (ww >= items || tid >= BN) return 0.f;
-      const int nn = (int)((ww / p.splits) % p.n_tiles) * BN + tid;
+    // Bias: EPI slices of BN floats behind the barrier block.  Each warpgroup stages and reads only the columns of ITS
+    // chunks (one element per thread), so the slice hand-over is a 128-thread named barrier per warpgroup and the two
+    // warpgroups never wait for each other.
+    float* const sbias0 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 384);
+    const int my_col = ((r / cpc) * 2 + wg) * cpc + r % cpc;       // the tile column whose bias this thread stages
+    auto bias_at = [&](long ww) -> float {   // (0 beyond N / the end of the work list)
+      if (ww >= items || my_col >= BN) return 0.f;
+      const int nn = (int)((ww / p.splits) % p.n_tiles) * BN + my_col;
       return nn < p.N ? __ldg(p.bias + nn) : 0.f;
     };
+    auto wg_sync = [&]() {
+      if (wg == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+    };
+    // one 32-column half of a bf16 chunk: + bias, activation, pack -> 16 words
+    auto convert_half = [&](const uint32_t (&v)[32], const float* sb, uint32_t* pkh) {
+#pragma unroll
+      for (int e = 0; e < 16; e += 2) {
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) bv = *reinterpret_cast<const float4*>(sb + 2 * e);
+        float4 x = make_float4(__uint_as_float(v[2 * e]) + bv.x, __uint_as_float(v[2 * e + 1]) + bv.y,
+                               __uint_as_float(v[2 * e + 2]) + bv.z, __uint_as_float(v[2 * e + 3]) + bv.w);
+        if (MODE == GM_CONV && p.act) {   // fused ReLU / LeakyReLU of the frozen conv stacks
+          const float ng = p.act == 1 ? 0.f : p.slope;
+          x.x = x.x > 0.f ? x.x : x.x * ng;
+          x.y = x.y > 0.f ? x.y : x.y * ng;
+          x.z = x.z > 0.f ? x.z : x.z * ng;
+          x.w = x.w > 0.f ? x.w : x.w * ng;
+        }
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y);
+        const __nv_bfloat162 h1 = __floats2bfloat162_rn(x.z, x.w);
+        pkh[e] = *reinterpret_cast<const uint32_t*>(&h0);
+        pkh[e + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+      }
+    };
     float bias_next = 0.f;
-    if (p.bias && Cfg::EPI == 2 && tid < BN) sbias0[tid] = bias_at(w_first);
+    if (p.bias && Cfg::EPI == 2 && my_col < BN) sbias0[my_col] = bias_at(w_first);
     int local = 0;
     for (long w = w_first; w < items; w += w_step, ++local) {
       const int buf = local % Cfg::ACC;
-      const float* sbias = sbias0 + (Cfg::EPI == 2 ? (local & 1) * BN : 0);
+      float* const sbias = sbias0 + (Cfg::EPI == 2 ? (local & 1) * BN : 0);
       if (p.bias) {   // this tile's bias slice, zero beyond N, read back as broadcast shared-memory vectors
         if (Cfg::EPI == 2) {
           // slice `local` was written during the previous tile (or before the loop); the next tile's element is
           // fetched now and stored when this tile is done, so no global-load latency sits in front of a tile
-          asm volatile("bar.sync 3, 256;" ::: "memory");
+          wg_sync();
           bias_next = bias_at(w + w_step);
         } else {
-          asm volatile("bar.sync 3, 256;" ::: "memory");      // both warpgroups are done with the previous tile's slice
-          if (tid < BN) sbias0[tid] = bias_at(w);
-          asm volatile("bar.sync 3, 256;" ::: "memory");
+          wg_sync();                                          // the warpgroup is done with the previous tile's slice
+          if (my_col < BN) sbias[my_col] = bias_at(w);
+          wg_sync();
         }
       }
       mbar_wait(&bars->acc_full[buf], (local / Cfg::ACC) & 1);
       tc_fence_after();
       WS_T(10);
       const uint32_t t = tmem + lane_off + buf * BN;
+      // hand one finished chunk (32 packed words per thread = one 128-byte row) to the store warp
+      auto hand_over = [&](const uint32_t (&pk)[32]) {
+        WS_T(13);
+        const int b = Cfg::EPI == 2 ? (nstore & 1) : 0, use = nstore / Cfg::EPI;
+        ++nstore;
+        if (use > 0) mbar_wait(&bars->st_free[wg * 2 + b], (use - 1) & 1);   // the store that last used this buffer has read it
+        WS_T(14);
+        uint4* srow = reinterpret_cast<uint4*>(sbuf0 + b * 16384 + r * 128);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) srow[q ^ sw] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&bars->st_full[wg * 2 + b]);
+        WS_T(15);
+      };
+      auto release_acc = [&]() {   // this warpgroup's share of the accumulator is in registers: hand the TMEM buffer back
+        tc_fence_before();
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&bars->acc_empty[buf]);
+      };
+      if (p.out_f32) {
 #pragma unroll 1
-      for (int c = wg; c < nchunk; c += 2) {
-        uint32_t pk[32];
-        if (p.out_f32) {
+        for (int c = wg; c < nchunk; c += 2) {
+          uint32_t pk[32];
           tmem_ld32(t + c * 32, pk);
           tc_wait_ld();
           if (p.bias) {
@@ -338,65 +428,42 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               pk[e] = __float_as_uint(x > 0.f ? x : (p.act == 1 ? 0.f : x * p.slope));
             }
           }
-        } else {
-          uint32_t v[2][32];
-          tmem_ld32(t + c * 64, v[0]);
-          tmem_ld32(t + c * 64 + 32, v[1]);
+          if (c + 2 >= nchunk) release_acc();
+          hand_over(pk);
+        }
+      } else {
+        // bf16 output: 64-column chunks read as two 32-column halves, software-pipelined -- the TMEM load of the next
+        // half (also the first half of the warpgroup's NEXT chunk) is in flight while this one is converted and stored
+        uint32_t va[32], vb[32];
+        if (wg < nchunk) tmem_ld32(t + wg * 64, va);
+#pragma unroll 1
+        for (int c = wg; c < nchunk; c += 2) {
+          uint32_t pk[32];
           tc_wait_ld();
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-#pragma unroll
-            for (int e = 0; e < 16; e += 2) {
-              float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (p.bias) bv = *reinterpret_cast<const float4*>(sbias + c * 64 + h * 32 + 2 * e);
-              float4 x = make_float4(__uint_as_float(v[h][2 * e]) + bv.x, __uint_as_float(v[h][2 * e + 1]) + bv.y,
-                                     __uint_as_float(v[h][2 * e + 2]) + bv.z, __uint_as_float(v[h][2 * e + 3]) + bv.w);
-              if (MODE == GM_CONV && p.act) {   // fused ReLU / LeakyReLU of the frozen conv stacks
-                const float ng = p.act == 1 ? 0.f : p.slope;
-                x.x = x.x > 0.f ? x.x : x.x * ng;
-                x.y = x.y > 0.f ? x.y : x.y * ng;
-                x.z = x.z > 0.f ? x.z : x.z * ng;
-                x.w = x.w > 0.f ? x.w : x.w * ng;
-              }
-              const __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y);
-              const __nv_bfloat162 h1 = __floats2bfloat162_rn(x.z, x.w);
-              pk[h * 16 + e] = *reinterpret_cast<const uint32_t*>(&h0);
-              pk[h * 16 + e + 1] = *reinterpret_cast<const uint32_t*>(&h1);
-            }
-          }
+          tmem_ld32(t + c * 64 + 32, vb);
+          convert_half(va, sbias + c * 64, pk);
+          tc_wait_ld();
+          if (c + 2 < nchunk) tmem_ld32(t + (c + 2) * 64, va); else release_acc();
+          convert_half(vb, sbias + c * 64 + 32, pk + 16);
+          hand_over(pk);
         }
-        if (c + 2 >= nchunk) {   // this warpgroup's share of the accumulator is in registers: hand the TMEM buffer back
-          tc_fence_before();
-          __syncwarp();
-          if ((tid & 31) == 0) mbar_arrive(&bars->acc_empty[buf]);
-        }
-        WS_T(13);
-        const int b = Cfg::EPI == 2 ? (nstore & 1) : 0, use = nstore / Cfg::EPI;
-        ++nstore;
-        if (use > 0) mbar_wait(&bars->st_free[wg * 2 + b], (use - 1) & 1);   // the store that last used this buffer has read it
-        WS_T(14);
-        uint4* srow = reinterpret_cast<uint4*>(sbuf0 + b * 16384 + r * 128);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) srow[q ^ sw] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-        fence_proxy_async();
-        __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(&bars->st_full[wg * 2 + b]);
-        WS_T(15);
       }
       if (nchunk == 1 && wg == 1) {   // BN = 64 bf16: a single chunk, warpgroup 1 only releases the accumulator
         tc_fence_before();
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(&bars->acc_empty[buf]);
       }
-      if (p.bias && Cfg::EPI == 2 && tid < BN) sbias0[((local + 1) & 1) * BN + tid] = bias_next;
+      if (p.bias && Cfg::EPI == 2 && my_col < BN) sbias0[((local + 1) & 1) * BN + my_col] = bias_next;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (CL2) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it / arrive on its barriers
+  if (CL2) cluster_sync_all();   // no CTA leaves while the pair's MMAs may still read its smem / arrive on its barriers
   WS_T(2);
   WS_T_FLUSH();
-  if (warp == 9) tmem_dealloc<512>(tmem);
+  if (warp == 9) {
+    if (CL2) tmem_dealloc_2cta<512>(tmem); else tmem_dealloc<512>(tmem);
+  }
 }
 
 // CTA pairs need a B tile that splits in two halves of whole swizzle groups / 64-column blocks
@@ -404,7 +471,7 @@ constexpr bool gm_pairable(int BN, bool B_MN) { return B_MN ? (BN % 128 == 0) : 
 
 template <int BN, bool A_MN, bool B_MN, int MODE, bool CL2>
 static int gemm_launch_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, GmParams p, cudaStream_t st) {
-  using Cfg = GmCfg<BN, MODE>;
+  using Cfg = GmCfg<BN, MODE, CL2>;
   static bool attr = false;
   auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, MODE, CL2>;
   if (!attr) {
@@ -432,7 +499,12 @@ static int gemm_launch_impl(const CUtensorMap& ta, const CUtensorMap& tb, const 
   return RF_OK;
 }
 
-static bool gm_use_pairs() {   // opt-in (RF_GEMM_PAIRS=1): measured neutral in isolation, -1.6 % on the train step
+// CTA pairs (one tcgen05.mma.cta_group::2 of M = 256 over two SMs, each CTA staging half of the B tile) are opt-in
+// (RF_GEMM_PAIRS=1).  Measured on the 16 MiT / DAFormer layer shapes in CUDA-graph replay: 154 / 149 / 154 us (forward /
+// dgrad / wgrad totals) against 152 / 148 / 153 us for single CTAs.  The pair's main loop IS faster (613 cycles per
+// 64-wide k-block of a 256 x 256 tile against ~870: the operand ingest per SM is halved), but at K <= 512 both variants
+// are bound by the epilogue (~4 800 cycles per 128 x 256 tile per CTA in the timeline traces), so the totals do not move.
+static bool gm_use_pairs() {
   static const bool on = [] { const char* e = getenv("RF_GEMM_PAIRS"); return e && e[0] == '1'; }();
   return on;
 }
