@@ -442,6 +442,12 @@ def main():
     model.concurrent_branches = concurrent
     ops.set_timer(None)
     pair_overhead_ms = ops.KernelTimer.calibrate(dev)
+    if os.environ.get("RF_BENCH_DEBUG_RECORDS") and rank == 0:     # the longest single launches of the pass, to stderr
+        torch.cuda.synchronize()
+        recs = sorted(((e0.elapsed_time(e1), name, i) for i, (name, e0, e1, _) in enumerate(timer.records)), reverse=True)
+        for ms_r, name, i in recs[:25]:
+            prev = timer.records[i - 1][0] if i else "-"
+            print("[records] %8.3f ms  #%d %s (after %s)" % (ms_r, i, name, prev), file=sys.stderr)
     kern = timer.summary(pair_overhead_ms)
     launches = timer.launches // ksteps
     step0 = 2 + ksteps

@@ -126,19 +126,22 @@ class Block(nn.Module):
         keep = 1.0 - dp.drop_prob
         return torch.empty(x.shape[0], dtype=torch.float32, device=x.device).bernoulli_(keep) / keep
 
-    def forward(self, x, H, W, carry=None):
+    def forward(self, x, H, W, carry=None, path_scales=None):
         """x: residual stream [B,N,C]; ``carry`` = (branch, scale) of the previous block's still
         un-added MLP branch.  The residual adds are fused into the LayerNorm that follows them
         (refign_b200.ops.add_layer_norm), so this returns (x, carry) with the last add pending:
-            x = x + dp(attn(norm1(x))); x = x + dp(mlp(norm2(x)))          (reference :203-207)"""
+            x = x + dp(attn(norm1(x))); x = x + dp(mlp(norm2(x)))          (reference :203-207)
+        ``path_scales``: the two per-sample drop-path factors of this block, pre-drawn for the whole backbone in one
+        launch by MixVisionTransformer.forward_features (else drawn here, two small launches per branch)."""
         if carry is None:
             h = ops.layer_norm(x, self.norm1)
         else:
             x, h = ops.add_layer_norm(x, carry[0], carry[1], self.norm1)
         a = self.attn(h, H, W)
-        x, h = ops.add_layer_norm(x, a, self._path_scale(x), self.norm2)
+        s_attn, s_mlp = path_scales if path_scales is not None else (self._path_scale(x), self._path_scale(x))
+        x, h = ops.add_layer_norm(x, a, s_attn, self.norm2)
         m = self.mlp(h, H, W)
-        return x, (m, self._path_scale(x))
+        return x, (m, s_mlp)
 
 
 class OverlapPatchEmbed(nn.Module):
@@ -248,14 +251,39 @@ class MixVisionTransformer(nn.Module):
         self.patch_embed1.requires_grad = False
 
     # ---- forward ----------------------------------------------------------------------------------
+    def _draw_path_scales(self, B, device):
+        """All drop-path factors of one forward, mask / keep_prob per (block, branch, sample), as ONE [2 * blocks, B]
+        tensor drawn with three launches (the per-branch draw of reference models/modules.py:587-596 is two small launches
+        x 104 branches x three training forwards per step).  None when nothing is dropped."""
+        if not self.training:
+            return None
+        probs = []
+        for s in range(4):
+            for blk in getattr(self, 'block%d' % (s + 1)):
+                dp = blk.drop_path
+                probs.append(float(dp.drop_prob) if isinstance(dp, DropPath) and dp.drop_prob and dp.training else 0.0)
+        if not any(probs):
+            return None
+        key = (tuple(probs), str(device))
+        cached = getattr(self, '_rf_keep', None)
+        if cached is None or cached[0] != key:
+            keep = torch.tensor([1.0 - p for p in probs for _ in (0, 1)], dtype=torch.float32, device=device).unsqueeze(1)
+            cached = (key, keep)
+            self._rf_keep = cached
+        keep = cached[1]
+        return (torch.rand(keep.shape[0], B, device=device) < keep).to(torch.float32) / keep
+
     def forward_features(self, x):
         outs = []
         B = x.shape[0]
+        scales = self._draw_path_scales(B, x.device) if x.is_cuda else None
+        bi = 0
         for s in range(4):
             x, H, W = getattr(self, 'patch_embed%d' % (s + 1))(x)
             carry = None
             for blk in getattr(self, 'block%d' % (s + 1)):
-                x, carry = blk(x, H, W, carry)
+                x, carry = blk(x, H, W, carry, None if scales is None else (scales[2 * bi], scales[2 * bi + 1]))
+                bi += 1
             norm = getattr(self, 'norm%d' % (s + 1))
             # stage outputs keep the residual stream's dtype (fp32, like LayerNorm under the reference's AMP):
             # they feed the feature-distance loss as well as the decode head
