@@ -23,6 +23,13 @@
 #include "rf_common.cuh"
 
 namespace rf {
+// local_corr_tc.cu
+int local_corr_tc_launch(const float* in1, const float* in2, float* out, float* norm_out, int B, int C, int H, int W, bool fuse,
+                         cudaStream_t st);
+bool local_corr_tc_ok(int C, int H, int W);
+}  // namespace rf
+
+namespace rf {
 
 // ----------------------------------------------------------------------------
 // tiled forward
@@ -688,6 +695,12 @@ extern "C" int rf_local_corr_fwd(const float* in1, const float* in2, float* out,
   const bool unit = kH == 1 && kW == 1 && sH == 1 && sW == 1 && padH == 0 && padW == 0 && dpH == 1 && dpW == 1;
   RF_REQUIRE(!fuse_relu_l2norm || unit, "rf_local_corr_fwd: fused relu+l2norm needs kernel 1, stride 1, pad 0, dilation_patch 1");
   const bool aligned = (W % 4 == 0) && (((uintptr_t)in1 | (uintptr_t)in2 | (uintptr_t)out | (uintptr_t)norm_out) % 16 == 0);
+  if (unit && aligned && pH == 9 && pW == 9 && local_corr_tc_ok(C, H, W)) {
+    // tensor-core banded GEMM (local_corr_tc.cu; bf16 hi/lo split, <= 2e-5 abs on unit-norm features).
+    // RF_LOCAL_CORR_TC=0 keeps the exact-fp32 FFMA tiles (A/B switch, read per call).
+    const char* e = getenv("RF_LOCAL_CORR_TC");
+    if (!(e && e[0] == '0')) return local_corr_tc_launch(in1, in2, out, norm_out, B, C, H, W, fuse_relu_l2norm != 0, st);
+  }
   if (unit && aligned && pH == pW && (pH == 3 || pH == 5 || pH == 7 || pH == 9)) {
     switch (pH) {
       case 3: return launch_tiled<3>(in1, in2, out, norm_out, B, C, H, W, fuse_relu_l2norm != 0, st);

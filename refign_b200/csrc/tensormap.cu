@@ -48,7 +48,9 @@ int make_tmap_nd(CUtensorMap* out, CUtensorMapDataType dt, int elem_bytes, const
   if (enc == nullptr) return RF_ECUDA;
   RF_REQUIRE(rank >= 2 && rank <= 5, "tensor map: rank must be 2..5");
   RF_REQUIRE(((uintptr_t)base & 15) == 0, "tensor map: base address must be 16-byte aligned");
-  RF_REQUIRE((uint64_t)box[0] * elem_bytes <= 128, "tensor map: inner box exceeds the 128-byte swizzle span");
+  RF_REQUIRE(swizzle == CU_TENSOR_MAP_SWIZZLE_NONE || (uint64_t)box[0] * elem_bytes <= 128,
+             "tensor map: inner box exceeds the 128-byte swizzle span");
+  RF_REQUIRE(((uint64_t)box[0] * elem_bytes) % 16 == 0, "tensor map: inner box must be a multiple of 16 bytes");
   cuuint64_t d[5], st[4];
   cuuint32_t b[5], es[5];
   for (int i = 0; i < rank; ++i) {

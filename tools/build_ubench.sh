@@ -10,3 +10,5 @@ nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo --expt-rel
   tools/trace_attn_fwd.cu refign_b200/csrc/tensormap.cu -o tools/_bin/trace_attn_fwd
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo --expt-relaxed-constexpr -ccbin /usr/bin/g++ \
   tools/trace_gemm.cu refign_b200/csrc/tensormap.cu -o tools/_bin/trace_gemm
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo --expt-relaxed-constexpr -ccbin /usr/bin/g++ \
+  tools/trace_local_corr.cu refign_b200/csrc/tensormap.cu -o tools/_bin/trace_local_corr
