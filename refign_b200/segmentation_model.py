@@ -150,7 +150,9 @@ class DomainAdaptationSegmentationModel(_Base):
         self.concurrent_branches = True       # teacher / alignment branches on side streams (see _fork_target_branches)
         self.fused_loss = True                # bilinear up-sampling fused into the cross-entropy (ops.upsample_cross_entropy)
         self.hrda_device_crop = False         # HRDA detail-crop origin in a device tensor (hrda.DeviceBox): graph-capturable
-        self._hrda_origin = None
+        self._hrda_origin = None               # [slot tensors] (see _draw_device_box)
+        self._hrda_slot_i = 0
+        self._hrda_prefilled = False
         self._side_streams = None
         self.load_weights(pretrained)
 
@@ -270,6 +272,8 @@ class DomainAdaptationSegmentationModel(_Base):
         target + reference, align, warp, refine.  Returns what the DACS mix needs."""
         opt.zero_grad()
         self.update_momentum_encoder()
+        if not self._hrda_prefilled:
+            self._hrda_slot_i = 0
         side = None
         if (self.concurrent_branches and batch['image_src'].is_cuda and self.use_refign and self.use_align
                 and not self.adapt_to_ref and self.alignment_head is not None):
@@ -393,17 +397,48 @@ class DomainAdaptationSegmentationModel(_Base):
                                        random_crop=self.head.training)
 
     def _draw_device_box(self, x):
-        """``hrda_device_crop``: the same host draws as ``hrda.random_detail_box``, copied into a persistent device
-        tensor (one slot per student forward of the step would be needed under CUDA graphs; eager use overwrites)."""
+        """``hrda_device_crop``: the same host draws as ``hrda.random_detail_box``, held in persistent device tensors --
+        one slot per student forward of a step (source, mixed).  Eager: the draw is copied into the next slot here.
+        Under CUDA graphs the slots are filled by ``_fill_hrda_slots`` BEFORE the graphs are replayed and this only
+        hands out the slot (nothing host-side may happen inside a captured region)."""
         H, W = x.shape[-2:]
         os2 = 2 * self.hrda_output_stride
         if not self.hrda_device_crop or H % (2 * os2) or W % (2 * os2):
             return None
+        slots = self._hrda_slots(x.device)
+        i = self._hrda_slot_i % len(slots)
+        self._hrda_slot_i += 1
+        if not self._hrda_prefilled:
+            y1, _, x1, _ = hrda.random_detail_box(H, W, H // 2, W // 2, float(os2))
+            slots[i].copy_(torch.tensor([y1, x1], dtype=torch.long), non_blocking=True)
+        return hrda.DeviceBox(slots[i], H // 2, W // 2)
+
+    def _hrda_slots(self, device):
+        if self._hrda_origin is None or self._hrda_origin[0].device != device:
+            self._hrda_origin = [torch.zeros(2, dtype=torch.long, device=device) for _ in range(2)]
+            # ring of pinned staging buffers + "copy done" events: the host may run several replayed steps ahead
+            pin = device.type == 'cuda'
+            self._hrda_ring = [(torch.zeros(2, 2, dtype=torch.long).pin_memory() if pin else torch.zeros(2, 2, dtype=torch.long),
+                                torch.cuda.Event() if pin else None) for _ in range(8)]
+            self._hrda_ring_i = 0
+        return self._hrda_origin
+
+    def _fill_hrda_slot(self, i, H, W, device):
+        """Draw one detail-crop origin on the host -- slot 0 (source forward) before graph A, slot 1 (mixed forward)
+        after the DACS draws and before graph B: the same draws in the same order of Python's ``random`` stream as the
+        eager step -- and copy it into the slot tensor the captured graph reads."""
+        slots = self._hrda_slots(device)
+        os2 = 2 * self.hrda_output_stride
+        host, ev = self._hrda_ring[self._hrda_ring_i % len(self._hrda_ring)]
+        self._hrda_ring_i += 1
+        if ev is not None:
+            ev.synchronize()                  # (no-op unless the host is several steps ahead of the device)
         y1, _, x1, _ = hrda.random_detail_box(H, W, H // 2, W // 2, float(os2))
-        if self._hrda_origin is None or self._hrda_origin.device != x.device:
-            self._hrda_origin = torch.zeros(2, dtype=torch.long, device=x.device)
-        self._hrda_origin.copy_(torch.tensor([y1, x1], dtype=torch.long), non_blocking=True)
-        return hrda.DeviceBox(self._hrda_origin.clone(), H // 2, W // 2)
+        host[0, 0], host[0, 1] = y1, x1
+        slots[i].copy_(host[0], non_blocking=True)
+        if ev is not None:
+            ev.record()
+        self._hrda_slot_i = i
 
     def _teacher_forward(self, x):
         if not self.use_hrda:
@@ -483,7 +518,11 @@ class DomainAdaptationSegmentationModel(_Base):
         Requires the flat-buffer runtime, static shapes and ``adapt_to_ref=False``."""
         assert self._rt is not None, "call setup_runtime() first"
         assert not self.adapt_to_ref, "the adapt_to_ref coin changes the control flow per step"
-        assert not self.use_hrda, "HRDA draws a new detail-crop box (host-side slicing offsets) every step"
+        if self.use_hrda:
+            # the detail-crop origin must live on the device (hrda.DeviceBox): the captured graphs read it from two
+            # slot tensors that the host refills before every replay
+            self.hrda_device_crop = True
+            self._hrda_prefilled = True
         self._rt['opt'].enable_device_hyper()
         self._graphs = {'n': 0, 'warmup': int(warmup), 'a': None, 'b': None, 'batch': None, 'mixed': None,
                         'out_a': None}
@@ -496,6 +535,11 @@ class DomainAdaptationSegmentationModel(_Base):
         for k, v in batch.items():
             G['batch'][k].copy_(v, non_blocking=True)
         sb = G['batch']
+        if self.use_hrda:
+            H, W = sb['image_src'].shape[-2:]
+            assert H % (4 * self.hrda_output_stride) == 0 and W % (4 * self.hrda_output_stride) == 0, \
+                "graphed HRDA needs image sides that are multiples of 4 x the output stride"
+            self._fill_hrda_slot(0, H, W, sb['image_src'].device)
         # step-dependent scalars (lr, Adam bias corrections, EMA momentum) -> device block read by the kernels
         opt.upload_hyper(runtime.ema_momentum(self.global_step, self.ema_momentum))
 
@@ -507,6 +551,8 @@ class DomainAdaptationSegmentationModel(_Base):
             else:
                 for dst, src in zip(G['mixed'], mixed):
                     dst.copy_(src)
+            if self.use_hrda:
+                self._fill_hrda_slot(1, sb['image_src'].shape[-2], sb['image_src'].shape[-1], sb['image_src'].device)
             return G['mixed']
 
         if G['n'] < G['warmup']:

@@ -90,3 +90,54 @@ def test_hrda_eval_forward_and_slide_inference_gpu():
             want = cpu_model(x)
         got = gpu_model(x.to(DEV))
         assert float((got.cpu() - want).abs().max()) <= 1e-3 * max(1.0, float(want.abs().max()))
+
+
+def _hrda_batch(S):
+    h = S // 2
+    g = torch.Generator().manual_seed(11)
+    batch = {'image_src': torch.randn(2, 3, S, S, generator=g), 'semantic_src': torch.randint(0, 19, (2, S, S), generator=g),
+             'image_trg': torch.randn(2, 3, S, S, generator=g)}
+    batch['image_ref'] = batch['image_trg'].roll((2, -3), (2, 3)) + 0.05 * torch.randn(2, 3, S, S, generator=g)
+    batch['semantic_src'][:, :h, :h] = 6
+    batch['semantic_src'][:, :h, h:] = 12
+    batch['semantic_src'][:, :4, :4] = 255
+    return {k: v.to(DEV) for k, v in batch.items()}
+
+
+def test_hrda_device_box_and_graph_replay_match_the_slicing_path(monkeypatch):
+    """The graph-capturable HRDA step: detail-crop origins in device slot tensors (hrda.DeviceBox: index_select /
+    index_copy instead of host-int slicing) must give the slicing path's step on the GPU -- eager, and replayed as CUDA
+    graphs with the host refilling the slots before every replay (same seeded draws in the same order).  Three steps
+    each (1 warm-up + capture + replay for the graphed run); losses to 1e-5 relative, parameters after three AdamW steps
+    to 5e-4 of their scale (index_copy / index_select change the summation order of a few gradients; AdamW divides by
+    sqrt(v) + eps, which amplifies last-bit differences of near-zero gradients)."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    monkeypatch.setattr(ps, 'get_class_masks', lambda labels: [((lab % 2) == 0).long().unsqueeze(0) for lab in labels])
+    base = _model()
+    batch = _hrda_batch(128)
+    runs = {}
+    for mode in ("slice", "device", "graph"):
+        m = copy.deepcopy(base).to(DEV)
+        m.concurrent_branches = False
+        m.setup_runtime()
+        if mode == "device":
+            m.hrda_device_crop = True
+        if mode == "graph":
+            m.enable_cuda_graphs(warmup=1)
+        random.seed(5)
+        torch.manual_seed(7)
+        losses = []
+        for step in range(3):
+            m.training_step(batch, step)
+            losses.append({k: float(v) for k, v in m._logged.items() if k.startswith('train_loss')})
+        torch.cuda.synchronize()
+        runs[mode] = (losses, {n: p.detach().clone() for n, p in m.named_parameters()})
+    ref_losses, ref_params = runs["slice"]
+    for mode in ("device", "graph"):
+        losses, params = runs[mode]
+        for step in range(3):
+            for k, v in ref_losses[step].items():
+                assert abs(losses[step][k] - v) <= 1e-5 * max(1.0, abs(v)), (mode, step, k, losses[step][k], v)
+        worst = max((float((params[n] - p).abs().max()) / (float(p.abs().max()) + 1e-3), n) for n, p in ref_params.items())
+        assert worst[0] < 5e-4, (mode, worst)
