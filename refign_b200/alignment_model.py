@@ -43,6 +43,13 @@ class AlignmentModel(_Base):
         ckpt = torch.load(resolve_checkpoint(pretrain_path), map_location='cpu')
         self.load_state_dict(ckpt['state_dict'] if 'state_dict' in ckpt else ckpt, strict=True)
 
+    def configure_optimizers(self):
+        """reference alignment_model.py:192-198: one optimizer over the trainable parameters + a per-step scheduler
+        (the entry point Lightning's ``fit`` calls; the stand-alone trainer of refign_b200/cli.py builds the same pair)."""
+        optimizer = _instantiate([p for p in self.parameters() if p.requires_grad], self.optimizer_init)
+        lr_scheduler = _instantiate(optimizer, self.lr_scheduler_init)
+        return [optimizer], [{'scheduler': lr_scheduler, 'interval': 'step'}]
+
     def _autocast(self, x):
         return torch.autocast('cuda', dtype=torch.bfloat16, enabled=self.precision == 'bf16' and x.is_cuda)
 

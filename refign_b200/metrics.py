@@ -175,7 +175,22 @@ class MetricCollection(nn.ModuleDict):
     """Minimal stand-in for the reference's ``MyMetricCollection`` (helpers/metrics.py:13-33): a dict of metrics whose
     ``compute`` flattens dict-valued results as ``<metric>_<key>``."""
 
-    def compute(self):
+    def sync(self, process_group=None):
+        """Sum every metric's state over the ranks (torchmetrics' ``dist_reduce_fx='sum'``, which the reference's
+        metrics rely on): without it multi-GPU validation reports per-rank-shard numbers."""
+        if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            return
+        if torch.distributed.get_world_size(process_group) == 1:
+            return
+        for metric in self.values():
+            for buf in metric.buffers():
+                torch.distributed.all_reduce(buf, group=process_group)
+
+    def compute(self, sync=True):
+        """``sync``: all-reduce the states first when a process group is initialised (called once per epoch end; the
+        states are reset right after, so the summed buffers are never accumulated into again)."""
+        if sync:
+            self.sync()
         out = {}
         for name, metric in self.items():
             value = metric.compute()

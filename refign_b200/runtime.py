@@ -109,11 +109,16 @@ class FlatAdamW:
         12-float device block so that a captured step can be replayed while the schedule advances."""
         if self.hyper is None:
             self.hyper = torch.zeros(12, dtype=torch.float32, device=self.flat.data.device)
-            self._hyper_host = torch.zeros(12, dtype=torch.float32).pin_memory()
+            # ring of pinned staging buffers with "copy done" events: the graphed step has no host sync, so the host may
+            # run several steps ahead of the device and must not rewrite scalars whose DMA has not executed yet
+            self._hyper_ring = [(torch.zeros(12, dtype=torch.float32).pin_memory(), torch.cuda.Event()) for _ in range(8)]
+            self._hyper_i = 0
 
     def upload_hyper(self, ema_m):
         """Host -> device copy of the scalars of the step about to run (async, pinned)."""
-        h = self._hyper_host
+        h, ev = self._hyper_ring[self._hyper_i % len(self._hyper_ring)]
+        self._hyper_i += 1
+        ev.synchronize()                      # (no-op unless the host is 8 steps ahead)
         t = self.step_count + 1
         for i, lr in enumerate(self.seg_lr):
             h[i] = lr
@@ -122,6 +127,7 @@ class FlatAdamW:
         h[10] = ema_m
         h[11] = 1.0 - ema_m
         self.hyper.copy_(h, non_blocking=True)
+        ev.record()
 
     def launch_step(self):
         """Device work of one optimiser step (all-reduce + AdamW kernel), no host bookkeeping."""

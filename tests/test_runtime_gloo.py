@@ -83,3 +83,34 @@ def test_two_rank_gloo_matches_single_process(tmp_path):
         single = _train(_make(), X, Y, 1, None)
     # mean over the full batch == mean of the two per-rank means (equal shard sizes)
     assert torch.allclose(r0, single, rtol=1e-5, atol=1e-6), (r0 - single).abs().max()
+
+
+def _metric_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from refign_b200.metrics import IoU, MetricCollection
+    torch.manual_seed(3)
+    logits, labels = torch.randn(4, 19, 8, 8), torch.randint(0, 19, (4, 8, 8))
+    mc = MetricCollection({'val_iou': IoU(num_classes=19, ignore_index=255)})
+    for m in mc.values():
+        m(logits[rank::world], labels[rank::world])          # every rank sees its shard of the validation set
+    value = mc.compute()['val_iou']                          # sums the confusion matrices over the ranks first
+    if rank == 0:
+        torch.save(value, out)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_metric_collection_sums_state_over_ranks(tmp_path):
+    """Multi-GPU validation (reference: torchmetrics dist_reduce_fx='sum'): MetricCollection.compute() all-reduces the
+    metric states, so two ranks on half of the data each report the single-process IoU, not their shard's."""
+    out = str(tmp_path / "iou.pt")
+    mp.spawn(_metric_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    from refign_b200.metrics import IoU
+    torch.manual_seed(3)
+    logits, labels = torch.randn(4, 19, 8, 8), torch.randint(0, 19, (4, 8, 8))
+    m = IoU(num_classes=19, ignore_index=255)
+    m(logits, labels)
+    assert torch.allclose(torch.load(out), m.compute(), rtol=1e-6, atol=0)
