@@ -87,6 +87,7 @@ class Attention(nn.Module):
         self.sr_ratio = sr_ratio
         if sr_ratio > 1:
             self.sr = nn.Conv2d(dim, dim, kernel_size=sr_ratio, stride=sr_ratio)
+            self.sr.weight._rf_sr_weight = True     # runtime.FlatParams stores it channels-last (the patch-GEMM layout)
             self.norm = nn.LayerNorm(dim)
 
     def forward(self, x, H, W):

@@ -841,9 +841,13 @@ def _sr_weight_perm(weight):
     if wp is None:
         src = weight._rf_bf16
         Co = src.shape[0]
-        wp = src.permute(0, 2, 3, 1).reshape(Co, -1).contiguous()
+        cl = src.permute(0, 2, 3, 1)
+        if cl.is_contiguous():      # stored channels-last by the runtime (FlatParams._view): the shadow IS the GEMM weight
+            wp = cl.view(Co, -1)
+        else:
+            wp = cl.reshape(Co, -1).contiguous()
+            _DERIVED.append((src, wp))
         weight._rf_bf16_perm = wp
-        _DERIVED.append((src, wp))
     return wp
 
 
@@ -1173,13 +1177,20 @@ class _SrConvGemm(torch.autograd.Function):
                 if dx.dtype != xdtype:
                     dx = dx.to(xdtype)
             if ctx.needs_input_grad[1]:
-                if ctx.own:
+                gcl = gw_t.permute(0, 2, 3, 1) if gw_t is not None else None
+                if ctx.own and gcl is not None and gcl.is_contiguous():
+                    # the flat gradient holds this weight channels-last: accumulate into it in place
+                    gemm_bf16(go2, xs2, out=gcl.view(Co, -1), a_mn_major=True, b_mn_major=True, accumulate=True)
+                    dwp = None
+                elif ctx.own:
                     dwp = torch.zeros(Co, s * s * C, device=go2.device, dtype=torch.float32)
                     gemm_bf16(go2, xs2, out=dwp, a_mn_major=True, b_mn_major=True, accumulate=True)
                     dwp = dwp.view(Co, s, s, C)
                 else:
                     dwp = _mm_f32(go2.t(), xs2).view(Co, s, s, C)            # layout of wperm
-                if gw_t is not None:
+                if dwp is None:
+                    pass                                  # already accumulated in place
+                elif gw_t is not None:
                     gw_t.permute(0, 2, 3, 1).add_(dwp)
                 else:
                     dw = dwp.permute(0, 3, 1, 2)

@@ -44,19 +44,32 @@ class FlatParams:
         with torch.no_grad():
             for p, o in zip(params, self.offsets):
                 n = p.numel()
-                self.data[o:o + n].copy_(p.data.reshape(-1))
-                p.data = self.data[o:o + n].view(p.shape)
+                self._view(self.data, p, o).copy_(p.data)
+                p.data = self._view(self.data, p, o)
                 if with_grad:
-                    p.grad = self.grad[o:o + n].view(p.shape)
+                    p.grad = self._view(self.grad, p, o)
                     # backward kernels may accumulate straight into this view (ops.grad_target)
                     p._rf_direct_grad = bool(self.grad.is_cuda)
+
+    @staticmethod
+    def _view(buf, p, o):
+        """The segment of ``buf`` that holds parameter ``p``, with p's logical shape.  4-D conv weights flagged
+        ``_rf_store_cl`` (the kernel == stride spatial-reduction convs of the MiT attention) are STORED channels-last
+        ([Co, kh, kw, Ci] in memory, the layout of the space-to-depth patch GEMM that runs them): the GEMM then reads
+        the bf16 shadow in place and its weight gradient accumulates straight into the flat gradient -- no permuted
+        copies per step.  Element-wise consumers (AdamW, EMA, all-reduce, casts) never see the difference."""
+        seg = buf[o:o + p.numel()]
+        if p.dim() == 4 and getattr(p, '_rf_store_cl', False):
+            co, ci, kh, kw = p.shape
+            return seg.view(co, kh, kw, ci).permute(0, 3, 1, 2)
+        return seg.view(p.shape)
 
     def attach_shadow(self):
         """Flat bf16 copy of the buffer; every parameter gets ``p._rf_bf16`` = its bf16 view (read by
         refign_b200.ops.linear under bf16 autocast).  ``refresh_shadow()`` must follow every update."""
         self.shadow = torch.empty(self.data.numel(), dtype=torch.bfloat16, device=self.data.device)
         for p, o in zip(self.params, self.offsets):
-            p._rf_bf16 = self.shadow[o:o + p.numel()].view(p.shape)
+            p._rf_bf16 = self._view(self.shadow, p, o)
         self.refresh_shadow()
 
     def refresh_shadow(self):
@@ -68,7 +81,7 @@ class FlatParams:
         """(Re)attach the flat gradient views (after anything that reset ``p.grad`` to None)."""
         for p, o in zip(self.params, self.offsets):
             if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * o:
-                p.grad = self.grad[o:o + p.numel()].view(p.shape)
+                p.grad = self._view(self.grad, p, o)
 
 
 def linear_warmup_poly_lr(step, base_lr, max_steps, warmup_iters=1500, warmup_ratio=1e-6, power=0.9, min_lr=0.0):

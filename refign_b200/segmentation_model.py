@@ -200,6 +200,12 @@ class DomainAdaptationSegmentationModel(_Base):
         ema = []
         for n in names:  # same permutation for the teacher: backbone.x <-> m_backbone.x, head.x <-> m_head.x
             ema.append(ema_by_name['m_' + n])
+        # the kernel == stride spatial-reduction convs run as patch GEMMs on channels-last weights: store them that way
+        # in the flat buffers (student and teacher alike, so the EMA update stays element-wise)
+        # (live and ema are in the same order; deepcopy does not carry Parameter attributes over to the teacher)
+        for pl_, pe_ in zip(live, ema):
+            if pl_.dim() == 4 and getattr(pl_, '_rf_sr_weight', False):
+                pl_._rf_store_cl = pe_._rf_store_cl = True
         flat_live = runtime.FlatParams(live, with_grad=True)
         flat_ema = runtime.FlatParams(ema, with_grad=False)
         if self.precision == 'bf16' and flat_live.data.is_cuda:
