@@ -369,9 +369,12 @@ int rf_adamw_step_dev(float* param, const float* grad, float* exp_avg, float* ex
  *         contraction is split over CTAs and partial sums are added with red.global (weight gradients into the flat
  *         gradient buffer); bias : f32 [N] or NULL.  All row pitches must be multiples of 8 elements.
  *   forward y = x W^T + b : (a = x, b = W);   dgrad dx = dy W : (a = dy, b = W, b_mn_major = 1);
- *   wgrad dW += dy^T x : (a = dy, a_mn_major = 1, b = x, b_mn_major = 1, out_f32 = 1, accumulate = 1). */
+ *   wgrad dW += dy^T x : (a = dy, a_mn_major = 1, b = x, b_mn_major = 1, out_f32 = 1, accumulate = 1).
+ *   colsum : f32 [M] or NULL (accumulating calls only): colsum[m] += sum_k A(m,k) -- the bias gradient db = sum_t dy[t,:]
+ *            of the same Linear layer, reduced by the tensor core inside the weight-gradient GEMM (one extra N = 16 MMA
+ *            per k-step against a tile of ones) instead of a separate column-sum launch. */
 int rf_gemm_bf16(const void* a, const void* b, const float* bias, void* out, int M, int N, int K, int a_mn_major,
-                 int b_mn_major, int out_f32, int accumulate, void* stream);
+                 int b_mn_major, int out_f32, int accumulate, float* colsum, void* stream);
 
 /* ---- 3x3 convolution (stride 1, padding = dilation) as an implicit GEMM on the same tcgen05 kernel ------------- */
 /* Replaces the library convolutions of the DAFormer bottleneck (models/heads/daformer.py:102-108, modules.py:16-56),

@@ -44,7 +44,7 @@ _SIGNATURES = {
     "rf_sr_attention_f32_fwd": (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_f32, c_p]),
     "rf_sr_attention_f32_bwd_workspace_bytes": (c_i64, [c_int, c_int, c_int]),
     "rf_sr_attention_f32_bwd": (c_int, [c_p] * 8 + [c_int, c_int, c_int, c_int, c_int, c_f32, c_p]),
-    "rf_gemm_bf16": (c_int, [c_p, c_p, c_p, c_p] + [c_int] * 7 + [c_p]),
+    "rf_gemm_bf16": (c_int, [c_p, c_p, c_p, c_p] + [c_int] * 7 + [c_p, c_p]),
     "rf_conv3x3_bf16": (c_int, [c_p, c_p, c_p, c_p] + [c_int] * 7 + [c_f32, c_int, c_p]),
     "rf_uncertainty_cnn_param_bytes": (c_int, []),
     "rf_uncertainty_cnn_fwd": (c_int, [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_f32, c_p]),

@@ -69,6 +69,7 @@ struct GmParams {
   int M, N, K;
   int m_tiles, n_tiles, k_blocks, splits, kb_per_split;
   int out_f32, accumulate;
+  float* colsum;           // MODE 0, optional: colsum[m] += sum_k A[m, k] (the bias gradient riding on the weight-gradient GEMM)
   // implicit-GEMM 3x3 convolution (MODE 1: forward / input gradient, MODE 2: weight gradient)
   int taps;                // 1 (GEMM, MODE 1) or 9 (MODE 2: one output tile set per filter tap)
   int H, W, tiles_h, tiles_w;      // MODE 1: pixel tiles of 8 x 16;  MODE 2: pixel k-blocks of 4 x 16
@@ -113,7 +114,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         mbar_init(&bars->full[s], 1);              // CTA pair: the leader's barrier collects both CTAs' loads
         mbar_init(&bars->empty[s], 1);
       }
-      for (int s = 0; s < Cfg::ACC; ++s) {
+      for (int s = 0; s < Cfg::ACC; ++s) {      // (all of them; with column sums only the first `nacc` are used)
         mbar_init(&bars->acc_full[s], 1);
         // CTA pair: the leader's MMAs also wait for ONE forwarded arrival per tile from the peer CTA (see the MMA warp)
         mbar_init(&bars->acc_empty[s], (CL2 && cluster_ctarank() == 0) ? 9 : 8);
@@ -128,6 +129,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   }
   if (warp == 9) {
     if (CL2) tmem_alloc_2cta<512>(&bars->tmem_base); else tmem_alloc<512>(&bars->tmem_base);
+  }
+  // Column sums of A (the bias gradient db[n] = sum_t dy[t, n] of a Linear layer, riding on its weight-gradient GEMM
+  // dW = dy^T x whose A operand IS dy^T): one extra N = 16 MMA per k-step against a tile of ONES puts sum_k A[m, k] into
+  // 16 spare accumulator columns -- the tensor core does the reduction, a separate column-sum launch per layer goes away.
+  // The ones tile (no-swizzle K-major core matrices, 512 B) lives in the bias slice, which an accumulating GEMM never uses;
+  // the spare columns are 448 + 16 * buffer, so at most 448 / BN (<= 4) accumulator buffers are in flight.
+  const bool do_cs = MODE == GM_GEMM && !CL2 && p.colsum != nullptr;
+  const int nacc = do_cs ? ((448 / BN) < 4 ? (448 / BN) : 4) : Cfg::ACC;
+  if (do_cs && tid < 256) {
+    reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 384)[tid] = 0x3F803F80u;   // bf16 (1.0, 1.0) x 512
+    fence_proxy_async();
   }
   tc_fence_before();
   __syncthreads();
@@ -234,8 +246,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       // leader, so the (slow: ~2 000 cycles with release semantics at cluster scope) remote arrival is not paid by the
       // eight epilogue warps inside their tile loop.
       for (long w = w_first; w < items; w += w_step, ++local) {
-        const int buf = local % Cfg::ACC;
-        mbar_wait(&bars->acc_empty[buf], (local / Cfg::ACC) & 1);
+        const int buf = local % nacc;
+        mbar_wait(&bars->acc_empty[buf], (local / nacc) & 1);
         if (elect_one()) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->acc_empty[buf]), 0));
         __syncwarp();
       }
@@ -243,10 +255,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     for (long w = (CL2 && rank != 0) ? items : w_first; w < items; w += w_step, ++local) {   // pair: the leader issues
       const int split = (int)(w % p.splits);
       const int kb0 = split * p.kb_per_split, kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
-      const int buf = local % Cfg::ACC;
-      if (local >= Cfg::ACC) mbar_wait(&bars->acc_empty[buf], ((local / Cfg::ACC) - 1) & 1);
+      const int buf = local % nacc;
+      if (local >= nacc) mbar_wait(&bars->acc_empty[buf], ((local / nacc) - 1) & 1);
       tc_fence_after();
       const uint32_t d = tmem + buf * BN;
+      const bool cs_item = do_cs && ((int)(w / p.splits) % p.n_tiles) == 0;     // one n-tile per m-tile carries the column sum
+      constexpr uint32_t IDESC_CS = make_idesc(FMT_BF16, GM_BM, 16, A_MN ? 1 : 0, 0);
+      const uint64_t d_ones = make_sdesc(smem_u32(reinterpret_cast<uint8_t*>(bars) + 384), 128, 256, 0);
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int st = it % Cfg::STAGES;
         mbar_wait(&bars->full[st], (it / Cfg::STAGES) & 1);
@@ -258,6 +273,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           for (int k = 0; k < GM_BK / 16; ++k) {
             if (CL2) mma_f16_ss_2cta(d, dA + k * KA, dB + k * KB, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
             else mma_f16_ss(d, dA + k * KA, dB + k * KB, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          if (cs_item) {
+#pragma unroll
+            for (int k = 0; k < GM_BK / 16; ++k)
+              mma_f16_ss(tmem + 448 + buf * 16, dA + k * KA, d_ones, IDESC_CS, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           if (CL2) tc_commit_2cta(&bars->empty[st], 3); else tc_commit(&bars->empty[st]);
           if (kb == kb1 - 1) {
@@ -367,7 +387,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     if (p.bias && Cfg::EPI == 2 && my_col < BN) sbias0[my_col] = bias_at(w_first);
     int local = 0;
     for (long w = w_first; w < items; w += w_step, ++local) {
-      const int buf = local % Cfg::ACC;
+      const int buf = local % nacc;
       float* const sbias = sbias0 + (Cfg::EPI == 2 ? (local & 1) * BN : 0);
       if (p.bias) {   // this tile's bias slice, zero beyond N, read back as broadcast shared-memory vectors
         if (Cfg::EPI == 2) {
@@ -381,7 +401,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           wg_sync();
         }
       }
-      mbar_wait(&bars->acc_full[buf], (local / Cfg::ACC) & 1);
+      mbar_wait(&bars->acc_full[buf], (local / nacc) & 1);
       tc_fence_after();
       WS_T(10);
       const uint32_t t = tmem + lane_off + buf * BN;
@@ -428,7 +448,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               pk[e] = __float_as_uint(x > 0.f ? x : (p.act == 1 ? 0.f : x * p.slope));
             }
           }
-          if (c + 2 >= nchunk) release_acc();
+          if (c + 2 >= nchunk) {
+            if (do_cs && wg == 0 && ((int)(w / p.splits) % p.n_tiles) == 0) {
+              uint32_t cs[8];
+              tmem_ld8(tmem + lane_off + 448 + buf * 16, cs);
+              tc_wait_ld();
+              const int m = (int)((w / p.splits) / p.n_tiles) % p.m_tiles * GM_BM + r;
+              if (m < p.M) atomicAdd(p.colsum + m, __uint_as_float(cs[0]));
+            }
+            release_acc();
+          }
           hand_over(pk);
         }
       } else {
@@ -550,8 +579,9 @@ static int pick_bn(long m_tiles, int N, bool b_mn, bool* pairs_out) {
 using namespace rf;
 
 extern "C" int rf_gemm_bf16(const void* a, const void* b, const float* bias, void* out, int M, int N, int K, int a_mn_major,
-                            int b_mn_major, int out_f32, int accumulate, void* stream) {
+                            int b_mn_major, int out_f32, int accumulate, float* colsum, void* stream) {
   RF_REQUIRE(a && b && out && M > 0 && N > 0 && K > 0, "rf_gemm_bf16: bad arguments");
+  RF_REQUIRE(!colsum || (accumulate && out_f32), "rf_gemm_bf16: the fused column sum rides on an accumulating fp32 GEMM");
   RF_REQUIRE((((uintptr_t)a | (uintptr_t)b | (uintptr_t)out) & 15) == 0, "rf_gemm_bf16: operands must be 16-byte aligned");
   RF_REQUIRE(!(accumulate && !out_f32), "rf_gemm_bf16: accumulation needs an fp32 output");
   RF_REQUIRE(!(accumulate && bias), "rf_gemm_bf16: bias and accumulation are exclusive");
@@ -560,7 +590,11 @@ extern "C" int rf_gemm_bf16(const void* a, const void* b, const float* bias, voi
   RF_REQUIRE(a_pitch % 8 == 0 && b_pitch % 8 == 0 && N % (out_f32 ? 4 : 8) == 0,
              "rf_gemm_bf16: M / N / K pitches must be multiples of 8 elements (got M %d N %d K %d)", M, N, K);
   bool pairs = false;
-  const int BN = pick_bn((M + GM_BM - 1) / GM_BM, N, b_mn_major != 0, &pairs);
+  int BN = pick_bn((M + GM_BM - 1) / GM_BM, N, b_mn_major != 0, &pairs);
+  if (colsum) {            // 16 spare accumulator columns per buffer: single CTAs, tiles of at most 192 columns
+    pairs = false;
+    if (BN == 256) BN = 128;
+  }
   CUtensorMap ta, tb;
   int rc;
   if (a_mn_major)   // stored [K, M]: box = 64 m (inner) x 64 k
@@ -591,6 +625,7 @@ extern "C" int rf_gemm_bf16(const void* a, const void* b, const float* bias, voi
   p.k_blocks = (K + GM_BK - 1) / GM_BK;
   p.out_f32 = out_f32;
   p.accumulate = accumulate;
+  p.colsum = colsum;
   p.taps = 1;
   p.H = p.W = p.tiles_h = p.tiles_w = p.cin_blocks = 1;
   p.act = 0;
@@ -659,6 +694,7 @@ extern "C" int rf_conv3x3_bf16(const void* x, const void* w, const float* bias, 
   p.kb_per_split = p.k_blocks;
   p.out_f32 = out_f32;
   p.accumulate = 0;
+  p.colsum = nullptr;
   p.taps = 1;
   p.H = H;
   p.W = W;
@@ -707,6 +743,7 @@ extern "C" int rf_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dw, i
   p.W = W;
   p.out_f32 = 1;
   p.accumulate = 1;
+  p.colsum = nullptr;
   p.act = 0;
   p.slope = 0.f;
   p.dil = 1;

@@ -576,9 +576,14 @@ import os as _os
 OWN_GEMM = _os.environ.get('RF_OWN_GEMM', '1') != '0'   # Linear layers on the tcgen05 GEMM (csrc/gemm_bf16.cu); RF_OWN_GEMM=0 = library GEMMs (comparison arm)
 
 
-def gemm_bf16(a, b, bias=None, out=None, a_mn_major=False, b_mn_major=False, out_dtype=torch.bfloat16, accumulate=False):
+FUSED_COLSUM = _os.environ.get('RF_FUSED_COLSUM', '1') != '0'   # bias gradients inside the weight-gradient GEMM (A/B switch)
+
+
+def gemm_bf16(a, b, bias=None, out=None, a_mn_major=False, b_mn_major=False, out_dtype=torch.bfloat16, accumulate=False,
+              colsum_out=None):
     """out[m,n] (+)= sum_k A(m,k) B(n,k) (+ bias[n]) on the tcgen05 GEMM kernel.  ``a`` is [M,K] (or [K,M] with
-    a_mn_major), ``b`` [N,K] (or [K,N] with b_mn_major), both contiguous bf16; ``out`` bf16 / f32 [M,N]."""
+    a_mn_major), ``b`` [N,K] (or [K,N] with b_mn_major), both contiguous bf16; ``out`` bf16 / f32 [M,N].
+    ``colsum_out`` (f32 [M], accumulating calls only): += sum_k A(m,k), reduced inside the same kernel."""
     require_cuda(a, b)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.is_contiguous() and b.is_contiguous()
     K, M = (a.shape[0], a.shape[1]) if a_mn_major else (a.shape[1], a.shape[0])
@@ -589,9 +594,11 @@ def gemm_bf16(a, b, bias=None, out=None, a_mn_major=False, b_mn_major=False, out
         out = torch.empty(M, N, device=a.device, dtype=out_dtype)
     assert out.is_contiguous() and out.shape == (M, N) and out.dtype in (torch.bfloat16, torch.float32)
     bias_f = None if bias is None else _f32c(bias)
+    if colsum_out is not None:
+        assert accumulate and colsum_out.dtype == torch.float32 and colsum_out.is_contiguous() and colsum_out.numel() == M
     with torch.cuda.device(a.device):
         _run("rf_gemm_bf16", ptr(a), ptr(b), ptr(bias_f), ptr(out), M, N, K, int(a_mn_major), int(b_mn_major),
-             int(out.dtype == torch.float32), int(accumulate), _stream(),
+             int(out.dtype == torch.float32), int(accumulate), ptr(colsum_out), _stream(),
              work=(2 * (M * K + N * K) + out.element_size() * M * N, 2 * M * N * K), tag="gemm_bf16")
     return out
 
@@ -757,18 +764,28 @@ class _LinearShadow(torch.autograd.Function):
                 if dx.dtype != ctx.x_dtype:
                     dx = dx.to(ctx.x_dtype)
             gw_t, gb_t = ctx.targets
+            bias_done = False
             if ctx.needs_input_grad[1]:
                 if own:    # dW += dy^T x: both operands read MN-major in place, fp32 partial sums red.add'ed into the target
+                    cs = None
+                    if FUSED_COLSUM and ctx.has_bias and ctx.needs_input_grad[2]:
+                        # db = column sums of dy ride on the same GEMM (its A operand is dy^T)
+                        if gb_t is not None:
+                            cs = gb_t
+                        else:
+                            db = cs = torch.zeros(go2.shape[1], device=go2.device, dtype=torch.float32)
+                        bias_done = True
                     if gw_t is not None:
-                        gemm_bf16(go2, x2, out=gw_t.view(wb.shape), a_mn_major=True, b_mn_major=True, accumulate=True)
+                        gemm_bf16(go2, x2, out=gw_t.view(wb.shape), a_mn_major=True, b_mn_major=True, accumulate=True,
+                                  colsum_out=cs)
                     else:
                         dw = torch.zeros(wb.shape, device=wb.device, dtype=torch.float32)
-                        gemm_bf16(go2, x2, out=dw, a_mn_major=True, b_mn_major=True, accumulate=True)
+                        gemm_bf16(go2, x2, out=dw, a_mn_major=True, b_mn_major=True, accumulate=True, colsum_out=cs)
                 elif gw_t is not None:
                     _mm_f32_acc(gw_t, go2.t(), x2)
                 else:
                     dw = _mm_f32(go2.t(), x2)
-            if ctx.has_bias and ctx.needs_input_grad[2]:
+            if ctx.has_bias and ctx.needs_input_grad[2] and not bias_done:
                 if go2.shape[1] % 8 != 0:
                     db = go2.float().sum(0)
                 elif gb_t is not None:
@@ -1164,6 +1181,7 @@ class _SrConvGemm(torch.autograd.Function):
         gw_t, gb_t = ctx.targets
         Co = wshape[0]
         dx = dw = db = None
+        bias_done = False
         with torch.autocast('cuda', enabled=False):
             go2 = go.reshape(-1, Co)
             if go2.dtype != torch.bfloat16:
@@ -1179,8 +1197,11 @@ class _SrConvGemm(torch.autograd.Function):
             if ctx.needs_input_grad[1]:
                 gcl = gw_t.permute(0, 2, 3, 1) if gw_t is not None else None
                 if ctx.own and gcl is not None and gcl.is_contiguous():
-                    # the flat gradient holds this weight channels-last: accumulate into it in place
-                    gemm_bf16(go2, xs2, out=gcl.view(Co, -1), a_mn_major=True, b_mn_major=True, accumulate=True)
+                    # the flat gradient holds this weight channels-last: accumulate into it in place; the bias gradient
+                    # (column sums of dy) rides on the same GEMM
+                    cs = gb_t if (FUSED_COLSUM and ctx.needs_input_grad[2] and gb_t is not None and Co % 8 == 0) else None
+                    gemm_bf16(go2, xs2, out=gcl.view(Co, -1), a_mn_major=True, b_mn_major=True, accumulate=True, colsum_out=cs)
+                    bias_done = cs is not None
                     dwp = None
                 elif ctx.own:
                     dwp = torch.zeros(Co, s * s * C, device=go2.device, dtype=torch.float32)
@@ -1194,7 +1215,7 @@ class _SrConvGemm(torch.autograd.Function):
                     gw_t.permute(0, 2, 3, 1).add_(dwp)
                 else:
                     dw = dwp.permute(0, 3, 1, 2)
-            if ctx.needs_input_grad[2]:
+            if ctx.needs_input_grad[2] and not bias_done:
                 if Co % 8 != 0:
                     db = go2.float().sum(0)
                 elif gb_t is not None:

@@ -161,3 +161,23 @@ def test_maxpool2x2_channels_last(shape):
     with torch.no_grad():
         got = ops.max_pool2x2(x)
     assert torch.equal(got, F.max_pool2d(x, 2, 2))
+
+
+@pytest.mark.parametrize("shape", [(8192, 320, 1280), (8192, 1280, 320), (2048, 512, 2048), (131072, 64, 64), (1000, 136, 72),
+                                   (4096, 640, 320), (520, 2048, 512)])
+def test_wgrad_gemm_with_fused_bias_gradient(shape):
+    """dW += dy^T x with the bias gradient db += sum_t dy[t, :] reduced by the tensor core inside the same kernel (an extra
+    N = 16 MMA per k-step against a tile of ones, 16 spare accumulator columns per buffer): both outputs accumulate on
+    top of existing contents; ragged output-feature counts, one / many m-tiles, split contraction."""
+    T, K_in, N_out = shape
+    torch.manual_seed(T + K_in + N_out)
+    x = torch.randn(T, K_in, device=DEV).bfloat16()
+    dy = torch.randn(T, N_out, device=DEV).bfloat16()
+    dw0 = torch.randn(N_out, K_in, device=DEV)
+    db0 = torch.randn(N_out, device=DEV)
+    dw, db = dw0.clone(), db0.clone()
+    ops.gemm_bf16(dy, x, out=dw, a_mn_major=True, b_mn_major=True, accumulate=True, colsum_out=db)
+    want_w = dw0 + dy.float().t() @ x.float()
+    want_b = db0 + dy.float().sum(0)
+    _close(dw, want_w, 2e-4, "dW")
+    _close(db, want_b, 2e-5, "db")

@@ -33,7 +33,7 @@ int main(int argc, char** argv) {
   for (int rep = 0; rep < 3; ++rep) {
     CK(cudaMemset(trace, 0, 2 * 11 * 256 * 8));
     CK(cudaEventRecord(e0));
-    if (rf_gemm_bf16(a, b, (acc || of32) ? nullptr : bias, out, M, N, K, amn, bmn, of32, acc, 0) != 0) return 1;
+    if (rf_gemm_bf16(a, b, (acc || of32) ? nullptr : bias, out, M, N, K, amn, bmn, of32, acc, nullptr, 0) != 0) return 1;
     CK(cudaEventRecord(e1));
     CK(cudaDeviceSynchronize());
     CK(cudaEventElapsedTime(&ms, e0, e1));
