@@ -135,9 +135,17 @@ class ClockSampler:
 
 # DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of one launch from the `ncu --set full` captures
 # summarised in profiles/r01_ncu_full_kernel_metrics.json, at the 1024x1024 stage-1 shape (B2 N65536 M1024, 1 head)
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the round's `ncu --set full` captures
+# (profiles/r02_ncu_full_kernel_metrics.json); outputs that fit the 126 MB L2 do not reach DRAM inside the launch
 NCU_TRAFFIC = {
-    "sr_attention_bwd": {"bytes": 51.41e6 + 0.73e6 + 36.21e6, "shape": "B2 N65536 M1024 h1 (dq + dkv kernels)",
-                         "algorithmic_bytes": 2 * (4 * 2 * 65536 * 64 + 2 * 2 * 1024 * 128)},
+    "sr_attention_bwd": {"bytes": 18.72e6, "shape": "B2 N4096 M1024 h5 (MiT-B5 stage 3, warp-specialised kernel)",
+                         "algorithmic_bytes": 2 * (4 * 2 * 4096 * 320 + 2 * 2 * 1024 * 640)},
+    "sr_attention_fwd": {"bytes": 7.91e6, "shape": "B2 N4096 M1024 h5 (MiT-B5 stage 3)",
+                         "algorithmic_bytes": 2 * (2 * 2 * 4096 * 320 + 2 * 1024 * 640)},
+    "gemm_bf16": {"bytes": 6.09e6, "shape": "M8192 N1280 K320 forward (Mix-FFN fc1 of MiT-B5 stage 3; the 21 MB output stays in L2)",
+                  "algorithmic_bytes": 2 * (8192 * 320 + 1280 * 320) + 2 * 8192 * 1280},
+    "conv3x3": {"bytes": 283.7e6 + 52.8e6, "shape": "2x256x256x1024 -> 256 (DAFormer bottleneck)",
+                "algorithmic_bytes": 2 * (2 * 256 * 256 * 1024 + 256 * 9 * 1024 + 2 * 256 * 256 * 256)},
 }
 
 
