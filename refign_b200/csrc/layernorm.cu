@@ -16,6 +16,8 @@
 // added to global fp32 buffers with one atomic per channel per CTA.
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include "rf_common.cuh"
 
 namespace rf {
@@ -237,6 +239,22 @@ static int ln_grid(long rows) {
   return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
 }
 
+// The backward ends with 2 C global atomics per CTA (dgamma / dbeta).  One CTA per 8 rows means 1 024-way contention per
+// address at MiT stage 3 (8 192 rows, the shape of 160 of the 208 calls of a step), where the launch is short enough
+// for that to show: 10.8 -> 6.7 us with 3 CTAs per SM looping over their rows (tools/bench_layernorm.py).  Long launches
+// (stage 1: 131 072 rows) keep the full grid, they are bandwidth-bound and lose with fewer warps in flight.
+// RF_LN_BWD_CTAS_PER_SM overrides the short-launch value.
+static int ln_bwd_grid(long rows) {
+  static const int per_sm = [] {
+    const char* e = getenv("RF_LN_BWD_CTAS_PER_SM");
+    const int v = e ? atoi(e) : 3;
+    return v < 1 ? 1 : (v > 8 ? 8 : v);
+  }();
+  long blocks = (rows + 7) / 8;
+  const long cap = (long)kNumSMs * (rows <= 16384 ? per_sm : 8);
+  return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+}
+
 template <typename TX, typename TB, typename TY>
 static int ln_fwd_dispatch(const void* x, const void* branch, const float* scale, const float* gamma,
                            const float* beta, float* xn, void* y, float* mean, float* rstd, long rows, int C,
@@ -266,7 +284,7 @@ template <typename TXN, typename TY, typename TB>
 static int ln_bwd_dispatch(const void* xn, const void* dy, const float* dxn_in, const float* mean, const float* rstd,
                            const float* gamma, const float* scale, float* dxn, void* dbranch, float* dgamma,
                            float* dbeta, long rows, int C, long rps, cudaStream_t st) {
-  const int grid = ln_grid(rows);
+  const int grid = ln_bwd_grid(rows);
   const size_t smem = sizeof(float) * 2 * C;
 #define RF_LN_BWD(NP)                                                                                            \
   add_layernorm_bwd_kernel<TXN, TY, TB, NP><<<grid, 256, smem, st>>>((const TXN*)xn, (const TY*)dy, dxn_in, mean, \
