@@ -8,9 +8,12 @@ namespace rf {
 __device__ long long* g_ws_trace;
 __device__ int g_ws_trace_blocks[2];
 __shared__ long long ws_trace_buf[11][256];     // per warp: [0] = count, then the records
+#ifndef WS_TRACE_SLOT
+#define WS_TRACE_SLOT(w) (w)          // which of the 11 log rows a warp writes (-1: none); kernels with more warps remap
+#endif
 __device__ __forceinline__ void ws_trace(int tag) {
-  const int warp = threadIdx.x >> 5;
-  if ((threadIdx.x & 31) != 0 || warp > 10) return;
+  const int warp = WS_TRACE_SLOT((int)(threadIdx.x >> 5));
+  if ((threadIdx.x & 31) != 0 || warp < 0 || warp > 10) return;
   long long* base = ws_trace_buf[warp];
   const int n = (int)base[0];
   if (n < 254) {
