@@ -20,7 +20,7 @@
 namespace rf {
 
 constexpr int UC_PIX = 16;           // pixels per CTA iteration
-constexpr int UC_THREADS = 256;
+constexpr int UC_THREADS = 512;          // 16 warps: the phases are latency-bound (dependent LDSM -> HMMA -> STS chains), not throughput-bound
 constexpr int UC_APITCH = 40;        // bf16 elements per activation row (32 channels + 8 pad: conflict-free ldmatrix rows)
 constexpr int UC_WPITCH = 296;       // bf16 elements per filter row (288 + 8 pad)
 // parameter block (bytes), built by refign_b200/modules.py: UncertaintyModule._fused_params
