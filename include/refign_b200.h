@@ -372,7 +372,8 @@ int rf_adamw_step_dev(float* param, const float* grad, float* exp_avg, float* ex
  *   wgrad dW += dy^T x : (a = dy, a_mn_major = 1, b = x, b_mn_major = 1, out_f32 = 1, accumulate = 1).
  *   colsum : f32 [M] or NULL (accumulating calls only): colsum[m] += sum_k A(m,k) -- the bias gradient db = sum_t dy[t,:]
  *            of the same Linear layer, reduced by the tensor core inside the weight-gradient GEMM (one extra N = 16 MMA
- *            per k-step against a tile of ones) instead of a separate column-sum launch. */
+ *            per k-step against a tile of ones) instead of a separate column-sum launch; needs the weight-gradient
+ *            layouts a_mn_major = b_mn_major = 1. */
 int rf_gemm_bf16(const void* a, const void* b, const float* bias, void* out, int M, int N, int K, int a_mn_major,
                  int b_mn_major, int out_f32, int accumulate, float* colsum, void* stream);
 

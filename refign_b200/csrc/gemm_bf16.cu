@@ -92,7 +92,7 @@ __device__ __forceinline__ void gm_load(void* smem_dst, const CUtensorMap* tm, u
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int MODE, bool CL2>
+template <int BN, bool A_MN, bool B_MN, int MODE, bool CL2, bool CS>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_out, const GmParams p) {
@@ -135,8 +135,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   // 16 spare accumulator columns -- the tensor core does the reduction, a separate column-sum launch per layer goes away.
   // The ones tile (no-swizzle K-major core matrices, 512 B) lives in the bias slice, which an accumulating GEMM never uses;
   // the spare columns are 448 + 16 * buffer, so at most 448 / BN (<= 4) accumulator buffers are in flight.
-  const bool do_cs = MODE == GM_GEMM && !CL2 && p.colsum != nullptr;
-  const int nacc = do_cs ? ((448 / BN) < 4 ? (448 / BN) : 4) : Cfg::ACC;
+  // (CS is a template parameter: with the buffer count a run-time value every `local % nacc` of the three roles became an
+  //  integer division and the plain GEMMs lost ~10 %)
+  constexpr bool do_cs = CS;
+  constexpr int nacc = CS ? ((448 / BN) < 4 ? (448 / BN) : 4) : Cfg::ACC;
+  static_assert(!CS || (MODE == GM_GEMM && !CL2 && nacc >= 1), "column sums ride on the plain single-CTA GEMM");
   if (do_cs && tid < 256) {
     reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 384)[tid] = 0x3F803F80u;   // bf16 (1.0, 1.0) x 512
     fence_proxy_async();
@@ -353,6 +356,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     // chunks (one element per thread), so the slice hand-over is a 128-thread named barrier per warpgroup and the two
     // warpgroups never wait for each other.
     float* const sbias0 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 384);
+    const uint32_t sbias0_s = smem_u32(sbias0), sbuf0_s = smem_u32(sbuf0);   // explicit shared-space accesses below
     const int my_col = ((r / cpc) * 2 + wg) * cpc + r % cpc;       // the tile column whose bias this thread stages
     auto bias_at = [&](long ww) -> float {   // (0 beyond N / the end of the work list)
       if (ww >= items || my_col >= BN) return 0.f;
@@ -363,11 +367,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       if (wg == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
     };
     // one 32-column half of a bf16 chunk: + bias, activation, pack -> 16 words
-    auto convert_half = [&](const uint32_t (&v)[32], const float* sb, uint32_t* pkh) {
+    auto convert_half = [&](const uint32_t (&v)[32], uint32_t sb, uint32_t* pkh) {   // sb: shared address of 32 bias floats
 #pragma unroll
       for (int e = 0; e < 16; e += 2) {
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias) bv = *reinterpret_cast<const float4*>(sb + 2 * e);
+        if (p.bias) bv = lds_f4(sb + 8 * e);
         float4 x = make_float4(__uint_as_float(v[2 * e]) + bv.x, __uint_as_float(v[2 * e + 1]) + bv.y,
                                __uint_as_float(v[2 * e + 2]) + bv.z, __uint_as_float(v[2 * e + 3]) + bv.w);
         if (MODE == GM_CONV && p.act) {   // fused ReLU / LeakyReLU of the frozen conv stacks
@@ -384,11 +388,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       }
     };
     float bias_next = 0.f;
-    if (p.bias && Cfg::EPI == 2 && my_col < BN) sbias0[my_col] = bias_at(w_first);
+    if (p.bias && Cfg::EPI == 2 && my_col < BN) sts_f1(sbias0_s + 4 * my_col, bias_at(w_first));
     int local = 0;
     for (long w = w_first; w < items; w += w_step, ++local) {
       const int buf = local % nacc;
-      float* const sbias = sbias0 + (Cfg::EPI == 2 ? (local & 1) * BN : 0);
+      const uint32_t sbias = sbias0_s + (Cfg::EPI == 2 ? (local & 1) * BN * 4 : 0);
       if (p.bias) {   // this tile's bias slice, zero beyond N, read back as broadcast shared-memory vectors
         if (Cfg::EPI == 2) {
           // slice `local` was written during the previous tile (or before the loop); the next tile's element is
@@ -397,7 +401,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           bias_next = bias_at(w + w_step);
         } else {
           wg_sync();                                          // the warpgroup is done with the previous tile's slice
-          if (my_col < BN) sbias[my_col] = bias_at(w);
+          if (my_col < BN) sts_f1(sbias + 4 * my_col, bias_at(w));
           wg_sync();
         }
       }
@@ -412,9 +416,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         ++nstore;
         if (use > 0) mbar_wait(&bars->st_free[wg * 2 + b], (use - 1) & 1);   // the store that last used this buffer has read it
         WS_T(14);
-        uint4* srow = reinterpret_cast<uint4*>(sbuf0 + b * 16384 + r * 128);
+        const uint32_t srow = sbuf0_s + b * 16384 + r * 128;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) srow[q ^ sw] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        for (int q = 0; q < 8; ++q) sts_u4(srow + ((q ^ sw) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
         fence_proxy_async();
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(&bars->st_full[wg * 2 + b]);
@@ -434,7 +438,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           if (p.bias) {
 #pragma unroll
             for (int e = 0; e < 32; e += 4) {
-              const float4 bv = *reinterpret_cast<const float4*>(sbias + c * 32 + e);
+              const float4 bv = lds_f4(sbias + 4 * (c * 32 + e));
               pk[e] = __float_as_uint(__uint_as_float(pk[e]) + bv.x);
               pk[e + 1] = __float_as_uint(__uint_as_float(pk[e + 1]) + bv.y);
               pk[e + 2] = __float_as_uint(__uint_as_float(pk[e + 2]) + bv.z);
@@ -470,10 +474,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           uint32_t pk[32];
           tc_wait_ld();
           tmem_ld32(t + c * 64 + 32, vb);
-          convert_half(va, sbias + c * 64, pk);
+          convert_half(va, sbias + 4 * (c * 64), pk);
           tc_wait_ld();
           if (c + 2 < nchunk) tmem_ld32(t + (c + 2) * 64, va); else release_acc();
-          convert_half(vb, sbias + c * 64 + 32, pk + 16);
+          convert_half(vb, sbias + 4 * (c * 64 + 32), pk + 16);
           hand_over(pk);
         }
       }
@@ -482,7 +486,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(&bars->acc_empty[buf]);
       }
-      if (p.bias && Cfg::EPI == 2 && my_col < BN) sbias0[((local + 1) & 1) * BN + my_col] = bias_next;
+      if (p.bias && Cfg::EPI == 2 && my_col < BN) sts_f1(sbias0_s + 4 * (((local + 1) & 1) * BN + my_col), bias_next);
     }
   }
   tc_fence_before();
@@ -498,11 +502,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 // CTA pairs need a B tile that splits in two halves of whole swizzle groups / 64-column blocks
 constexpr bool gm_pairable(int BN, bool B_MN) { return B_MN ? (BN % 128 == 0) : (BN % 16 == 0); }
 
-template <int BN, bool A_MN, bool B_MN, int MODE, bool CL2>
+template <int BN, bool A_MN, bool B_MN, int MODE, bool CL2, bool CS = false>
 static int gemm_launch_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, GmParams p, cudaStream_t st) {
   using Cfg = GmCfg<BN, MODE, CL2>;
   static bool attr = false;
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, MODE, CL2>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, MODE, CL2, CS>;
   if (!attr) {
     RF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr = true;
@@ -543,6 +547,13 @@ static int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
                        bool pairs = false) {
   if constexpr (gm_pairable(BN, B_MN)) {
     if (pairs) return gemm_launch_impl<BN, A_MN, B_MN, MODE, true>(ta, tb, to, p, st);
+  }
+  if constexpr (MODE == GM_GEMM && A_MN && B_MN && BN <= 192) {     // the weight-gradient layouts can carry the column sum
+    if (p.colsum != nullptr) return gemm_launch_impl<BN, A_MN, B_MN, MODE, false, true>(ta, tb, to, p, st);
+  }
+  if (p.colsum != nullptr) {
+    set_error("rf_gemm_bf16: the fused column sum needs a_mn_major = b_mn_major = 1 (the weight-gradient layouts)");
+    return RF_EINVAL;
   }
   return gemm_launch_impl<BN, A_MN, B_MN, MODE, false>(ta, tb, to, p, st);
 }

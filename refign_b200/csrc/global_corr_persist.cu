@@ -101,8 +101,9 @@ __device__ __forceinline__ float2 gp_value(float2 x, float2 fr2, float2 fc, bool
 
 // One 32-column block of one accumulator row (thread = row).  ncols = valid columns of this block (>= 32: all).
 template <int PASS>
-__device__ __forceinline__ void gp_block(const uint32_t (&v)[32], const float* __restrict__ fcol,
-                                         const float* __restrict__ fnorm, uint8_t* stage, int lane, float frow,
+// fcol / fnorm / stage are SHARED-space addresses: the accesses below are explicit ld.shared / st.shared (pointers into
+// the manually aligned dynamic window lose their provenance and would compile to generic LD.E / ST.E)
+__device__ __forceinline__ void gp_block(const uint32_t (&v)[32], uint32_t fcol, uint32_t fnorm, uint32_t stage, int lane, float frow,
                                          bool mm, bool nrm, int ncols, float& racc, float* __restrict__ out_blk,
                                          long ld_out, int nrows) {
   if (PASS == GP_ROWMAX) {
@@ -129,7 +130,7 @@ __device__ __forceinline__ void gp_block(const uint32_t (&v)[32], const float* _
     float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
     for (int i4 = 0; i4 < 8; ++i4) {
-      const float4 fc = *reinterpret_cast<const float4*>(fcol + 4 * i4);   // warp-uniform address: broadcast
+      const float4 fc = lds_f4(fcol + 16 * i4);   // warp-uniform address: broadcast
       const float2 a = gp_value(make_float2(__uint_as_float(v[4 * i4]), __uint_as_float(v[4 * i4 + 1])), fr2,
                                 make_float2(fc.x, fc.y), mm, nrm);
       const float2 b = gp_value(make_float2(__uint_as_float(v[4 * i4 + 2]), __uint_as_float(v[4 * i4 + 3])), fr2,
@@ -145,15 +146,16 @@ __device__ __forceinline__ void gp_block(const uint32_t (&v)[32], const float* _
   __syncwarp();   // the previous block's reads of the buffer are complete
 #pragma unroll
   for (int i4 = 0; i4 < 8; ++i4) {
-    const float4 fc = *reinterpret_cast<const float4*>(fcol + 4 * i4);
-    const float4 fn = *reinterpret_cast<const float4*>(fnorm + 4 * i4);
+    const float4 fc = lds_f4(fcol + 16 * i4);
+    const float4 fn = lds_f4(fnorm + 16 * i4);
     float2 a = gp_value(make_float2(__uint_as_float(v[4 * i4]), __uint_as_float(v[4 * i4 + 1])), fr2,
                         make_float2(fc.x, fc.y), mm, nrm);
     float2 b = gp_value(make_float2(__uint_as_float(v[4 * i4 + 2]), __uint_as_float(v[4 * i4 + 3])), fr2,
                         make_float2(fc.z, fc.w), mm, nrm);
     a = __fmul2_rn(a, make_float2(fn.x, fn.y));
     b = __fmul2_rn(b, make_float2(fn.z, fn.w));
-    *reinterpret_cast<float4*>(stage + lane * 128 + ((i4 ^ (lane & 7)) << 4)) = make_float4(a.x, a.y, b.x, b.y);
+    sts_u4(stage + lane * 128 + ((i4 ^ (lane & 7)) << 4), __float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(b.x),
+           __float_as_uint(b.y));
   }
   __syncwarp();
   const int j = lane & 7, r0 = lane >> 3;
@@ -162,7 +164,7 @@ __device__ __forceinline__ void gp_block(const uint32_t (&v)[32], const float* _
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int r = it * 4 + r0;
-      st_cs_f4(p, *reinterpret_cast<const float4*>(stage + r * 128 + ((j ^ (r & 7)) << 4)));
+      st_cs_f4(p, lds_f4(stage + r * 128 + ((j ^ (r & 7)) << 4)));
       p += 4 * ld_out;
     }
   } else {
@@ -170,7 +172,7 @@ __device__ __forceinline__ void gp_block(const uint32_t (&v)[32], const float* _
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int r = it * 4 + r0;
-      if (col_ok && r < nrows) st_cs_f4(p, *reinterpret_cast<const float4*>(stage + r * 128 + ((j ^ (r & 7)) << 4)));
+      if (col_ok && r < nrows) st_cs_f4(p, lds_f4(stage + r * 128 + ((j ^ (r & 7)) << 4)));
       p += 4 * ld_out;
     }
   }
@@ -347,9 +349,9 @@ global_corr_persist_kernel(const __grid_constant__ CUtensorMap tm_a, const __gri
           __syncwarp();
           if (lane == 0) mbar_arrive(&sh->acc_empty[buf]);
         }
-        gp_block<PASS>(v0, fcol + ch * 64, fnorm + ch * 64, stage, lane, frow, mm, nrm, ncols - ch * 64, racc,
+        gp_block<PASS>(v0, smem_u32(fcol + ch * 64), smem_u32(fnorm + ch * 64), smem_u32(stage), lane, frow, mm, nrm, ncols - ch * 64, racc,
                        out_blk + ch * 64, NB, nrows);
-        gp_block<PASS>(v1, fcol + ch * 64 + 32, fnorm + ch * 64 + 32, stage, lane, frow, mm, nrm, ncols - ch * 64 - 32,
+        gp_block<PASS>(v1, smem_u32(fcol + ch * 64 + 32), smem_u32(fnorm + ch * 64 + 32), smem_u32(stage), lane, frow, mm, nrm, ncols - ch * 64 - 32,
                        racc, out_blk + ch * 64 + 32, NB, nrows);
       }
       const int pb = t.b;

@@ -132,19 +132,20 @@ local_corr_tc_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_const
         WS_T(31);
         if (it >= LT_STAGES) mbar_wait(&bars->empty[st], ((it / LT_STAGES) - 1) & 1);
         WS_T(32);
-        const uint8_t* rbuf = raw + rs * LT_RAW;
-        uint8_t* stage = smem + st * LT_STAGE;
+        // explicit shared-space accesses (plain dereferences of the manually aligned window compile to generic LD / ST)
+        const uint32_t rbuf = smem_u32(raw) + rs * LT_RAW;
+        const uint32_t stage = smem_u32(smem) + st * LT_STAGE;
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
           if (dst[i] != 0xffffffffu) {
-            const float4 v = *reinterpret_cast<const float4*>(rbuf + src[i]);
+            const float4 v = lds_f4(rbuf + src[i]);
             const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
             const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
             const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y);
             const __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
             const uint32_t lo_off = dst[i] < 2 * LT_A_BYTES ? LT_A_BYTES : LT_B_BYTES;   // [A hi][A lo][B hi][B lo]
-            *reinterpret_cast<uint2*>(stage + dst[i]) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
-            *reinterpret_cast<uint2*>(stage + dst[i] + lo_off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+            sts_u2(stage + dst[i], *reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+            sts_u2(stage + dst[i] + lo_off, *reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
           }
         }
         fence_proxy_async();          // generic-proxy writes -> visible to the tensor core's async-proxy reads
@@ -210,7 +211,7 @@ local_corr_tc_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_const
     // ------------------------------------------------------------------ band extraction (warp = tile row, lane = tile column)
     const int q = warp & 3;                        // TMEM lane quarter this warp may access = its tile row
     const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16);
-    float* brow = bounce + (q * 32 + lane) * LT_BOUNCE_PITCH;
+    const uint32_t brow = smem_u32(bounce) + (q * 32 + lane) * LT_BOUNCE_PITCH * 4;   // this lane's bounce row (shared address)
     int local = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++local) {
       const int b = t / (tiles_y * tiles_x), y0 = ((t / tiles_x) % tiles_y) * LT_TH, x0 = (t % tiles_x) * LT_TW;
@@ -227,16 +228,16 @@ local_corr_tc_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_const
       for (int dy = 0; dy < LT_P; ++dy) {
         tc_wait_ld();
 #pragma unroll
-        for (int c = 0; c < 32; c += 4) *reinterpret_cast<uint4*>(brow + c) = make_uint4(h0[c], h0[c + 1], h0[c + 2], h0[c + 3]);
-        *reinterpret_cast<uint4*>(brow + 32) = make_uint4(h1[0], h1[1], h1[2], h1[3]);
-        *reinterpret_cast<uint4*>(brow + 36) = make_uint4(h1[4], h1[5], h1[6], h1[7]);
+        for (int c = 0; c < 32; c += 4) sts_u4(brow + 4 * c, h0[c], h0[c + 1], h0[c + 2], h0[c + 3]);
+        sts_u4(brow + 128, h1[0], h1[1], h1[2], h1[3]);
+        sts_u4(brow + 144, h1[4], h1[5], h1[6], h1[7]);
         if (dy + 1 < LT_P) {
           tmem_ld32(tbase + (q + dy + 1) * LT_HW, h0);
           tmem_ld8(tbase + (q + dy + 1) * LT_HW + 32, h1);
         }
         __syncwarp();                               // (a lane only reads its own row: ordering within the thread suffices,
 #pragma unroll                                      //  the barrier keeps the compiler from reordering the shared accesses)
-        for (int dx = 0; dx < LT_P; ++dx) v[dy * LT_P + dx] = brow[lane + dx];
+        for (int dx = 0; dx < LT_P; ++dx) v[dy * LT_P + dx] = lds_f1(brow + 4 * (lane + dx));
         __syncwarp();
       }
       tc_fence_before();

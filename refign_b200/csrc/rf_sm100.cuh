@@ -291,6 +291,30 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
       : "memory");
 }
 
+// ---------------------------------------------------------------- explicit shared-space accesses
+// Pointers into the manually aligned dynamic shared-memory window lose their address-space provenance (the alignment
+// goes through an integer), so plain C++ dereferences compile to GENERIC LD.E / ST.E: they queue behind global traffic
+// (ncu: "lg" stalls) and cost a long-scoreboard round trip.  Hot paths use these on 32-bit shared addresses instead.
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ float lds_f1(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts_u4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void sts_u2(uint32_t saddr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(saddr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void sts_f1(uint32_t saddr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
+}
+
 // ---------------------------------------------------------------- CTA pairs (cta_group::2): one MMA spans two SMs
 // address of `local` (a shared::cta address of this CTA) in CTA `rank` of the cluster
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
