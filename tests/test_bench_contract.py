@@ -12,8 +12,12 @@ def _line(name):
         return json.loads(f.read().strip().splitlines()[-1])
 
 
-def test_final_bench_line_has_the_contract_keys():
-    d = _line("r01_bench_1024_t_final.json")
+import pytest
+
+
+@pytest.mark.parametrize("name", ["r01_bench_1024_t_final.json", "r02_bench_1024_g_final.json"])
+def test_final_bench_line_has_the_contract_keys(name):
+    d = _line(name)
     for k, t in (("metric", str), ("value", float), ("unit", str), ("n_gpus", int), ("steps", int), ("warmup", int),
                  ("ms_per_step", float), ("higher_is_better", bool), ("scaling", str), ("dtype", str), ("data", str),
                  ("config", dict), ("clocks", dict), ("e2e", dict), ("gpu_launches", int), ("roofline", dict),
@@ -34,11 +38,15 @@ def test_final_bench_line_has_the_contract_keys():
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
 
 
-def test_two_gpu_line_is_the_aggregate():
-    d1, d2 = _line("r01_bench_1024_t_final.json"), _line("r01_bench_1024_n2_t_final.json")
-    assert d2["n_gpus"] == 2 and d2["config"]["global_batch_pairs"] == 2 * d1["config"]["global_batch_pairs"]
+@pytest.mark.parametrize("names", [("r01_bench_1024_t_final.json", "r01_bench_1024_n2_t_final.json", 2),
+                                   ("r02_bench_1024_d_final.json", "r02_bench_1024_n2_final.json", 2),
+                                   ("r02_bench_1024_d_final.json", "r02_bench_1024_n8_final.json", 8)])
+def test_multi_gpu_line_is_the_aggregate(names):
+    d1, d2, n = _line(names[0]), _line(names[1]), names[2]
+    assert d2["n_gpus"] == n and d2["config"]["global_batch_pairs"] == n * d1["config"]["global_batch_pairs"]
     assert abs(d2["value"] - d2["config"]["global_batch_pairs"] / (d2["ms_per_step"] * 1e-3)) <= 1e-6 * d2["value"]
-    assert d2["value"] > 1.8 * d1["value"]     # weak scaling over NVLink: > 90 % at N = 2
+    assert d2["value"] > 0.9 * n * d1["value"]     # weak scaling over NVLink: > 90 %
+    assert d2["roofline"] is not None and d2["e2e"]["value"] > 0
 
 
 def test_multi_gpu_corr_sweep_collects_per_rank_files(monkeypatch):
