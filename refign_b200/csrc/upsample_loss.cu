@@ -11,6 +11,8 @@
 // registers: the forward reads the low-resolution logits (L2-resident) + labels and writes one scalar, the
 // backward is a gather per low-resolution pixel over the (2s)^2 full-resolution pixels that read it (their
 // softmax is recomputed; no atomics on the gradient).
+#include <stdlib.h>
+
 #include "rf_common.cuh"
 
 namespace rf {
@@ -204,6 +206,145 @@ upsample_ce_bwd_kernel(const float* __restrict__ low, const long long* __restric
     if (K > 0 || k < KK) o[(long)k * h * w] = acc[k] * g;
 }
 
+// Tiled form of the same gradient (round 2): the gather kernel above evaluates the softmax of every full-resolution pixel
+// once per low-resolution pixel that reads it -- four times.  Here one CTA owns an 8 x 64 tile of full-resolution pixels:
+//   1. every pixel's softmax is evaluated ONCE and  c_yx (softmax_k - [k == target])  goes to shared memory [k][y][x];
+//   2. the bilinear adjoint is separable: a reduction along x into the tile's low-resolution columns
+//      (R[k][y][j] = sum_x wx(x, j) C[k][y][x]; the x that touch column j form one contiguous run), then along y;
+//   3. the tile's partial sums are added to grad_low with red.global (a low-resolution pixel collects from at most four
+//      tiles), so grad_low must be zero on entry.
+// Needs the up-sampling factor to be >= 2 in both directions (the tile then covers <= 6 x 34 low-resolution pixels).
+constexpr int UT_TH = 8, UT_TW = 64, UT_LH = 6, UT_LW = 34;   // 60 KB of shared memory at K = 19: three CTAs per SM
+
+template <int K>
+__global__ void __launch_bounds__(256)
+upsample_ce_bwd_tile_kernel(const float* __restrict__ low, const long long* __restrict__ target,
+                            const float* __restrict__ weight, const float* __restrict__ grad_loss,
+                            float* __restrict__ grad_low, int B, int KK, int h, int w, int H, int W, int ignore_index,
+                            float inv_count) {
+  constexpr int KR = K > 0 ? K : UL_MAXK;
+  extern __shared__ float ut_smem[];
+  float* C = ut_smem;                                   // [KK][UT_TH][UT_TW]
+  float* R = C + (size_t)KK * UT_TH * UT_TW;            // [KK][UT_TH][UT_LW]
+  __shared__ int cx0[UT_TW], cx1[UT_TW], ry0[UT_TH], ry1[UT_TH];
+  __shared__ float clx[UT_TW], rly[UT_TH];
+  __shared__ int xs[UT_LW], xe[UT_LW], ys[UT_LH], ye[UT_LH];
+  const int tid = threadIdx.x;
+  const int tx0 = blockIdx.x * UT_TW, ty0 = blockIdx.y * UT_TH, b = blockIdx.z;
+  const float sy = (float)h / (float)H, sx = (float)w / (float)W;
+  // ---- taps of the tile's columns / rows (outside the image: weight 0 through an impossible cell index)
+  if (tid < UT_TW) {
+    const int x = tx0 + tid;
+    int a = -1, c = -1;
+    float l = 0.f;
+    if (x < W) ul_coord(x, w, sx, a, c, l);
+    cx0[tid] = a; cx1[tid] = c; clx[tid] = l;
+  } else if (tid < UT_TW + UT_TH) {
+    const int i = tid - UT_TW, y = ty0 + i;
+    int a = -1, c = -1;
+    float l = 0.f;
+    if (y < H) ul_coord(y, h, sy, a, c, l);
+    ry0[i] = a; ry1[i] = c; rly[i] = l;
+  }
+  __syncthreads();
+  const int pxa = cx0[0], pya = ry0[0];                 // first low-resolution column / row the tile touches
+  // the run of tile columns (rows) that touch low-resolution column j (row i); x0 / x1 are non-decreasing in x
+  if (tid < UT_LW) {
+    int lo = UT_TW, hi = 0;
+    for (int x = 0; x < UT_TW; ++x)
+      if (cx0[x] == pxa + tid || cx1[x] == pxa + tid) { lo = min(lo, x); hi = x + 1; }
+    xs[tid] = lo; xe[tid] = hi;
+  } else if (tid >= 64 && tid < 64 + UT_LH) {
+    const int i = tid - 64;
+    int lo = UT_TH, hi = 0;
+    for (int y = 0; y < UT_TH; ++y)
+      if (ry0[y] == pya + i || ry1[y] == pya + i) { lo = min(lo, y); hi = y + 1; }
+    ys[i] = lo; ye[i] = hi;
+  }
+  for (int i = tid; i < KK * UT_TH * UT_LW; i += 256) R[i] = 0.f;      // (visible after the barrier that follows step 1)
+  // ---- 1. one softmax per pixel -> C
+  const float* lowb = low + (long)b * KK * h * w;
+  for (int i = tid; i < UT_TH * UT_TW; i += 256) {
+    const int yy = i / UT_TW, xx = i % UT_TW;
+    const int y = ty0 + yy, x = tx0 + xx;
+    bool live = y < H && x < W;
+    long long t = 0;
+    long fi = 0;
+    if (live) {
+      fi = ((long)b * H + y) * W + x;
+      t = target[fi];
+      live = !(t == ignore_index || t < 0 || t >= KK);
+    }
+    if (live) {
+      float pr[KR];
+      ul_softmax<K>(lowb, KK, h, w, sy, sx, y, x, pr);
+      const float c = weight ? __ldg(weight + fi) : 1.f;
+#pragma unroll
+      for (int k = 0; k < KR; ++k)
+        if (K > 0 || k < KK) C[(k * UT_TH + yy) * UT_TW + xx] = c * (pr[k] - (k == (int)t ? 1.f : 0.f));
+    } else {
+      for (int k = 0; k < KK; ++k) C[(k * UT_TH + yy) * UT_TW + xx] = 0.f;
+    }
+  }
+  __syncthreads();
+  // ---- 2a. along x: one thread per (class, tile row) walks its 64 columns once.  The low-resolution column x0(x) is
+  // non-decreasing and advances by at most one per x (factor >= 2), x1 is x0 or x0 + 1: two running sums, flushed to R
+  // when x0 moves on -- no atomics, no searches.
+  const int ncol = min(UT_LW, w - pxa), nrow = min(UT_LH, h - pya);
+  // (four 16-column segments per row keep all 256 threads busy: with one thread per row 5 of the 8 warps walked 64
+  //  dependent shared-memory loads while the rest sat at the barrier -- 35 % of the stall samples; the cells at segment
+  //  borders are shared, so the flushes are shared-memory adds into the zeroed R)
+  for (int it = tid; it < KK * UT_TH * 4; it += 256) {
+    const int seg = it & 3, rid = it >> 2;
+    const float* row = C + rid * UT_TW;
+    float* rrow = R + rid * UT_LW;
+    int cur = cx0[seg * 16];
+    if (cur < 0) continue;                             // the whole segment is beyond the image
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll 4
+    for (int x = seg * 16; x < seg * 16 + 16; ++x) {
+      const int c0 = cx0[x];
+      if (c0 < 0) break;
+      if (c0 != cur) {
+        atomicAdd(&rrow[cur - pxa], a0);
+        a0 = a1;
+        a1 = 0.f;
+        cur = c0;
+      }
+      const float c = row[x], l = clx[x];
+      a0 = fmaf(1.f - l, c, a0);
+      if (cx1[x] == cur) a0 = fmaf(l, c, a0); else a1 = fmaf(l, c, a1);
+    }
+    atomicAdd(&rrow[cur - pxa], a0);
+    if (cur + 1 - pxa < UT_LW) atomicAdd(&rrow[cur + 1 - pxa], a1);
+  }
+  __syncthreads();
+  // ---- 2b. along y (same walk over the 8 tile rows, one thread per (class, low-resolution column)), 3. add to the gradient
+  const float g = __ldg(grad_loss) * inv_count;
+  for (int it = tid; it < KK * UT_LW; it += 256) {
+    const int j = it % UT_LW, k = it / UT_LW;
+    if (j >= ncol || xs[j] >= xe[j]) continue;         // this low-resolution column gets nothing from the tile
+    float* gcol = grad_low + ((long)b * KK + k) * h * w + pxa + j;
+    int cur = pya;
+    float a0 = 0.f, a1 = 0.f;
+    for (int yy = 0; yy < UT_TH; ++yy) {
+      const int r0 = ry0[yy];
+      if (r0 < 0) break;
+      if (r0 != cur) {
+        atomicAdd(gcol + (long)cur * w, a0 * g);
+        a0 = a1;
+        a1 = 0.f;
+        cur = r0;
+      }
+      const float c = R[(k * UT_TH + yy) * UT_LW + j], l = rly[yy];
+      a0 = fmaf(1.f - l, c, a0);
+      if (ry1[yy] == cur) a0 = fmaf(l, c, a0); else a1 = fmaf(l, c, a1);
+    }
+    atomicAdd(gcol + (long)cur * w, a0 * g);
+    if (cur + 1 < h && cur + 1 - pya < nrow) atomicAdd(gcol + (long)(cur + 1) * w, a1 * g);
+  }
+}
+
 // plain bilinear up-sampling of an fp32 NCHW tensor (align_corners = false): one thread per 4 consecutive x and
 // FOUR output rows; 3-D grid (x, row group, plane) -- the flat 1-D form spent 344 instructions per thread on 64-bit
 // index divisions (issue slots 87 % busy at 23 % of the HBM roof); here the x taps are computed once for four rows.
@@ -271,6 +412,28 @@ extern "C" int rf_upsample_ce_bwd(const float* logits, const int64_t* target, co
   RF_REQUIRE(blocks < (1l << 31), "rf_upsample_ce_bwd: tensor too large");
   const float inv_count = 1.0f / (float)((double)B * H * W);
   cudaStream_t st = (cudaStream_t)stream;
+  // tiled scatter form (one softmax per full-resolution pixel) for up-sampling factors >= 2; RF_UPSAMPLE_CE_BWD=gather
+  // keeps the gather kernel (A/B switch)
+  static const bool tiled_on = [] { const char* e = getenv("RF_UPSAMPLE_CE_BWD"); return !(e && e[0] == 'g'); }();
+  const size_t tile_smem = sizeof(float) * (size_t)K * UT_TH * (UT_TW + UT_LW);
+  if (tiled_on && H >= 2 * h && W >= 2 * w && tile_smem <= 200 * 1024 && B <= 65535 && (H + UT_TH - 1) / UT_TH <= 65535) {
+    static bool attr = false;
+    if (!attr) {
+      RF_CUDA(cudaFuncSetAttribute(upsample_ce_bwd_tile_kernel<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      RF_CUDA(cudaFuncSetAttribute(upsample_ce_bwd_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr = true;
+    }
+    RF_CUDA(cudaMemsetAsync(grad_logits, 0, sizeof(float) * (size_t)B * K * h * w, st));
+    dim3 grid((unsigned)((W + UT_TW - 1) / UT_TW), (unsigned)((H + UT_TH - 1) / UT_TH), (unsigned)B);
+    if (K == 19)
+      upsample_ce_bwd_tile_kernel<19><<<grid, 256, tile_smem, st>>>(logits, (const long long*)target, pixel_weight, grad_loss,
+                                                                   grad_logits, B, K, h, w, H, W, ignore_index, inv_count);
+    else
+      upsample_ce_bwd_tile_kernel<0><<<grid, 256, tile_smem, st>>>(logits, (const long long*)target, pixel_weight, grad_loss,
+                                                                  grad_logits, B, K, h, w, H, W, ignore_index, inv_count);
+    RF_CHECK_LAUNCH("upsample_ce_bwd_tile_kernel");
+    return RF_OK;
+  }
   if (K == 19)
     upsample_ce_bwd_kernel<19><<<(unsigned)blocks, 128, 0, st>>>(logits, (const long long*)target, pixel_weight, grad_loss,
                                                                  grad_logits, B, K, h, w, H, W, ignore_index, inv_count);
