@@ -15,7 +15,7 @@ def _line(name):
 import pytest
 
 
-@pytest.mark.parametrize("name", ["r01_bench_1024_t_final.json", "r02_bench_1024_g_final.json"])
+@pytest.mark.parametrize("name", ["r01_bench_1024_t_final.json", "r02_bench_1024_g_final.json", "r02_bench_1024_i_final_default_run.json"])
 def test_final_bench_line_has_the_contract_keys(name):
     d = _line(name)
     for k, t in (("metric", str), ("value", float), ("unit", str), ("n_gpus", int), ("steps", int), ("warmup", int),
